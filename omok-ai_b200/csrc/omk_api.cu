@@ -1,0 +1,757 @@
+// omk_api.cu -- extern "C" boundary of libomok_b200.so (see include/omok_b200.h).
+// Host-side orchestration only: pool allocation, argument staging, kernel sequencing.
+// There is no CPU compute path: every operation is a CUDA kernel on the context's stream.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "omk_internal.h"
+
+using namespace omk;
+
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(OMK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+#define CKV(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) g_err = std::string(#call) + ": " + cudaGetErrorString(e__);            \
+    } while (0)
+
+static const long long kLens[kNetTensors] = {
+    384, 128,
+    4096, 32, 288, 1024, 32, 4096, 128,
+    4096, 32, 288, 1024, 32, 4096, 128,
+    4096, 32, 288, 1024, 32, 4096, 128,
+    10368LL * 512, 512, 512 * 512, 512, 512, 1, 512 * 81, 81};
+
+extern "C" const char *omk_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t omk_version(void) { return 100; }
+
+// ------------------------------------------------------------------ workspace
+static int32_t ensure_workspace(omk_ctx *c, int rows) {
+    rows = (rows + 127) / 128 * 128;
+    if (rows <= c->ws.max_rows) return OMK_OK;
+    CK(cudaStreamSynchronize(c->stream));
+    Workspace &w = c->ws;
+    cudaFree(w.nn_in); cudaFree(w.req_tree); cudaFree(w.req_node); cudaFree(w.P); cudaFree(w.V);
+    cudaFree(w.act0); cudaFree(w.act1); cudaFree(w.act2); cudaFree(w.logits);
+    w.max_rows = 0;
+    CK(cudaMalloc(&w.nn_in, sizeof(NNIn) * (size_t)rows));
+    CK(cudaMalloc(&w.req_tree, sizeof(uint32_t) * (size_t)rows));
+    CK(cudaMalloc(&w.req_node, sizeof(uint32_t) * (size_t)rows));
+    CK(cudaMalloc(&w.P, sizeof(float) * (size_t)rows * kRow));
+    CK(cudaMalloc(&w.V, sizeof(float) * (size_t)rows));
+    CK(cudaMalloc(&w.act0, sizeof(float) * (size_t)rows * 10368));
+    CK(cudaMalloc(&w.act1, sizeof(float) * (size_t)rows * 512));
+    CK(cudaMalloc(&w.act2, sizeof(float) * (size_t)rows * 512));
+    CK(cudaMalloc(&w.logits, sizeof(float) * (size_t)rows * 128));
+    CK(cudaMemsetAsync(w.act0, 0, sizeof(float) * (size_t)rows * 10368, c->stream));
+    CK(cudaMemsetAsync(w.nn_in, 0, sizeof(NNIn) * (size_t)rows, c->stream));
+    w.max_rows = rows;
+    return OMK_OK;
+}
+
+static int32_t check_device_error(omk_ctx *c) {
+    uint32_t e = 0;
+    CK(cudaMemcpyAsync(&e, c->dev_error, sizeof e, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    if (e & 1u) {
+        uint32_t z = 0;
+        cudaMemcpyAsync(c->dev_error, &z, sizeof z, cudaMemcpyHostToDevice, c->stream);
+        return fail(OMK_ERR_CAPACITY, "a tree ran out of node slots (capacity_nodes=" + std::to_string(c->cap_nodes) + ")");
+    }
+    return OMK_OK;
+}
+
+// stage a host id list (or the identity) on the device; returns nullptr for identity
+static int32_t stage_ids(omk_ctx *c, const int32_t *ids, int n, const int32_t **out, int limit) {
+    *out = nullptr;
+    if (n < 0 || n > limit) return fail(OMK_ERR_INVALID, "n out of range for the pool capacity");
+    if (!ids) return OMK_OK;
+    for (int i = 0; i < n; ++i)
+        if (ids[i] < 0 || ids[i] >= limit) return fail(OMK_ERR_INVALID, "id out of range");
+    CK(cudaMemcpyAsync(c->ws.ids, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    *out = c->ws.ids;
+    return OMK_OK;
+}
+
+static void run_evaluator(omk_ctx *c, int evaluator, int rows_bound) {
+    if (evaluator == OMK_EVAL_HASH)
+        launch_eval_hash(c, rows_bound);
+    else
+        net_forward(c, nullptr, rows_bound);
+}
+
+static int32_t check_evaluator(omk_ctx *c, int evaluator) {
+    if (evaluator != OMK_EVAL_NET && evaluator != OMK_EVAL_HASH) return fail(OMK_ERR_INVALID, "unknown evaluator");
+    if (evaluator == OMK_EVAL_NET && !c->net.loaded) return fail(OMK_ERR_STATE, "network weights not loaded");
+    return OMK_OK;
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int32_t omk_ctx_create(int32_t device, int32_t capacity_envs, int32_t capacity_trees, int32_t capacity_nodes,
+                                  uint64_t seed, omk_ctx **out) {
+    if (!out) return fail(OMK_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (capacity_envs < 0 || capacity_trees < 0 || capacity_nodes < 2 || capacity_nodes > 65535)
+        return fail(OMK_ERR_INVALID, "bad capacity (capacity_nodes must be in [2, 65535])");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(OMK_ERR_CUDA, "no CUDA device: libomok_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(OMK_ERR_INVALID, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(OMK_ERR_CUDA, "libomok_b200 is built for sm_100a (B200) only");
+
+    omk_ctx *c = new omk_ctx();
+    c->device = device;
+    c->n_sms = prop.multiProcessorCount;
+    c->cap_envs = capacity_envs;
+    c->cap_trees = capacity_trees;
+    c->cap_nodes = capacity_nodes;
+    c->seed = seed;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    const int ce = capacity_envs > 0 ? capacity_envs : 1, ct = capacity_trees > 0 ? capacity_trees : 1;
+    CK(cudaMalloc(&c->envs, sizeof(EnvRec) * (size_t)ce));
+    CK(cudaMalloc(&c->tree_hdrs, sizeof(TreeHdr) * (size_t)ct));
+    CK(cudaMalloc(&c->tree_nodes, (size_t)ct * (size_t)capacity_nodes * kNodeBytes));
+    CK(cudaMalloc(&c->remap, sizeof(uint16_t) * (size_t)ct * (size_t)capacity_nodes));
+    CK(cudaMalloc(&c->dev_error, sizeof(uint32_t)));
+    CK(cudaMalloc(&c->dev_sims, sizeof(unsigned long long) * 2));
+    CK(cudaMemsetAsync(c->dev_error, 0, sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(c->dev_sims, 0, sizeof(unsigned long long) * 2, c->stream));
+    CK(cudaMemsetAsync(c->tree_hdrs, 0, sizeof(TreeHdr) * (size_t)ct, c->stream));
+    CK(cudaMemsetAsync(c->envs, 0, sizeof(EnvRec) * (size_t)ce, c->stream));
+    Workspace &w = c->ws;
+    const int cm = ce > ct ? ce : ct;
+    CK(cudaMalloc(&w.n_req, sizeof(uint32_t) * 4));
+    CK(cudaMemsetAsync(w.n_req, 0, sizeof(uint32_t) * 4, c->stream));
+    CK(cudaMalloc(&w.slot_base, sizeof(uint32_t) * (size_t)ct));
+    CK(cudaMalloc(&w.slot_count, sizeof(uint32_t) * (size_t)ct));
+    CK(cudaMalloc(&w.ids, sizeof(int32_t) * (size_t)cm));
+    CK(cudaMalloc(&w.actions, sizeof(int32_t) * (size_t)cm));
+    CK(cudaMalloc(&w.modes, (size_t)cm));
+    CK(cudaMalloc(&w.temps, sizeof(float) * (size_t)cm));
+    CK(cudaMalloc(&w.status, (size_t)cm));
+    CK(cudaMalloc(&w.policy_out, sizeof(float) * (size_t)ct * kCells));
+    CK(cudaMalloc(&w.streams, sizeof(uint32_t) * (size_t)ct));
+    for (int i = 0; i < kNetTensors; ++i) CK(cudaMalloc(&c->net.t[i], sizeof(float) * (size_t)kLens[i]));
+    CK(cudaMalloc(&c->net.heads_w, sizeof(float) * 512 * 128));
+    CK(cudaMalloc(&c->net.heads_b, sizeof(float) * 128));
+    CK(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
+    if (!c) return OMK_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    Workspace &w = c->ws;
+    void *ptrs[] = {c->envs, c->tree_hdrs, c->tree_nodes, c->remap, c->dev_error, c->dev_sims, w.nn_in, w.req_tree,
+                    w.req_node, w.P, w.V, w.act0, w.act1, w.act2, w.logits, w.n_req, w.slot_base, w.slot_count, w.ids,
+                    w.actions, w.modes, w.temps, w.status, w.policy_out, w.streams, c->net.heads_w, c->net.heads_b,
+                    c->sp_ply, c->sp_buf};
+    for (void *p : ptrs) cudaFree(p);
+    for (int i = 0; i < kNetTensors; ++i) cudaFree(c->net.t[i]);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_ctx_synchronize(omk_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return OMK_OK;
+}
+extern "C" void *omk_ctx_stream(omk_ctx *c) { return (void *)c->stream; }
+extern "C" int64_t omk_ctx_launch_count(omk_ctx *c) { return c->launches; }
+
+// ------------------------------------------------------------------ network
+extern "C" int32_t omk_net_load_params(omk_ctx *c, const float *const *tensors, const int64_t *lens) {
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < kNetTensors; ++i)
+        if (!tensors[i] || lens[i] != kLens[i])
+            return fail(OMK_ERR_INVALID, "tensor " + std::to_string(i) + ": expected " + std::to_string(kLens[i]) + " elements");
+    for (int i = 0; i < kNetTensors; ++i)
+        CK(cudaMemcpyAsync(c->net.t[i], tensors[i], sizeof(float) * (size_t)kLens[i], cudaMemcpyHostToDevice, c->stream));
+    net_pack_heads(c);
+    CK(cudaStreamSynchronize(c->stream));
+    c->net.loaded = true;
+    return OMK_OK;
+}
+extern "C" int32_t omk_net_get_params(omk_ctx *c, float *const *tensors, const int64_t *lens) {
+    CK(cudaSetDevice(c->device));
+    if (!c->net.loaded) return fail(OMK_ERR_STATE, "network weights not loaded");
+    for (int i = 0; i < kNetTensors; ++i)
+        if (!tensors[i] || lens[i] != kLens[i]) return fail(OMK_ERR_INVALID, "bad tensor length");
+    for (int i = 0; i < kNetTensors; ++i)
+        CK(cudaMemcpyAsync(tensors[i], c->net.t[i], sizeof(float) * (size_t)kLens[i], cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OMK_OK;
+}
+extern "C" int32_t omk_net_init_random(omk_ctx *c, uint64_t seed) {
+    CK(cudaSetDevice(c->device));
+    launch_net_init_random(c, seed);
+    net_pack_heads(c);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    c->net.loaded = true;
+    return OMK_OK;
+}
+
+static int32_t net_eval_common(omk_ctx *c, int n, const float *images_dev, float *out_p, float *out_v) {
+    net_forward(c, images_dev, n);
+    // P rows are padded to 96 floats on the device; compact on the way out
+    CK(cudaMemcpy2DAsync(out_p, sizeof(float) * kCells, c->ws.P, sizeof(float) * kRow, sizeof(float) * kCells, (size_t)n,
+                         cudaMemcpyDeviceToHost, c->stream));
+    if (out_v) CK(cudaMemcpyAsync(out_v, c->ws.V, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_net_eval(omk_ctx *c, const uint8_t *boards, const uint8_t *turns, int32_t n, int32_t mode,
+                                float *out_p, float *out_v) {
+    CK(cudaSetDevice(c->device));
+    if (!c->net.loaded) return fail(OMK_ERR_STATE, "network weights not loaded");
+    if (n < 0 || !boards || !turns || !out_p) return fail(OMK_ERR_INVALID, "bad arguments");
+    if (n == 0) return OMK_OK;
+    int32_t rc = ensure_workspace(c, n);
+    if (rc) return rc;
+    uint8_t *d_boards = nullptr, *d_turns = nullptr;
+    CK(cudaMalloc(&d_boards, (size_t)n * kCells));
+    CK(cudaMalloc(&d_turns, (size_t)n));
+    CK(cudaMemcpyAsync(d_boards, boards, (size_t)n * kCells, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_turns, turns, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    launch_pack_boards(c, d_boards, d_turns, n, mode);
+    rc = net_eval_common(c, n, nullptr, out_p, out_v);
+    cudaFree(d_boards);
+    cudaFree(d_turns);
+    return rc;
+}
+
+extern "C" int32_t omk_net_eval_images(omk_ctx *c, const float *images, int32_t n, float *out_p, float *out_v) {
+    CK(cudaSetDevice(c->device));
+    if (!c->net.loaded) return fail(OMK_ERR_STATE, "network weights not loaded");
+    if (n < 0 || !images || !out_p) return fail(OMK_ERR_INVALID, "bad arguments");
+    if (n == 0) return OMK_OK;
+    int32_t rc = ensure_workspace(c, n);
+    if (rc) return rc;
+    float *d_img = nullptr;
+    CK(cudaMalloc(&d_img, sizeof(float) * (size_t)n * 243));
+    CK(cudaMemcpyAsync(d_img, images, sizeof(float) * (size_t)n * 243, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t nn = (uint32_t)n;
+    CK(cudaMemcpyAsync(c->ws.n_req, &nn, sizeof nn, cudaMemcpyHostToDevice, c->stream));
+    rc = net_eval_common(c, n, d_img, out_p, out_v);
+    cudaFree(d_img);
+    return rc;
+}
+
+// ------------------------------------------------------------------ environment
+extern "C" int32_t omk_env_reset(omk_ctx *c, const int32_t *ids, int32_t n) {
+    CK(cudaSetDevice(c->device));
+    const int32_t *d_ids;
+    int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_envs);
+    if (rc) return rc;
+    launch_env_reset(c, d_ids, n);
+    CK(cudaStreamSynchronize(c->stream));
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_env_step(omk_ctx *c, const int32_t *ids, const uint8_t *actions, int32_t n, int8_t *out_status,
+                                uint32_t *out_legal) {
+    CK(cudaSetDevice(c->device));
+    if (!actions) return fail(OMK_ERR_INVALID, "actions is NULL");
+    const int32_t *d_ids;
+    int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_envs);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    uint8_t *d_act = nullptr;
+    int8_t *d_st = nullptr;
+    uint32_t *d_legal = nullptr;
+    CK(cudaMalloc(&d_act, (size_t)n));
+    CK(cudaMalloc(&d_st, (size_t)n));
+    if (out_legal) CK(cudaMalloc(&d_legal, sizeof(uint32_t) * 3 * (size_t)n));
+    CK(cudaMemcpyAsync(d_act, actions, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    launch_env_step(c, d_ids, d_act, n, d_st, d_legal);
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_st, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_legal) CK(cudaMemcpyAsync(out_legal, d_legal, sizeof(uint32_t) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    cudaFree(d_act); cudaFree(d_st); cudaFree(d_legal);
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_env_step_device(omk_ctx *c, const uint8_t *actions_device, int32_t n, int8_t *out_status_device,
+                                       uint32_t *out_legal_device) {
+    if (n < 0 || n > c->cap_envs) return fail(OMK_ERR_INVALID, "n exceeds capacity_envs");
+    launch_env_step(c, nullptr, actions_device, n, out_status_device, out_legal_device);
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_env_get(omk_ctx *c, const int32_t *ids, int32_t n, uint8_t *out_boards, uint8_t *out_turns,
+                               uint16_t *out_legal_counts) {
+    CK(cudaSetDevice(c->device));
+    const int32_t *d_ids;
+    int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_envs);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    uint8_t *d_b = nullptr, *d_t = nullptr;
+    uint16_t *d_l = nullptr;
+    CK(cudaMalloc(&d_b, (size_t)n * kCells));
+    CK(cudaMalloc(&d_t, (size_t)n));
+    CK(cudaMalloc(&d_l, sizeof(uint16_t) * (size_t)n));
+    launch_env_get(c, d_ids, n, d_b, d_t, d_l);
+    if (out_boards) CK(cudaMemcpyAsync(out_boards, d_b, (size_t)n * kCells, cudaMemcpyDeviceToHost, c->stream));
+    if (out_turns) CK(cudaMemcpyAsync(out_turns, d_t, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_legal_counts) CK(cudaMemcpyAsync(out_legal_counts, d_l, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_b); cudaFree(d_t); cudaFree(d_l);
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_env_set(omk_ctx *c, const int32_t *ids, int32_t n, const uint8_t *boards, const uint8_t *turns) {
+    CK(cudaSetDevice(c->device));
+    if (!boards || !turns) return fail(OMK_ERR_INVALID, "NULL argument");
+    const int32_t *d_ids;
+    int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_envs);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    uint8_t *d_b = nullptr, *d_t = nullptr;
+    CK(cudaMalloc(&d_b, (size_t)n * kCells));
+    CK(cudaMalloc(&d_t, (size_t)n));
+    CK(cudaMemcpyAsync(d_b, boards, (size_t)n * kCells, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_t, turns, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    launch_env_set(c, d_ids, n, d_b, d_t);
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_b); cudaFree(d_t);
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_env_encode(omk_ctx *c, const int32_t *ids, int32_t n, int32_t mode, float *out) {
+    CK(cudaSetDevice(c->device));
+    if (!out) return fail(OMK_ERR_INVALID, "out is NULL");
+    const int32_t *d_ids;
+    int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_envs);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    float *d_o = nullptr;
+    CK(cudaMalloc(&d_o, sizeof(float) * 243 * (size_t)n));
+    launch_env_encode(c, d_ids, n, mode, d_o);
+    CK(cudaMemcpyAsync(out, d_o, sizeof(float) * 243 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_o);
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_env_random_playout(omk_ctx *c, int32_t n, int32_t plies, uint8_t *out_actions, int8_t *out_status) {
+    CK(cudaSetDevice(c->device));
+    if (n < 0 || n > c->cap_envs || plies < 0) return fail(OMK_ERR_INVALID, "bad arguments");
+    if (n == 0 || plies == 0) return OMK_OK;
+    uint8_t *d_a = nullptr;
+    int8_t *d_s = nullptr;
+    const size_t tot = (size_t)n * (size_t)plies;
+    if (out_actions) CK(cudaMalloc(&d_a, tot));
+    if (out_status) CK(cudaMalloc(&d_s, tot));
+    launch_env_playout(c, n, plies, d_a, d_s);
+    if (out_actions) CK(cudaMemcpyAsync(out_actions, d_a, tot, cudaMemcpyDeviceToHost, c->stream));
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_s, tot, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    cudaFree(d_a); cudaFree(d_s);
+    return OMK_OK;
+}
+
+// ------------------------------------------------------------------ tree pool
+extern "C" int32_t omk_pool_new_games(omk_ctx *c, const int32_t *ids, int32_t n, const uint32_t *streams, int32_t evaluator) {
+    CK(cudaSetDevice(c->device));
+    int32_t rc = check_evaluator(c, evaluator);
+    if (rc) return rc;
+    const int32_t *d_ids;
+    rc = stage_ids(c, ids, n, &d_ids, c->cap_trees);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    rc = ensure_workspace(c, n);
+    if (rc) return rc;
+    const uint32_t *d_streams = nullptr;
+    if (streams) {
+        CK(cudaMemcpyAsync(c->ws.streams, streams, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        d_streams = c->ws.streams;
+    }
+    launch_reset_requests(c);
+    launch_new_games(c, d_ids, n, d_streams, nullptr, nullptr);
+    run_evaluator(c, evaluator, n);
+    launch_apply(c, d_ids, n, kApplyNewGame);
+    return check_device_error(c);
+}
+
+extern "C" int32_t omk_pool_search(omk_ctx *c, const int32_t *ids, int32_t n, int32_t count, int32_t batch_size, float epsilon,
+                                   float alpha, int32_t evaluator) {
+    CK(cudaSetDevice(c->device));
+    int32_t rc = check_evaluator(c, evaluator);
+    if (rc) return rc;
+    if (batch_size < 1 || batch_size > kMaxBatchPerTree) return fail(OMK_ERR_INVALID, "batch_size must be in [1, 64]");
+    if (count < 0) return fail(OMK_ERR_INVALID, "count < 0");
+    const int32_t *d_ids;
+    rc = stage_ids(c, ids, n, &d_ids, c->cap_trees);
+    if (rc) return rc;
+    if (n == 0 || count == 0) return OMK_OK;
+    const int rows = n * batch_size;
+    rc = ensure_workspace(c, rows);
+    if (rc) return rc;
+    const int rounds = (count + batch_size - 1) / batch_size;  // parallel_mcts_executor.rs:39-42,207
+    for (int r = 0; r < rounds; ++r) {
+        if (r == 0) launch_root_noise(c, d_ids, n, epsilon, alpha);
+        launch_reset_requests(c);
+        launch_select_expand(c, d_ids, n, batch_size);
+        run_evaluator(c, evaluator, rows);
+        launch_apply(c, d_ids, n, kApplySearch);
+    }
+    return check_device_error(c);
+}
+
+extern "C" int32_t omk_pool_sample(omk_ctx *c, const int32_t *ids, int32_t n, const uint8_t *modes, const float *temperatures,
+                                   int32_t *out_actions, float *out_policy) {
+    CK(cudaSetDevice(c->device));
+    const int32_t *d_ids;
+    int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_trees);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    const uint8_t *d_modes = nullptr;
+    const float *d_temps = nullptr;
+    if (modes) {
+        bool any_boltz = false;
+        for (int i = 0; i < n; ++i) any_boltz |= modes[i] == OMK_SAMPLE_BOLTZMANN;
+        if (any_boltz && !temperatures) return fail(OMK_ERR_INVALID, "Boltzmann sampling needs temperatures");
+        CK(cudaMemcpyAsync(c->ws.modes, modes, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        d_modes = c->ws.modes;
+        if (temperatures) {
+            CK(cudaMemcpyAsync(c->ws.temps, temperatures, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+            d_temps = c->ws.temps;
+        }
+    }
+    launch_sample(c, d_ids, n, d_modes, d_temps, c->ws.actions, c->ws.policy_out, nullptr);
+    if (out_actions) CK(cudaMemcpyAsync(out_actions, c->ws.actions, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_policy) CK(cudaMemcpyAsync(out_policy, c->ws.policy_out, sizeof(float) * kCells * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_pool_policy(omk_ctx *c, const int32_t *ids, int32_t n, float *out_policy, uint8_t *out_valid) {
+    CK(cudaSetDevice(c->device));
+    const int32_t *d_ids;
+    int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_trees);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    launch_sample(c, d_ids, n, nullptr, nullptr, nullptr, c->ws.policy_out, c->ws.modes);
+    if (out_policy) CK(cudaMemcpyAsync(out_policy, c->ws.policy_out, sizeof(float) * kCells * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_valid) CK(cudaMemcpyAsync(out_valid, c->ws.modes, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_pool_ensure_action(omk_ctx *c, const int32_t *ids, const int32_t *actions, int32_t n, int32_t evaluator) {
+    CK(cudaSetDevice(c->device));
+    int32_t rc = check_evaluator(c, evaluator);
+    if (rc) return rc;
+    if (!actions) return fail(OMK_ERR_INVALID, "actions is NULL");
+    const int32_t *d_ids;
+    rc = stage_ids(c, ids, n, &d_ids, c->cap_trees);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    rc = ensure_workspace(c, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->ws.actions, actions, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    launch_reset_requests(c);
+    launch_ensure_prepare(c, d_ids, c->ws.actions, n);
+    run_evaluator(c, evaluator, n);
+    launch_apply(c, d_ids, n, kApplyEnsure);
+    return check_device_error(c);
+}
+
+extern "C" int32_t omk_pool_play(omk_ctx *c, const int32_t *ids, const int32_t *actions, int32_t n, int8_t *out_status) {
+    CK(cudaSetDevice(c->device));
+    if (!actions) return fail(OMK_ERR_INVALID, "actions is NULL");
+    const int32_t *d_ids;
+    int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_trees);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    CK(cudaMemcpyAsync(c->ws.actions, actions, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    launch_play(c, d_ids, c->ws.actions, n, c->ws.status);
+    if (out_status) CK(cudaMemcpyAsync(out_status, c->ws.status, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return OMK_OK;
+}
+
+struct RootDump {
+    int32_t actions[kCells];
+    unsigned long long n[kCells];
+    float w[kCells], p[kCells];
+    int32_t len;
+    float policy[kCells];
+    uint32_t misc[16];
+};
+
+static int32_t dump_root(omk_ctx *c, int32_t id, RootDump *host) {
+    CK(cudaSetDevice(c->device));
+    if (id < 0 || id >= c->cap_trees) return fail(OMK_ERR_INVALID, "tree id out of range");
+    RootDump *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(RootDump)));
+    launch_root_children(c, id, d->actions, d->n, d->w, d->p, &d->len, d->policy, d->misc);
+    CK(cudaMemcpyAsync(host, d, sizeof(RootDump), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    cudaFree(d);
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_pool_root_children(omk_ctx *c, int32_t id, int32_t *out_actions, uint64_t *out_n, float *out_w,
+                                          float *out_p, int32_t *out_len) {
+    RootDump h;
+    int32_t rc = dump_root(c, id, &h);
+    if (rc) return rc;
+    for (int i = 0; i < h.len; ++i) {
+        if (out_actions) out_actions[i] = h.actions[i];
+        if (out_n) out_n[i] = h.n[i];
+        if (out_w) out_w[i] = h.w[i];
+        if (out_p) out_p[i] = h.p[i];
+    }
+    if (out_len) *out_len = h.len;
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_pool_root_stats(omk_ctx *c, int32_t id, uint64_t *out_n, float *out_w, float *out_p, int32_t *out_status,
+                                       float *out_policy) {
+    RootDump h;
+    int32_t rc = dump_root(c, id, &h);
+    if (rc) return rc;
+    if (out_n) *out_n = h.misc[0];
+    if (out_w) memcpy(out_w, &h.misc[1], 4);
+    if (out_p) memcpy(out_p, &h.misc[2], 4);
+    if (out_status) *out_status = (int32_t)h.misc[3];
+    if (out_policy) memcpy(out_policy, h.policy, sizeof h.policy);
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_pool_tree_info(omk_ctx *c, int32_t id, int32_t *out_nodes, uint32_t *out_rng_counter) {
+    RootDump h;
+    int32_t rc = dump_root(c, id, &h);
+    if (rc) return rc;
+    if (out_nodes) *out_nodes = (int32_t)h.misc[4];
+    if (out_rng_counter) *out_rng_counter = h.misc[5];
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_pool_get_env(omk_ctx *c, int32_t id, uint8_t *out_board, uint8_t *out_turn, uint16_t *out_legal_count) {
+    RootDump h;
+    int32_t rc = dump_root(c, id, &h);
+    if (rc) return rc;
+    if (out_board)
+        for (int i = 0; i < kCells; ++i) {
+            const bool b = (h.misc[8 + (i >> 5)] >> (i & 31)) & 1u, w = (h.misc[11 + (i >> 5)] >> (i & 31)) & 1u;
+            out_board[i] = b ? 1 : (w ? 2 : 0);
+        }
+    if (out_turn) *out_turn = (uint8_t)(h.misc[6] & 0xFF);
+    if (out_legal_count) *out_legal_count = (uint16_t)((h.misc[6] >> 8) & 0xFF);
+    return OMK_OK;
+}
+
+// ------------------------------------------------------------------ self-play driver
+struct SpLayout {
+    int32_t *mover, *other, *actions;
+    float *temps;
+    uint8_t *modes;
+    int8_t *status, *status2;
+    float *root_policy;
+    unsigned long long *counters;  // [0] games finished
+    size_t bytes;
+};
+static SpLayout sp_layout(omk_ctx *c, int n) {
+    SpLayout L;
+    uint8_t *base = reinterpret_cast<uint8_t *>(c->sp_buf);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { uint8_t *p = base + off; off = (off + bytes + 255) & ~(size_t)255; return p; };
+    L.mover = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)n));
+    L.other = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)n));
+    L.actions = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)n));
+    L.temps = reinterpret_cast<float *>(take(sizeof(float) * (size_t)n));
+    L.modes = take((size_t)n);
+    L.status = reinterpret_cast<int8_t *>(take((size_t)n));
+    L.status2 = reinterpret_cast<int8_t *>(take((size_t)n));
+    L.root_policy = reinterpret_cast<float *>(take(sizeof(float) * kRow));
+    L.counters = reinterpret_cast<unsigned long long *>(take(64));
+    L.bytes = off;
+    return L;
+}
+extern "C" int32_t omk_selfplay_begin(omk_ctx *c, const omk_selfplay_config *cfg) {
+    CK(cudaSetDevice(c->device));
+    if (!cfg) return fail(OMK_ERR_INVALID, "cfg is NULL");
+    if (cfg->n_games < 1 || 2 * cfg->n_games > c->cap_trees) return fail(OMK_ERR_INVALID, "need capacity_trees >= 2*n_games");
+    if (cfg->batch_size < 1 || cfg->batch_size > kMaxBatchPerTree || cfg->count < 1) return fail(OMK_ERR_INVALID, "bad count/batch_size");
+    int32_t rc = check_evaluator(c, cfg->evaluator);
+    if (rc) return rc;
+    const int n = cfg->n_games;
+    const int rows = n * cfg->batch_size > 2 * n ? n * cfg->batch_size : 2 * n;
+    rc = ensure_workspace(c, rows);
+    if (rc) return rc;
+    c->sp_cfg = *cfg;
+    cudaFree(c->sp_ply);
+    cudaFree(c->sp_buf);
+    c->sp_ply = nullptr;
+    c->sp_buf = nullptr;
+    CK(cudaMalloc(&c->sp_ply, sizeof(int32_t) * (size_t)n));
+    CK(cudaMemsetAsync(c->sp_ply, 0, sizeof(int32_t) * (size_t)n, c->stream));
+    const SpLayout L = sp_layout(c, n);
+    CK(cudaMalloc(&c->sp_buf, L.bytes));
+    CK(cudaMemsetAsync(c->sp_buf, 0, L.bytes, c->stream));
+    const SpLayout M = sp_layout(c, n);
+    // Agent::new for all 2n trees (stream id = tree id); then cache the root's raw policy for restarts:
+    // evaluating the empty board is deterministic, so reusing it is bit-identical to evaluating it again
+    launch_reset_requests(c);
+    launch_new_games(c, nullptr, 2 * n, nullptr, nullptr, nullptr);
+    run_evaluator(c, cfg->evaluator, 2 * n);
+    launch_apply(c, nullptr, 2 * n, kApplyNewGame);
+    CK(cudaMemcpyAsync(M.root_policy, c->tree_nodes + kOffPolicy, sizeof(float) * kCells, cudaMemcpyDeviceToDevice, c->stream));
+    c->sp_active = true;
+    return check_device_error(c);
+}
+
+extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, uint8_t *out_boards, float *out_policy,
+                                    int8_t *out_status, int32_t *out_actions, omk_selfplay_stats *stats) {
+    CK(cudaSetDevice(c->device));
+    if (!c->sp_active) return fail(OMK_ERR_STATE, "omk_selfplay_begin has not been called");
+    if (plies < 0) return fail(OMK_ERR_INVALID, "plies < 0");
+    const omk_selfplay_config &cfg = c->sp_cfg;
+    const int n = cfg.n_games;
+    const int rows = n * cfg.batch_size;
+    const int rounds = (cfg.count + cfg.batch_size - 1) / cfg.batch_size;
+
+    const SpLayout L = sp_layout(c, n);
+    int32_t *mover = L.mover, *other = L.other, *actions = L.actions;
+    float *temps = L.temps;
+    uint8_t *modes = L.modes;
+    int8_t *status = L.status, *status2 = L.status2;
+    float *root_policy = L.root_policy;
+    unsigned long long *counters = L.counters;
+
+    // transition staging on the device: [ply][game]
+    const size_t tot = (size_t)plies * (size_t)n;
+    uint8_t *d_boards = nullptr;
+    float *d_policy = nullptr;
+    int8_t *d_status = nullptr;
+    int32_t *d_actions = nullptr;
+    if (tot) {
+        CK(cudaMalloc(&d_boards, tot * kCells));
+        CK(cudaMalloc(&d_policy, tot * kCells * sizeof(float)));
+        CK(cudaMalloc(&d_status, tot));
+        CK(cudaMalloc(&d_actions, tot * sizeof(int32_t)));
+    }
+    unsigned long long h_before[2] = {0, 0}, h_after[2] = {0, 0}, h_fin0 = 0, h_fin1 = 0;
+    CK(cudaMemcpyAsync(h_before, c->dev_sims, sizeof h_before, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&h_fin0, counters, sizeof h_fin0, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;
+    auto span_begin = [&](int kind) {
+        if (!profile) return;
+        Span s; s.kind = kind;
+        cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+        cudaEventRecord(s.a, c->stream);
+        spans.push_back(s);
+    };
+    auto span_end = [&]() { if (profile) cudaEventRecord(spans.back().b, c->stream); };
+
+    size_t d2h = 0;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int ply = 0; ply < plies; ++ply) {
+        span_begin(1);
+        launch_sp_prepare(c, n, mover, other, modes, temps);
+        launch_root_noise(c, mover, n, cfg.epsilon, cfg.alpha);
+        span_end();
+        for (int r = 0; r < rounds; ++r) {
+            span_begin(1);
+            launch_reset_requests(c);
+            launch_select_expand(c, mover, n, cfg.batch_size);
+            span_end();
+            span_begin(0);
+            run_evaluator(c, cfg.evaluator, rows);
+            span_end();
+            span_begin(1);
+            launch_apply(c, mover, n, kApplySearch);
+            span_end();
+        }
+        span_begin(1);
+        launch_sample(c, mover, n, modes, temps, actions, c->ws.policy_out, nullptr);
+        launch_sp_record(c, n, mover, actions, c->ws.policy_out, d_boards + (size_t)ply * n * kCells,
+                         d_policy + (size_t)ply * n * kCells, d_actions + (size_t)ply * n);
+        launch_play(c, mover, actions, n, status);
+        launch_reset_requests(c);
+        launch_ensure_prepare(c, other, actions, n);
+        span_end();
+        span_begin(0);
+        run_evaluator(c, cfg.evaluator, n);
+        span_end();
+        span_begin(1);
+        launch_apply(c, other, n, kApplyEnsure);
+        launch_play(c, other, actions, n, status2);
+        CK(cudaMemcpyAsync(d_status + (size_t)ply * n, status, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+        // finished games restart with fresh trees for both colours (cached root policy) and ply 0
+        launch_new_games(c, mover, n, nullptr, status, root_policy);
+        launch_new_games(c, other, n, nullptr, status, root_policy);
+        launch_sp_advance(c, n, status, counters);
+        span_end();
+    }
+    launch_reset_requests(c);  // folds the last round's request count into the evaluator total
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if (tot) {
+        if (out_boards) { CK(cudaMemcpyAsync(out_boards, d_boards, tot * kCells, cudaMemcpyDeviceToHost, c->stream)); d2h += tot * kCells; }
+        if (out_policy) { CK(cudaMemcpyAsync(out_policy, d_policy, tot * kCells * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); d2h += tot * kCells * 4; }
+        if (out_status) { CK(cudaMemcpyAsync(out_status, d_status, tot, cudaMemcpyDeviceToHost, c->stream)); d2h += tot; }
+        if (out_actions) { CK(cudaMemcpyAsync(out_actions, d_actions, tot * 4, cudaMemcpyDeviceToHost, c->stream)); d2h += tot * 4; }
+    }
+    CK(cudaMemcpyAsync(h_after, c->dev_sims, sizeof h_after, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&h_fin1, counters, sizeof h_fin1, cudaMemcpyDeviceToHost, c->stream));
+    int32_t rc = check_device_error(c);
+    cudaFree(d_boards); cudaFree(d_policy); cudaFree(d_status); cudaFree(d_actions);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->simulations = (int64_t)(h_after[0] - h_before[0]);
+        stats->nn_evals = (int64_t)(h_after[1] - h_before[1]);
+        stats->positions = (int64_t)tot;
+        stats->games_finished = (int64_t)(h_fin1 - h_fin0);
+        stats->d2h_bytes = (int64_t)d2h;
+        stats->h2d_bytes = 0;
+        cudaEventElapsedTime(&stats->gpu_ms, c->ev0, c->ev1);
+        for (auto &s : spans) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, s.a, s.b);
+            (s.kind == 0 ? stats->gpu_ms_net : stats->gpu_ms_tree) += ms;
+        }
+    }
+    for (auto &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    return rc;
+}

@@ -1,0 +1,116 @@
+// omk_internal.h -- host-side context and kernel launcher prototypes (not part of the ABI).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/omok_b200.h"
+#include "omk_device.cuh"
+
+namespace omk {
+
+constexpr int kMaxBatchPerTree = 64;  // per-tree requests per round (evaluate_batch_size)
+constexpr int kNetTensors = 31;
+
+enum ApplyMode { kApplySearch = 0, kApplyNewGame = 1, kApplyEnsure = 2 };
+
+struct NetWeights {
+    float *t[kNetTensors] = {};  // device copies in checkpoint order
+    float *heads_w = nullptr;    // [512][128]: cols 0..80 policy, col 81 value, rest 0
+    float *heads_b = nullptr;    // [128]
+    bool loaded = false;
+};
+
+struct Workspace {  // evaluator request/response buffers, sized for max_rows
+    int max_rows = 0;
+    NNIn *nn_in = nullptr;        // [max_rows]
+    uint32_t *req_tree = nullptr; // [max_rows]
+    uint32_t *req_node = nullptr; // [max_rows]
+    float *P = nullptr;           // [max_rows][96]
+    float *V = nullptr;           // [max_rows]
+    float *act0 = nullptr;        // [max_rows][10368] tower output == fc0 input
+    float *act1 = nullptr;        // [max_rows][512]
+    float *act2 = nullptr;        // [max_rows][512]
+    float *logits = nullptr;      // [max_rows][128]
+    uint32_t *n_req = nullptr;    // device counter
+    uint32_t *slot_base = nullptr, *slot_count = nullptr;  // [capacity_trees]
+    int32_t *ids = nullptr;       // [capacity_trees] device copy of the call's id list
+    int32_t *actions = nullptr;   // [capacity_trees]
+    uint8_t *modes = nullptr;     // [capacity_trees]
+    float *temps = nullptr;       // [capacity_trees]
+    int8_t *status = nullptr;     // [capacity_trees]
+    float *policy_out = nullptr;  // [capacity_trees][81]
+    uint32_t *streams = nullptr;  // [capacity_trees]
+};
+
+}  // namespace omk
+
+struct omk_ctx {
+    int device = 0;
+    int n_sms = 0;
+    int cap_envs = 0, cap_trees = 0, cap_nodes = 0;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+
+    omk::EnvRec *envs = nullptr;
+    omk::TreeHdr *tree_hdrs = nullptr;
+    uint8_t *tree_nodes = nullptr;   // [cap_trees][cap_nodes][kNodeBytes]
+    uint16_t *remap = nullptr;       // [cap_trees][cap_nodes] compaction scratch
+    uint32_t *dev_error = nullptr;   // sticky device error word
+    unsigned long long *dev_sims = nullptr;  // simulations counter
+
+    omk::NetWeights net;
+    omk::Workspace ws;
+
+    // self-play driver state
+    omk_selfplay_config sp_cfg{};
+    bool sp_active = false;
+    int32_t *sp_ply = nullptr;        // [n_games] device ply counters
+    void *sp_buf = nullptr;           // per-game scratch (ids, actions, modes, status, cached root policy)
+    // pinned host staging
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace omk {
+
+// ---- launchers (each increments ctx->launches) ----
+// env_kernels.cu
+void launch_env_reset(omk_ctx *c, const int32_t *ids_dev, int n);
+void launch_env_step(omk_ctx *c, const int32_t *ids_dev, const uint8_t *actions_dev, int n, int8_t *status_dev,
+                     uint32_t *legal_dev);
+void launch_env_get(omk_ctx *c, const int32_t *ids_dev, int n, uint8_t *boards_dev, uint8_t *turns_dev,
+                    uint16_t *legal_dev);
+void launch_env_set(omk_ctx *c, const int32_t *ids_dev, int n, const uint8_t *boards_dev, const uint8_t *turns_dev);
+void launch_env_encode(omk_ctx *c, const int32_t *ids_dev, int n, int mode, float *out_dev);
+void launch_env_playout(omk_ctx *c, int n, int plies, uint8_t *actions_dev, int8_t *status_dev);
+void launch_pack_boards(omk_ctx *c, const uint8_t *boards_dev, const uint8_t *turns_dev, int n, int mode);
+
+// tree_kernels.cu
+// only_if_terminal != nullptr: restart only slots whose status is terminal, keep their random stream running;
+// root_policy != nullptr: install that raw policy instead of queueing an evaluation
+void launch_new_games(omk_ctx *c, const int32_t *ids_dev, int n, const uint32_t *streams_dev,
+                      const int8_t *only_if_terminal, const float *root_policy);
+void launch_root_noise(omk_ctx *c, const int32_t *ids_dev, int n, float epsilon, float alpha);
+void launch_select_expand(omk_ctx *c, const int32_t *ids_dev, int n, int batch);
+void launch_apply(omk_ctx *c, const int32_t *ids_dev, int n, int mode);
+void launch_sample(omk_ctx *c, const int32_t *ids_dev, int n, const uint8_t *modes_dev, const float *temps_dev,
+                   int32_t *actions_dev, float *policy_dev, uint8_t *valid_dev);
+void launch_ensure_prepare(omk_ctx *c, const int32_t *ids_dev, const int32_t *actions_dev, int n);
+void launch_play(omk_ctx *c, const int32_t *ids_dev, const int32_t *actions_dev, int n, int8_t *status_dev);
+void launch_root_children(omk_ctx *c, int tree, int32_t *actions_dev, unsigned long long *n_dev, float *w_dev,
+                          float *p_dev, int32_t *len_dev, float *policy_dev, uint32_t *misc_dev);
+void launch_eval_hash(omk_ctx *c, int rows_bound);
+void launch_reset_requests(omk_ctx *c);
+void launch_sp_prepare(omk_ctx *c, int n, int32_t *mover, int32_t *other, uint8_t *modes, float *temps);
+void launch_sp_record(omk_ctx *c, int n, const int32_t *mover, const int32_t *actions, const float *policy_in,
+                      uint8_t *boards_out, float *policy_out, int32_t *actions_out);
+void launch_sp_advance(omk_ctx *c, int n, const int8_t *status, unsigned long long *counters);
+
+// net_kernels.cu
+void net_forward(omk_ctx *c, const float *images_dev /* or nullptr: use ws.nn_in */, int max_rows);
+void net_pack_heads(omk_ctx *c);
+void launch_net_init_random(omk_ctx *c, uint64_t seed);
+
+}  // namespace omk

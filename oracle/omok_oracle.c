@@ -244,6 +244,28 @@ void orc_dirichlet81(uint64_t seed, uint32_t stream, uint32_t noise_epoch, float
     for (int i = 0; i < ORC_CELLS; ++i) out[i] *= inv;
 }
 
+/* BASELINE config 2 driver: n boards, each plays `plies` uniformly random legal moves
+ * (stream = board index, one bounded draw per ply over the ascending list of empty
+ * cells), auto-reset after a terminal status.  Traces are [ply][board].            */
+void orc_random_playout(int n, int plies, uint64_t seed, uint8_t *out_actions, int8_t *out_status, orc_env *final_envs) {
+    for (int i = 0; i < n; ++i) {
+        orc_env env;
+        orc_env_new(&env);
+        uint32_t ctr = 0;
+        for (int ply = 0; ply < plies; ++ply) {
+            int avail[ORC_CELLS], k = 0;
+            for (int c = 0; c < ORC_CELLS; ++c)
+                if (env.board[c] == ORC_EMPTY) avail[k++] = c;
+            const int action = avail[orc_rng_below(seed, (uint32_t)i, &ctr, (uint32_t)k)];
+            const int st = orc_env_place_stone(&env, action);
+            if (out_actions) out_actions[(size_t)ply * n + i] = (uint8_t)action;
+            if (out_status) out_status[(size_t)ply * n + i] = (int8_t)st;
+            if (st != ORC_IN_PROGRESS) orc_env_new(&env);
+        }
+        if (final_envs) final_envs[i] = env;
+    }
+}
+
 /* ====================================================================== */
 /* fake evaluator (exact): hash of the packed board -> P in (0,1], V in [-1,1) */
 /* ====================================================================== */
@@ -261,6 +283,12 @@ void orc_hash_eval(const orc_env *env, int opponent_mode, float *p81, float *v) 
     for (int a = 0; a < ORC_CELLS; ++a)
         p81[a] = (float)((mix64(h + GOLDEN * (uint64_t)(a + 1)) >> 40) + 1) * 5.9604644775390625e-08f; /* 2^-24 */
     if (v) *v = (float)(mix64(h + GOLDEN * 82ull) >> 40) * 1.1920928955078125e-07f - 1.0f; /* 2^-23 */
+}
+
+/* orc_eval_fn-shaped wrapper so searches can run the fake net without leaving C */
+void orc_eval_hash_batch(void *user, const orc_env *envs, int n, int mode, float *out_p, float *out_v) {
+    (void)user;
+    for (int i = 0; i < n; ++i) orc_hash_eval(&envs[i], mode, out_p + (size_t)i * ORC_CELLS, out_v ? out_v + i : NULL);
 }
 
 /* ====================================================================== */

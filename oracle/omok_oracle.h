@@ -52,6 +52,9 @@ void orc_env_encode_board(const orc_env *env, int turn, float *dst162);
 /* alpha-zero/src/encoder.rs:10-46; mode 0 = EnvTurnMode::Player, 1 = ::Opponent */
 void orc_encode_nn_input(const orc_env *envs, int n, int mode, float *out243);
 
+/* BASELINE config 2 (random-play boards); traces [ply][board]; final_envs[n] may be NULL */
+void orc_random_playout(int n, int plies, uint64_t seed, uint8_t *out_actions, int8_t *out_status, orc_env *final_envs);
+
 /* ---- specified random stream (replaces thread_rng) ---- */
 uint32_t orc_rng_u32(uint64_t seed, uint32_t stream, uint32_t counter);
 /* uniform integer in [0, bound) drawing from (seed, stream, *counter) */
@@ -71,6 +74,9 @@ void orc_hash_eval(const orc_env *env, int opponent_mode, float *p81, float *v);
  * envs: n environments; mode: 0 Player / 1 Opponent encoding;
  * out_p: n*81, out_v: n (ignored by evaluate_p callers).                      */
 typedef void (*orc_eval_fn)(void *user, const orc_env *envs, int n, int mode, float *out_p, float *out_v);
+
+/* the fake net as an orc_eval_fn */
+void orc_eval_hash_batch(void *user, const orc_env *envs, int n, int mode, float *out_p, float *out_v);
 
 typedef struct orc_agent orc_agent;
 

@@ -58,6 +58,7 @@ def lib():
     L.orc_env_place_stone.restype = C.c_int
     L.orc_env_encode_board.argtypes = [P(Env), C.c_int, P(C.c_float)]
     L.orc_encode_nn_input.argtypes = [P(Env), C.c_int, C.c_int, P(C.c_float)]
+    L.orc_random_playout.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, P(Env)]
     L.orc_rng_u32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
     L.orc_rng_u32.restype = C.c_uint32
     L.orc_rng_below.argtypes = [C.c_uint64, C.c_uint32, P(C.c_uint32), C.c_uint32]
@@ -141,6 +142,16 @@ class Environment:
         return o
 
 
+def random_playout(n: int, plies: int, seed: int):
+    """(actions [plies,n] u8, status [plies,n] i8, final boards [n,81], final turns [n])."""
+    actions = np.zeros((plies, n), dtype=np.uint8)
+    status = np.zeros((plies, n), dtype=np.int8)
+    envs = (Env * n)()
+    lib().orc_random_playout(n, plies, seed, actions.ctypes.data, status.ctypes.data, envs)
+    boards, turns = envs_to_arrays(envs, n)
+    return actions, status, boards, turns
+
+
 def envs_to_arrays(envs_ptr, n: int):
     """(boards [n,81] u8, turns [n] u8) from an orc_env array pointer."""
     boards = np.empty((n, CELLS), dtype=np.uint8)
@@ -196,6 +207,17 @@ class HashEvaluator(Evaluator):
             lib().orc_hash_eval(C.byref(e), mode, _fp(p[i]), C.byref(vv))
             v[i] = vv.value
         return p, v
+
+
+class NativeHashEvaluator:
+    """orc_eval_hash_batch passed straight to C (no Python in the loop); same results as HashEvaluator."""
+
+    def __init__(self):
+        self._cb = C.cast(lib().orc_eval_hash_batch, EVAL_FN)
+
+    @property
+    def fn(self):
+        return self._cb
 
 
 class TorchEvaluator(Evaluator):

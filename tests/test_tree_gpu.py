@@ -1,0 +1,129 @@
+"""K2 parity (through the C ABI): search with the exact hash evaluator must reproduce the oracle's
+visit counts, w, p, root statistics, random-stream position and node counts BIT-EXACTLY, including
+across sample / play / ensure_action_exists / re-rooting."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(omk):
+    c = omk.Context(device=0, capacity_envs=4, capacity_trees=256, capacity_nodes=4096, seed=2024)
+    yield c
+    c.close()
+
+
+def assert_tree_equal(ctx, tree, agent, where=""):
+    ga, gn, gw, gp = ctx.pool_root_children(tree)
+    oa, on, ow, op = agent.root_children()
+    assert np.array_equal(ga, oa), f"{where}: child actions / creation order"
+    assert np.array_equal(gn, on), f"{where}: visit counts"
+    assert gw.tobytes() == ow.tobytes(), f"{where}: w"
+    assert gp.tobytes() == op.tobytes(), f"{where}: p"
+    n, w, p, st, pol = ctx.pool_root_stats(tree)
+    rn, rw, rp, rst, rpol = agent.root_stats()
+    assert (n, st) == (rn, rst), where
+    assert np.float32(w).tobytes() == np.float32(rw).tobytes(), where
+    assert np.float32(p).tobytes() == np.float32(rp).tobytes(), where
+    assert pol.tobytes() == rpol.tobytes(), f"{where}: root policy"
+    nodes, ctr = ctx.pool_tree_info(tree)
+    assert nodes == agent.node_count, f"{where}: node count"
+    assert ctr == agent.rng_counter, f"{where}: rng counter"
+    board, turn, legal = ctx.pool_get_env(tree)
+    assert np.array_equal(board, agent.board()) and turn == agent.env.turn and legal == agent.env.legal_move_count
+
+
+@pytest.mark.parametrize("count,batch,eps,alpha", [(800, 16, 0.0, 1.0), (800, 8, 0.0, 1.0), (600, 16, 0.25, 0.03), (50, 1, 0.25, 0.3), (100, 64, 0.5, 1.0), (96, 32, 0.25, 2.5)])
+def test_search_matches_oracle_bit_exact(ctx, omk, orc, count, batch, eps, alpha):
+    T = 24
+    ev = orc.NativeHashEvaluator()
+    streams = np.arange(100, 100 + T, dtype=np.uint32)
+    agents = [orc.Agent(ev, ctx.seed, int(s)) for s in streams]
+    ctx.pool_new_games(n=T, streams=streams, evaluator=omk.EVAL_HASH)
+    for t in range(T):
+        assert_tree_equal(ctx, t, agents[t], "new")
+    orc.execute(agents, count, batch, eps, alpha, ev)
+    ctx.pool_search(n=T, count=count, batch_size=batch, epsilon=eps, alpha=alpha, evaluator=omk.EVAL_HASH)
+    for t in range(T):
+        assert_tree_equal(ctx, t, agents[t], f"tree {t}")
+
+
+def test_full_self_play_games_match_oracle(ctx, omk, orc):
+    """Trainer-shaped self-play (src/trainer.rs:86-204): two agents per game, Boltzmann for the first plies then
+    Best, ensure_action_exists + play on the opponent tree; compared after every step until all games end."""
+    G = 12
+    ev = orc.NativeHashEvaluator()
+    black = [orc.Agent(ev, ctx.seed, 2 * g) for g in range(G)]
+    white = [orc.Agent(ev, ctx.seed, 2 * g + 1) for g in range(G)]
+    ctx.pool_new_games(n=2 * G, evaluator=omk.EVAL_HASH)  # stream == tree id
+    live = list(range(G))
+    ply = 0
+    threshold = 6
+    while live and ply < 81:
+        movers = [black[g] if ply % 2 == 0 else white[g] for g in live]
+        others = [white[g] if ply % 2 == 0 else black[g] for g in live]
+        mids = [2 * g + (ply % 2) for g in live]
+        oids = [2 * g + 1 - (ply % 2) for g in live]
+        orc.execute(movers, 200, 16, 0.25, 0.03, ev)
+        ctx.pool_search(ids=mids, count=200, batch_size=16, epsilon=0.25, alpha=0.03, evaluator=omk.EVAL_HASH)
+        mode = 1 if ply < threshold else 0
+        acts, pol = ctx.pool_sample(ids=mids, modes=[mode] * len(live), temperatures=[1.0] * len(live))
+        ref = [m.sample_action(mode, 1.0) for m in movers]
+        assert [int(a) for a in acts] == [r[0] for r in ref], f"ply {ply}: sampled actions"
+        assert np.stack([r[1] for r in ref]).tobytes() == pol.tobytes(), f"ply {ply}: visit policy"
+        st = ctx.pool_play(acts, ids=mids)
+        rst = [m.play_action(int(a)) for m, a in zip(movers, acts)]
+        assert [int(s) for s in st] == rst
+        ctx.pool_ensure_action(acts, ids=oids, evaluator=omk.EVAL_HASH)
+        for o, a in zip(others, acts):
+            o.ensure_action_exists(int(a), ev)
+        st2 = ctx.pool_play(acts, ids=oids)
+        rst2 = [o.play_action(int(a)) for o, a in zip(others, acts)]
+        assert [int(s) for s in st2] == [(-1 if r is None else r) for r in rst2]
+        for g, mid, oid in zip(live, mids, oids):
+            assert_tree_equal(ctx, mid, black[g] if ply % 2 == 0 else white[g], f"ply {ply} game {g} mover")
+            assert_tree_equal(ctx, oid, white[g] if ply % 2 == 0 else black[g], f"ply {ply} game {g} other")
+        live = [g for g, s in zip(live, st) if s == 0]
+        ply += 1
+    assert not live or ply == 81
+
+
+def test_play_edge_cases(ctx, omk):
+    ctx.pool_new_games(ids=[200], evaluator=omk.EVAL_HASH)
+    assert ctx.pool_play([5], ids=[200])[0] == -1  # action not in the tree
+    assert ctx.pool_policy(ids=[200])[1][0] == 0  # no children -> None
+    assert ctx.pool_sample(ids=[200])[0][0] == -1
+    ctx.pool_ensure_action([5], ids=[200], evaluator=omk.EVAL_HASH)
+    assert ctx.pool_policy(ids=[200])[1][0] == 0  # child exists but no visits -> None (sum < EPSILON)
+    assert ctx.pool_play([5], ids=[200])[0] == 0
+    ctx.pool_ensure_action([5], ids=[200], evaluator=omk.EVAL_HASH)  # occupied cell: child for an illegal action
+    assert ctx.pool_play([5], ids=[200])[0] == -1  # place_stone refuses -> None, tree untouched
+    assert ctx.pool_tree_info(200)[0] == 2
+    ctx.pool_ensure_action([81], ids=[200], evaluator=omk.EVAL_HASH)  # out of range: no-op
+    assert ctx.pool_tree_info(200)[0] == 2
+
+
+def test_capacity_error_is_loud(omk):
+    c = omk.Context(device=0, capacity_envs=1, capacity_trees=2, capacity_nodes=64, seed=1)
+    c.pool_new_games(n=2, evaluator=omk.EVAL_HASH)
+    with pytest.raises(omk.OmkError) as e:
+        c.pool_search(n=2, count=800, batch_size=16, epsilon=0.0, alpha=1.0, evaluator=omk.EVAL_HASH)
+    assert e.value.code == -3
+    c.close()
+
+
+def test_reference_shaped_api(ctx, omk, orc):
+    """The host mirror reads like the reference: Agent / ParallelMCTSExecutor / MCTSExecutor."""
+    ev = orc.NativeHashEvaluator()
+    a = omk.Agent(ctx, evaluator=omk.EVAL_HASH, stream=7)
+    ref = orc.Agent(ev, ctx.seed, 7)
+    assert a.compute_policy() is None and ref.compute_policy() is None
+    omk.MCTSExecutor().run(800, 8, 0.0, 1.0, a)  # benchmark crate constants (benchmark/src/main.rs:9-10)
+    orc.execute([ref], 800, 8, 0.0, 1.0, ev)
+    act, pol = a.sample_action(omk.ActionSamplingMode.Best)
+    ract, rpol = ref.sample_action(0)
+    assert act == ract and pol.tobytes() == rpol.tobytes()
+    assert a.play_action(act) == omk.GameStatus.InProgress
+    assert a.play_action(act) is None
+    assert a.env["turn"] == omk.Turn.White
