@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the self-play hot path (BASELINE.json configs[2]).
+
+Workload (per GPU): 1024 concurrent self-play games, two trees per game as in the reference trainer
+(src/trainer.rs:86-94), 800 simulations per move in rounds of 16 per tree (epsilon 0.25, alpha 0.03,
+Boltzmann(1.0) for the first 30 plies then Best), random-init residual policy/value network.
+One "step" = one ply on every game = 1024 positions = 1024 x 800 simulations.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun: one process per GPU, per-GPU game pools, NO data-path collective
+(games are independent units -> weak scaling); only the timing barrier / max-over-ranks uses NCCL.
+
+The line's `value` is device-resident throughput (omk_selfplay_run, CUDA events); `e2e` drives the same
+ply through the granular C-ABI calls a Rust `alpha-zero` shim would make (host id/action buffers in,
+actions/policies/status out, every call synchronising) -- that is the headline against the reference arm.
+`--impl reference` times the CPU oracle (C restatement, all host cores) with the PyTorch-CPU fp32 network
+standing in for TensorFlow-CPU, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GAMES_PER_GPU = 1024
+COUNT, BATCH, EPS, ALPHA, TEMP, TEMP_THRESHOLD = 800, 16, 0.25, 0.03, 1.0, 30
+CAP_NODES = 4096
+FLOP_FC0 = 2 * 10368 * 512
+FLOP_POSITION = 15_906_240
+CPU_SAMPLE_TREES = 64
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: CPU oracle + PyTorch-CPU fp32 network on the box's host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_selfplay_sample(steps: int, warmup: int, trees: int = CPU_SAMPLE_TREES):
+    """Each step: one ply (800 sims/move, rounds of 16) on `trees` concurrent trees, trainer semantics."""
+    import numpy as np
+    import torch
+
+    from oracle import net_oracle, oracle as orc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = net_oracle.random_params(0)
+    ev = orc.TorchEvaluator(params)
+    games = trees
+    black = [orc.Agent(ev, 0, 2 * g) for g in range(games)]
+    white = [orc.Agent(ev, 0, 2 * g + 1) for g in range(games)]
+    ply = [0] * games
+
+    def one_ply():
+        movers = [black[g] if ply[g] % 2 == 0 else white[g] for g in range(games)]
+        others = [white[g] if ply[g] % 2 == 0 else black[g] for g in range(games)]
+        sims = orc.execute(movers, COUNT, BATCH, EPS, ALPHA, ev, n_threads=cores)
+        for g in range(games):
+            act, _ = movers[g].sample_action(1 if ply[g] < TEMP_THRESHOLD else 0, TEMP)
+            st = movers[g].play_action(act)
+            others[g].ensure_action_exists(act, ev)
+            others[g].play_action(act)
+            if st != 0:
+                black[g], white[g], ply[g] = orc.Agent(ev, 0, 2 * g), orc.Agent(ev, 0, 2 * g + 1), 0
+            else:
+                ply[g] += 1
+        return sims
+
+    for _ in range(warmup):
+        one_ply()
+    t0 = time.perf_counter()
+    sims = 0
+    for _ in range(steps):
+        sims += one_ply()
+    dt = time.perf_counter() - t0
+    return {"sims": sims, "positions": steps * games, "seconds": dt, "cores": cores, "trees": trees,
+            "nn_positions": ev.positions}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    warm = min(args.warmup, 1)
+    r = cpu_selfplay_sample(steps, warm)
+    value = r["sims"] / r["seconds"]
+    line = {
+        "impl": "reference",
+        "metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s",
+        "positions_per_sec": r["positions"] / r["seconds"],
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * r["seconds"] / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "simulations/s", "cores": r["cores"], "kind": "port",
+                         "sample": f"{r['trees']} concurrent trees x {steps} plies x {COUNT} sims/move (rounds of {BATCH}); "
+                                   "C oracle on all host cores + PyTorch-CPU fp32 network in place of TensorFlow-CPU"},
+        "e2e": {"value": value, "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": f"BASELINE configs[2]: batched MCTS, {GAMES_PER_GPU} concurrent trees per GPU x {COUNT} sims/move, "
+                        f"rounds of {BATCH}, eps {EPS}, alpha {ALPHA}, random-init residual policy/value net; "
+                        "trainer-shaped self-play (2 trees per game, ensure_action_exists + re-root each ply)",
+            "games_per_gpu": GAMES_PER_GPU, "trees_per_gpu": 2 * GAMES_PER_GPU, "sims_per_move": COUNT,
+            "nn_batch_per_tree": BATCH, "capacity_nodes": CAP_NODES, "parallelism": f"games sharded x{n_gpus}, no collective",
+            "l2": "no flush: each round streams a 680 MB fc0 input (>> 126 MB L2) and ~2.9 GB of tree records are resident"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+
+    omk = importlib.import_module("omok-ai_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    games = args.games
+    warm = max(3, args.warmup)
+    steps = max(1, args.steps)
+    ctx = omk.Context(device=local_rank, capacity_envs=4, capacity_trees=2 * games, capacity_nodes=CAP_NODES, seed=1000 + rank)
+    ctx.net_init_random(0)  # same random-init weights on every rank (no broadcast needed)
+    ctx.selfplay_begin(games, COUNT, BATCH, EPS, ALPHA, TEMP, TEMP_THRESHOLD, omk.EVAL_NET)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    # ---- device-resident arm: `value` ----
+    ctx.selfplay_run(warm, profile=0, want_transitions=False)
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    stats, *_ = ctx.selfplay_run(steps, profile=1, want_transitions=False)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    ms = float(stats.gpu_ms)
+    sims, positions, nn_evals = int(stats.simulations), int(stats.positions), int(stats.nn_evals)
+    fc0_ms, fc0_launches = stats.by_kind()["fc0"]
+
+    # ---- e2e arm: granular C-ABI calls with host buffers, as the Rust alpha-zero shim would issue them ----
+    e2e_steps = steps
+    ids_b = np.arange(0, 2 * games, 2, dtype=np.int32)
+    ids_w = ids_b + 1
+    ctx.pool_new_games(n=2 * games, evaluator=omk.EVAL_NET)
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    e2e_sims = 0
+    for p in range(e2e_steps):
+        mover, other = (ids_b, ids_w) if p % 2 == 0 else (ids_w, ids_b)
+        ctx.pool_search(ids=mover, count=COUNT, batch_size=BATCH, epsilon=EPS, alpha=ALPHA, evaluator=omk.EVAL_NET)
+        e2e_sims += games * (-(-COUNT // BATCH) * BATCH)
+        modes = np.full(games, 1 if p < TEMP_THRESHOLD else 0, np.uint8)
+        acts, pol = ctx.pool_sample(ids=mover, modes=modes, temperatures=np.full(games, TEMP, np.float32))
+        st = ctx.pool_play(acts, ids=mover)
+        ctx.pool_ensure_action(acts, ids=other, evaluator=omk.EVAL_NET)
+        ctx.pool_play(acts, ids=other)
+        h2d += mover.nbytes * 5 + modes.nbytes + games * 4 + acts.nbytes * 3
+        d2h += acts.nbytes + pol.nbytes + st.nbytes * 2 + 4 * 3
+        assert (st == 0).all() or p >= 8, "a game ended implausibly early"
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- aggregate over ranks: max time, summed work ----
+    if dist:
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+        w = torch.tensor([sims, positions, nn_evals, launches, e2e_sims], device="cuda", dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        sims, positions, nn_evals, launches, e2e_sims = (int(x) for x in w.tolist())
+
+    if rank == 0:
+        peaks = read_peaks()
+        rows_per_launch = (int(stats.nn_evals) / max(1, fc0_launches))
+        # fc0 launches also cover the (small) ensure_action batches; algorithmic flops = rows actually evaluated
+        fc0_tflops = (int(stats.nn_evals) * FLOP_FC0) / (fc0_ms * 1e-3) / 1e12 if fc0_ms > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        line = {
+            "metric": "mcts_simulations_per_sec", "value": sims / (ms * 1e-3), "unit": "simulations/s",
+            "positions_per_sec": positions / (ms * 1e-3), "nn_evals_per_sec": nn_evals / (ms * 1e-3),
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_sims / e2e_s, "unit": "simulations/s", "h2d_bytes_per_step": h2d // e2e_steps,
+                    "d2h_bytes_per_step": d2h // e2e_steps,
+                    "path": "omk_pool_search/sample/play/ensure_action/play per ply with host id+action buffers"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "k_gemm (fc0 10368->512, fp32 CUDA cores)",
+                         "achieved": fc0_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fc0_tflops / peak,
+                         "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); fp32-accurate path, see DESIGN.md",
+                         "avg_launch_ms": fc0_ms / max(1, fc0_launches), "rows_per_launch": rows_per_launch,
+                         "share_of_step": fc0_ms / float(stats.gpu_ms) if stats.gpu_ms else None,
+                         "traffic": None},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_selfplay_sample(1, 0)
+            line["cpu_baseline"] = {
+                "value": r["sims"] / r["seconds"], "unit": "simulations/s", "cores": r["cores"], "kind": "port",
+                "sample": f"{r['trees']} concurrent trees x 1 ply x {COUNT} sims/move; C oracle (pthreads over trees) + "
+                          "PyTorch-CPU fp32 network standing in for TensorFlow-CPU"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

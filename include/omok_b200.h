@@ -159,6 +159,19 @@ OMK_API int32_t omk_pool_tree_info(omk_ctx *ctx, int32_t id, int32_t *out_nodes,
  * ply < temperature_threshold, then Best), play, ensure_action_exists + play on the
  * opponent trees, auto-restart finished games.  Transitions (board 81 B, pi 81 f32,
  * mover-view z placeholder, game id, ply) stream to a pinned host ring.          */
+/* kernel families for profiling spans */
+enum {
+    OMK_K_TOWER = 0,      /* k_tower: stem + 3 bottleneck blocks */
+    OMK_K_FC0 = 1,        /* k_gemm 10368 -> 512 (67 % of the network's flops) */
+    OMK_K_FC1 = 2,        /* k_gemm 512 -> 512 */
+    OMK_K_HEADS = 3,      /* k_gemm 512 -> 82 + k_heads (tanh / softmax) */
+    OMK_K_HASH = 4,       /* k_eval_hash */
+    OMK_K_SELECT = 5,     /* k_select_expand (+ request counter reset) */
+    OMK_K_APPLY = 6,      /* k_apply */
+    OMK_K_MOVE = 7,       /* per-ply kernels: noise, sample, record, play, ensure, restart */
+    OMK_K_COUNT = 8
+};
+
 typedef struct {
     int32_t n_games;
     int32_t count;       /* evaluate_count       (src/config.rs:91) */
@@ -177,8 +190,10 @@ typedef struct {
     int64_t games_finished;
     int64_t h2d_bytes, d2h_bytes;
     float gpu_ms;           /* CUDA-event time of the whole call on the context stream */
-    float gpu_ms_net;       /* summed CUDA-event time of evaluator kernels (0 unless profiling on) */
-    float gpu_ms_tree;      /* summed CUDA-event time of tree kernels (0 unless profiling on) */
+    /* per-kernel-family CUDA-event time and launch count inside the call, indexed by OMK_K_*;
+     * filled according to the `profile` level (0: none, 1: fc0 only, 2: every family) */
+    float kind_ms[OMK_K_COUNT];
+    int64_t kind_launches[OMK_K_COUNT];
 } omk_selfplay_stats;
 
 OMK_API int32_t omk_selfplay_begin(omk_ctx *ctx, const omk_selfplay_config *cfg);

@@ -55,9 +55,14 @@ class SelfPlayStats(C.Structure):
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
         ("gpu_ms", C.c_float),
-        ("gpu_ms_net", C.c_float),
-        ("gpu_ms_tree", C.c_float),
+        ("kind_ms", C.c_float * 8),
+        ("kind_launches", C.c_int64 * 8),
     ]
+
+    KINDS = ("tower", "fc0", "fc1", "heads", "hash", "select_expand", "apply", "move")
+
+    def by_kind(self):
+        return {k: (float(self.kind_ms[i]), int(self.kind_launches[i])) for i, k in enumerate(self.KINDS)}
 
 
 def lib_path() -> str:
@@ -332,7 +337,7 @@ class Context:
         self._sp_n = n_games
         self._check(self.L.omk_selfplay_begin(self.h, C.byref(cfg)))
 
-    def selfplay_run(self, plies: int, profile: bool = False, want_transitions: bool = True):
+    def selfplay_run(self, plies: int, profile: int = 0, want_transitions: bool = True):
         n = self._sp_n
         boards = np.zeros((plies, n, CELLS), dtype=np.uint8) if want_transitions else None
         policy = np.zeros((plies, n, CELLS), dtype=np.float32) if want_transitions else None

@@ -405,11 +405,7 @@ void launch_net_init_random(omk_ctx *c, uint64_t seed) {
 }
 
 void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_tower, cudaFuncAttributeMaxDynamicSharedMemorySize, kTowerSmemBytes);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(k_tower, cudaFuncAttributeMaxDynamicSharedMemorySize, kTowerSmemBytes);
     if (max_rows > c->ws.max_rows) max_rows = c->ws.max_rows;
     if (max_rows <= 0) return;
     TowerWeights tw;
@@ -421,16 +417,24 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
         tw.b1[r] = c->net.t[b + 4]; tw.w2[r] = c->net.t[b + 5]; tw.b2[r] = c->net.t[b + 6];
     }
     const int tower_grid = max_rows < c->n_sms ? max_rows : c->n_sms;
+    bool sp = prof_begin(c, OMK_K_TOWER, 2);
     k_tower<<<tower_grid, kTowerThreads, kTowerSmemBytes, c->stream>>>(tw, c->ws.nn_in, images_dev, c->ws.n_req, max_rows,
                                                                       c->ws.act0);
+    prof_end(c, sp);
     const int mt = (max_rows + GM - 1) / GM;
+    sp = prof_begin(c, OMK_K_FC0, 1);
     k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act0, c->net.t[23], c->net.t[24], c->ws.act1, c->ws.n_req,
                                                       max_rows, kFc, kFlat, 1);
+    prof_end(c, sp);
+    sp = prof_begin(c, OMK_K_FC1, 2);
     k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act1, c->net.t[25], c->net.t[26], c->ws.act2, c->ws.n_req,
                                                       max_rows, kFc, kFc, 1);
+    prof_end(c, sp);
+    sp = prof_begin(c, OMK_K_HEADS, 2);
     k_gemm<<<dim3(1, mt), 256, 0, c->stream>>>(c->ws.act2, c->net.heads_w, c->net.heads_b, c->ws.logits, c->ws.n_req, max_rows,
                                                128, kFc, 0);
     k_heads<<<(max_rows + 7) / 8, 256, 0, c->stream>>>(c->ws.logits, c->ws.n_req, max_rows, c->ws.P, c->ws.V);
+    prof_end(c, sp);
     c->launches += 5;
 }
 

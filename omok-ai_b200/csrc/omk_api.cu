@@ -87,10 +87,34 @@ static int32_t stage_ids(omk_ctx *c, const int32_t *ids, int n, const int32_t **
     return OMK_OK;
 }
 
+namespace omk {
+bool prof_begin(omk_ctx *c, int kind, int min_level) {
+    if (c->prof_level < min_level) return false;
+    omk_prof_span s;
+    s.kind = kind;
+    for (cudaEvent_t *e : {&s.a, &s.b}) {
+        if (c->prof_pool.empty()) {
+            cudaEventCreate(e);
+        } else {
+            *e = c->prof_pool.back();
+            c->prof_pool.pop_back();
+        }
+    }
+    cudaEventRecord(s.a, c->stream);
+    c->prof_spans.push_back(s);
+    return true;
+}
+void prof_end(omk_ctx *c, bool opened) {
+    if (opened) cudaEventRecord(c->prof_spans.back().b, c->stream);
+}
+}  // namespace omk
+
 static void run_evaluator(omk_ctx *c, int evaluator, int rows_bound) {
-    if (evaluator == OMK_EVAL_HASH)
+    if (evaluator == OMK_EVAL_HASH) {
+        const bool sp = prof_begin(c, OMK_K_HASH, 2);
         launch_eval_hash(c, rows_bound);
-    else
+        prof_end(c, sp);
+    } else
         net_forward(c, nullptr, rows_bound);
 }
 
@@ -171,6 +195,7 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < kNetTensors; ++i) cudaFree(c->net.t[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -674,48 +699,37 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
     CK(cudaMemcpyAsync(&h_fin0, counters, sizeof h_fin0, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
 
-    struct Span { cudaEvent_t a, b; int kind; };
-    std::vector<Span> spans;
-    auto span_begin = [&](int kind) {
-        if (!profile) return;
-        Span s; s.kind = kind;
-        cudaEventCreate(&s.a); cudaEventCreate(&s.b);
-        cudaEventRecord(s.a, c->stream);
-        spans.push_back(s);
-    };
-    auto span_end = [&]() { if (profile) cudaEventRecord(spans.back().b, c->stream); };
+    c->prof_level = profile;
+    auto span_begin = [&](int kind) { return prof_begin(c, kind, 2); };
+    auto span_end = [&](bool sp) { prof_end(c, sp); };
 
     size_t d2h = 0;
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int ply = 0; ply < plies; ++ply) {
-        span_begin(1);
+        bool sp = span_begin(OMK_K_MOVE);
         launch_sp_prepare(c, n, mover, other, modes, temps);
         launch_root_noise(c, mover, n, cfg.epsilon, cfg.alpha);
-        span_end();
+        span_end(sp);
         for (int r = 0; r < rounds; ++r) {
-            span_begin(1);
+            sp = span_begin(OMK_K_SELECT);
             launch_reset_requests(c);
             launch_select_expand(c, mover, n, cfg.batch_size);
-            span_end();
-            span_begin(0);
+            span_end(sp);
             run_evaluator(c, cfg.evaluator, rows);
-            span_end();
-            span_begin(1);
+            sp = span_begin(OMK_K_APPLY);
             launch_apply(c, mover, n, kApplySearch);
-            span_end();
+            span_end(sp);
         }
-        span_begin(1);
+        sp = span_begin(OMK_K_MOVE);
         launch_sample(c, mover, n, modes, temps, actions, c->ws.policy_out, nullptr);
         launch_sp_record(c, n, mover, actions, c->ws.policy_out, d_boards + (size_t)ply * n * kCells,
                          d_policy + (size_t)ply * n * kCells, d_actions + (size_t)ply * n);
         launch_play(c, mover, actions, n, status);
         launch_reset_requests(c);
         launch_ensure_prepare(c, other, actions, n);
-        span_end();
-        span_begin(0);
+        span_end(sp);
         run_evaluator(c, cfg.evaluator, n);
-        span_end();
-        span_begin(1);
+        sp = span_begin(OMK_K_MOVE);
         launch_apply(c, other, n, kApplyEnsure);
         launch_play(c, other, actions, n, status2);
         CK(cudaMemcpyAsync(d_status + (size_t)ply * n, status, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
@@ -723,7 +737,7 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
         launch_new_games(c, mover, n, nullptr, status, root_policy);
         launch_new_games(c, other, n, nullptr, status, root_policy);
         launch_sp_advance(c, n, status, counters);
-        span_end();
+        span_end(sp);
     }
     launch_reset_requests(c);  // folds the last round's request count into the evaluator total
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -746,12 +760,18 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
         stats->d2h_bytes = (int64_t)d2h;
         stats->h2d_bytes = 0;
         cudaEventElapsedTime(&stats->gpu_ms, c->ev0, c->ev1);
-        for (auto &s : spans) {
+        for (auto &s : c->prof_spans) {
             float ms = 0;
             cudaEventElapsedTime(&ms, s.a, s.b);
-            (s.kind == 0 ? stats->gpu_ms_net : stats->gpu_ms_tree) += ms;
+            stats->kind_ms[s.kind] += ms;
+            stats->kind_launches[s.kind] += 1;
         }
     }
-    for (auto &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto &s : c->prof_spans) {
+        c->prof_pool.push_back(s.a);
+        c->prof_pool.push_back(s.b);
+    }
+    c->prof_spans.clear();
+    c->prof_level = 0;
     return rc;
 }

