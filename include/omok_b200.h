@@ -96,6 +96,13 @@ OMK_API int32_t omk_net_eval(omk_ctx *ctx, const uint8_t *boards, const uint8_t 
  * (alpha-zero/src/encoder.rs:10-46; any float values, not only {0,1}).          */
 OMK_API int32_t omk_net_eval_images(omk_ctx *ctx, const float *images, int32_t n, float *out_p, float *out_v);
 
+/* ---------------------------------------------------------------- diagnostics (tests / A-B runs)
+ * fc0 kernel choice: 0 = fp32 CUDA-core GEMM, 1 = tcgen05 kind::tf32 with 3-pass error compensation (default;
+ * env OMK_FC0=simt|tc at context creation).  omk_debug_get_buffer copies an intermediate activation buffer
+ * (0 fc0 input, 1 fc0 output, 2 fc1 output, 3 head logits, 4/5 fc0 input hi/lo parts) to the host.        */
+OMK_API int32_t omk_debug_set_fc0_mode(omk_ctx *ctx, int32_t mode);
+OMK_API int32_t omk_debug_get_buffer(omk_ctx *ctx, int32_t which, float *out, int64_t count);
+
 /* ---------------------------------------------------------------- environment
  * Replaces environment::Environment (environment/src/lib.rs:62-193), batched.   */
 OMK_API int32_t omk_env_reset(omk_ctx *ctx, const int32_t *ids, int32_t n);                      /* Environment::new  :73 */

@@ -103,6 +103,8 @@ def load_library():
     L.omk_net_init_random.argtypes = [vp, u64]
     L.omk_net_eval.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.omk_net_eval_images.argtypes = [vp, vp, i32, vp, vp]
+    L.omk_debug_set_fc0_mode.argtypes = [vp, i32]
+    L.omk_debug_get_buffer.argtypes = [vp, i32, vp, i64]
     L.omk_env_reset.argtypes = [vp, vp, i32]
     L.omk_env_step.argtypes = [vp, vp, vp, i32, vp, vp]
     L.omk_env_step_device.argtypes = [vp, vp, i32, vp, vp]
@@ -210,6 +212,14 @@ class Context:
         v = np.zeros(n, dtype=np.float32) if want_v else None
         self._check(self.L.omk_net_eval_images(self.h, _ptr(images), n, _ptr(p), _ptr(v)))
         return p, v
+
+    def debug_set_fc0_mode(self, mode: int):
+        self._check(self.L.omk_debug_set_fc0_mode(self.h, mode))
+
+    def debug_get_buffer(self, which: int, count: int):
+        out = np.zeros(count, dtype=np.float32)
+        self._check(self.L.omk_debug_get_buffer(self.h, which, _ptr(out), count))
+        return out
 
     # ---- environment pool ----
     def env_reset(self, ids=None, n=None):

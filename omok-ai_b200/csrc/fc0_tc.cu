@@ -1,0 +1,288 @@
+// fc0_tc.cu -- K3 tensor-core path for fc0 (10368 -> 512, 67 % of the network's flops).
+//
+//   C[M x 512] = lrelu( A[M x 10368] . W[10368 x 512] + b )        (alpha-zero/src/network.rs:139-150)
+//
+// fp32-class accuracy on the 5th-gen tensor cores: every operand is split into a TF32-exact
+// high part and a residual low part (x = hi + lo, hi = x with the 13 low mantissa bits cleared)
+// and each k-step issues three tcgen05.mma kind::tf32 into one TMEM accumulator:
+//        hi.hi + hi.lo + lo.hi        (the dropped lo.lo term is ~2^-22 relative)
+// which holds the north-star 1e-3 tolerance where one-pass TF32 misses it by 50x.
+//
+// Structure (one CTA per 128 x 256 output tile, 6 warps):
+//   warp 0     TMA producer: four 2-D tiled loads per k-block (A_hi, A_lo, W_hi, W_lo; 128-byte
+//              rows, SWIZZLE_128B) into a 2-stage ring, completion on an mbarrier (expect_tx)
+//   warp 1     TMEM allocator + single-thread MMA issuer: 4 k-steps x 3 products of
+//              128 x 256 x 8 per k-block, tcgen05.commit releases the stage / signals the epilogue
+//   warps 2-5  epilogue: tcgen05.ld 32x32b from their TMEM lane quadrant, + bias, lrelu, store
+// Both operands are K-major: A rows are positions, and W is transposed once at load time.
+#include <cuda.h>
+
+#include "omk_internal.h"
+
+namespace omk {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_K = 10368, TC_N = 512;
+constexpr int TC_NKB = TC_K / TC_BK;  // 324
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;  // 32 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 96 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_TMEM_COLS = 256;
+// instruction descriptor: D=F32 (bit 4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// spin on the phase parity; a bounded spin turns a pipeline bug into a trap instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address, 16-byte units
+    d |= (uint64_t)0 << 16;                        // leading byte offset: unused for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row core groups
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_fc0_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+             const float *__restrict__ bias, float *__restrict__ C, const uint32_t *n_req, int max_rows) {
+    extern __shared__ uint8_t smem_raw[];
+    const int rows = (int)min(*n_req, (uint32_t)max_rows);
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+    if (m0 >= rows) return;  // uniform for the whole CTA, before any barrier or TMEM use
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tmem_full = bars + 16 * TC_STAGES, tmem_slot = tmem_full + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_hi));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo));
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < TC_NKB; ++kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const uint32_t st = base + s * TC_STAGE_BYTES;
+                const uint32_t bar = full0 + 8 * s;
+                mbar_expect_tx(bar, TC_STAGE_BYTES);
+                tma_load_2d(st, &map_a_hi, bar, kb * TC_BK, m0);
+                tma_load_2d(st + TC_A_BYTES, &map_a_lo, bar, kb * TC_BK, m0);
+                tma_load_2d(st + 2 * TC_A_BYTES, &map_b_hi, bar, kb * TC_BK, n0);
+                tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &map_b_lo, bar, kb * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            for (int kb = 0; kb < TC_NKB; ++kb) {
+                const int s = kb % TC_STAGES;
+                const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * TC_STAGE_BYTES;
+                const uint64_t a_hi = make_desc_sw128(st), a_lo = make_desc_sw128(st + TC_A_BYTES);
+                const uint64_t b_hi = make_desc_sw128(st + 2 * TC_A_BYTES), b_lo = make_desc_sw128(st + 2 * TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per k-step inside the swizzle atom
+                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, TC_IDESC, (kb | k) != 0 ? 1u : 0u);
+                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, TC_IDESC, 1u);
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, TC_IDESC, 1u);
+                }
+                umma_commit(empty0 + 8 * s);  // stage reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full);  // accumulator complete
+        }
+    } else {  // ===== epilogue: warps 2..5 own TMEM lane quadrants 2,3,0,1 =====
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + q * 32 + lane;
+        float *crow = C + (size_t)row * TC_N + n0;
+        const float *brow = bias + n0;
+#pragma unroll 1
+        for (int c = 0; c < TC_BN; c += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4 *>(brow + c + j);
+                float4 o;
+                o.x = __uint_as_float(v[j + 0]) + b.x;
+                o.y = __uint_as_float(v[j + 1]) + b.y;
+                o.z = __uint_as_float(v[j + 2]) + b.z;
+                o.w = __uint_as_float(v[j + 3]) + b.w;
+                o.x = o.x > 0.0f ? o.x : 0.2f * o.x;
+                o.y = o.y > 0.0f ? o.y : 0.2f * o.y;
+                o.z = o.z > 0.0f ? o.z : 0.2f * o.z;
+                o.w = o.w > 0.0f ? o.w : 0.2f * o.w;
+                *reinterpret_cast<float4 *>(crow + c + j) = o;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// W[10368][512] -> K-major transposed hi / lo parts Wt[512][10368]
+__global__ void k_fc0_split_weights(const float *__restrict__ W, float *__restrict__ hi, float *__restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = W[(size_t)(k0 + r) * TC_N + n0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const float x = tile[tx][r];  // W[k0+tx][n0+r]
+        const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        hi[(size_t)(n0 + r) * TC_K + k0 + tx] = h;
+        lo[(size_t)(n0 + r) * TC_K + k0 + tx] = x - h;
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool encode_map(CUtensorMap *map, float *ptr, uint64_t rows, uint32_t box_rows) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+        fn = (PFN_encodeTiled)p;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)TC_K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)TC_K * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Fc0TcState {
+    CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+    float *a_hi_ptr = nullptr;
+    int a_rows = 0;
+    bool weights_ready = false;
+};
+
+static Fc0TcState *state_of(omk_ctx *c) {
+    if (!c->fc0_tc_state) c->fc0_tc_state = new Fc0TcState();
+    return reinterpret_cast<Fc0TcState *>(c->fc0_tc_state);
+}
+
+void fc0_tc_free(omk_ctx *c) {
+    delete reinterpret_cast<Fc0TcState *>(c->fc0_tc_state);
+    c->fc0_tc_state = nullptr;
+}
+
+// (re)build the split transposed weights; call after the fc0 weights change
+bool fc0_tc_prepare_weights(omk_ctx *c) {
+    Fc0TcState *s = state_of(c);
+    if (!c->net.fc0_wt_hi) {
+        if (cudaMalloc(&c->net.fc0_wt_hi, sizeof(float) * (size_t)TC_K * TC_N) != cudaSuccess) return false;
+        if (cudaMalloc(&c->net.fc0_wt_lo, sizeof(float) * (size_t)TC_K * TC_N) != cudaSuccess) return false;
+    }
+    k_fc0_split_weights<<<dim3(TC_K / 32, TC_N / 32), 256, 0, c->stream>>>(c->net.t[23], c->net.fc0_wt_hi, c->net.fc0_wt_lo);
+    c->launches++;
+    if (!encode_map(&s->map_b_hi, c->net.fc0_wt_hi, TC_N, TC_BN)) return false;
+    if (!encode_map(&s->map_b_lo, c->net.fc0_wt_lo, TC_N, TC_BN)) return false;
+    s->weights_ready = true;
+    return true;
+}
+
+bool launch_fc0_tc(omk_ctx *c, int rows_bound) {
+    Fc0TcState *s = state_of(c);
+    if (!s->weights_ready) return false;
+    if (s->a_hi_ptr != c->ws.act0_hi || s->a_rows != c->ws.max_rows) {
+        if (!encode_map(&s->map_a_hi, c->ws.act0_hi, (uint64_t)c->ws.max_rows, TC_BM)) return false;
+        if (!encode_map(&s->map_a_lo, c->ws.act0_lo, (uint64_t)c->ws.max_rows, TC_BM)) return false;
+        s->a_hi_ptr = c->ws.act0_hi;
+        s->a_rows = c->ws.max_rows;
+    }
+    cudaFuncSetAttribute(k_fc0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    const int mt = (rows_bound + TC_BM - 1) / TC_BM;
+    k_fc0_tc<<<dim3(TC_N / TC_BN, mt), TC_THREADS, TC_SMEM_BYTES, c->stream>>>(s->map_a_hi, s->map_a_lo, s->map_b_hi, s->map_b_lo,
+                                                                            c->net.t[24], c->ws.act1, c->ws.n_req, rows_bound);
+    c->launches++;
+    return true;
+}
+
+}  // namespace omk

@@ -95,7 +95,8 @@ __device__ __forceinline__ void gemm_n32(const float *A, const float *W, const f
 }
 
 __global__ void __launch_bounds__(kTowerThreads, 1)
-    k_tower(TowerWeights tw, const NNIn *nn_in, const float *images, const uint32_t *n_req, int max_rows, float *act0) {
+    k_tower(TowerWeights tw, const NNIn *nn_in, const float *images, const uint32_t *n_req, int max_rows, float *act0,
+            float *act0_hi, float *act0_lo) {
     extern __shared__ __align__(16) float sm[];
     const int t = threadIdx.x;
     const int rows = (int)min(*n_req, (uint32_t)max_rows);
@@ -222,10 +223,26 @@ __global__ void __launch_bounds__(kTowerThreads, 1)
             __syncthreads();
         }
         // ---- flatten NHWC: index = pixel*128 + channel (network.rs:127-137) ----
-        float *dst = act0 + (size_t)row * kFlat;
-        for (int idx = t; idx < kCells * 32; idx += kTowerThreads) {
-            const int pix = idx >> 5, c4 = (idx & 31) * 4;
-            *reinterpret_cast<float4 *>(dst + pix * kCh + c4) = *reinterpret_cast<const float4 *>(X + pix * kXStride + c4);
+        if (act0_hi) {
+            // tensor-core fc0: split every activation into a TF32-exact high part and its exact residual
+            float *dh = act0_hi + (size_t)row * kFlat, *dl = act0_lo + (size_t)row * kFlat;
+            for (int idx = t; idx < kCells * 32; idx += kTowerThreads) {
+                const int pix = idx >> 5, c4 = (idx & 31) * 4;
+                const float4 x = *reinterpret_cast<const float4 *>(X + pix * kXStride + c4);
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+                *reinterpret_cast<float4 *>(dh + pix * kCh + c4) = h;
+                *reinterpret_cast<float4 *>(dl + pix * kCh + c4) = l;
+            }
+        } else {
+            float *dst = act0 + (size_t)row * kFlat;
+            for (int idx = t; idx < kCells * 32; idx += kTowerThreads) {
+                const int pix = idx >> 5, c4 = (idx & 31) * 4;
+                *reinterpret_cast<float4 *>(dst + pix * kCh + c4) = *reinterpret_cast<const float4 *>(X + pix * kXStride + c4);
+            }
         }
         __syncthreads();
     }
@@ -418,13 +435,20 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     }
     const int tower_grid = max_rows < c->n_sms ? max_rows : c->n_sms;
     bool sp = prof_begin(c, OMK_K_TOWER, 2);
+    const bool tc = c->fc0_mode == 1;
     k_tower<<<tower_grid, kTowerThreads, kTowerSmemBytes, c->stream>>>(tw, c->ws.nn_in, images_dev, c->ws.n_req, max_rows,
-                                                                      c->ws.act0);
+                                                                      c->ws.act0, tc ? c->ws.act0_hi : nullptr,
+                                                                      tc ? c->ws.act0_lo : nullptr);
     prof_end(c, sp);
     const int mt = (max_rows + GM - 1) / GM;
     sp = prof_begin(c, OMK_K_FC0, 1);
-    k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act0, c->net.t[23], c->net.t[24], c->ws.act1, c->ws.n_req,
-                                                      max_rows, kFc, kFlat, 1);
+    if (tc) {
+        launch_fc0_tc(c, max_rows);
+        c->launches--;  // counted once below with the other network kernels
+    } else {
+        k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act0, c->net.t[23], c->net.t[24], c->ws.act1, c->ws.n_req,
+                                                          max_rows, kFc, kFlat, 1);
+    }
     prof_end(c, sp);
     sp = prof_begin(c, OMK_K_FC1, 2);
     k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act1, c->net.t[25], c->net.t[26], c->ws.act2, c->ws.n_req,

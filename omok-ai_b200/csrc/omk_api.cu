@@ -45,7 +45,8 @@ static int32_t ensure_workspace(omk_ctx *c, int rows) {
     CK(cudaStreamSynchronize(c->stream));
     Workspace &w = c->ws;
     cudaFree(w.nn_in); cudaFree(w.req_tree); cudaFree(w.req_node); cudaFree(w.P); cudaFree(w.V);
-    cudaFree(w.act0); cudaFree(w.act1); cudaFree(w.act2); cudaFree(w.logits);
+    cudaFree(w.act0); cudaFree(w.act1); cudaFree(w.act2); cudaFree(w.logits); cudaFree(w.act0_hi); cudaFree(w.act0_lo);
+    w.act0 = w.act0_hi = w.act0_lo = nullptr;
     w.max_rows = 0;
     CK(cudaMalloc(&w.nn_in, sizeof(NNIn) * (size_t)rows));
     CK(cudaMalloc(&w.req_tree, sizeof(uint32_t) * (size_t)rows));
@@ -53,6 +54,10 @@ static int32_t ensure_workspace(omk_ctx *c, int rows) {
     CK(cudaMalloc(&w.P, sizeof(float) * (size_t)rows * kRow));
     CK(cudaMalloc(&w.V, sizeof(float) * (size_t)rows));
     CK(cudaMalloc(&w.act0, sizeof(float) * (size_t)rows * 10368));
+    CK(cudaMalloc(&w.act0_hi, sizeof(float) * (size_t)rows * 10368));
+    CK(cudaMalloc(&w.act0_lo, sizeof(float) * (size_t)rows * 10368));
+    CK(cudaMemsetAsync(w.act0_hi, 0, sizeof(float) * (size_t)rows * 10368, c->stream));
+    CK(cudaMemsetAsync(w.act0_lo, 0, sizeof(float) * (size_t)rows * 10368, c->stream));
     CK(cudaMalloc(&w.act1, sizeof(float) * (size_t)rows * 512));
     CK(cudaMalloc(&w.act2, sizeof(float) * (size_t)rows * 512));
     CK(cudaMalloc(&w.logits, sizeof(float) * (size_t)rows * 128));
@@ -148,6 +153,7 @@ extern "C" int32_t omk_ctx_create(int32_t device, int32_t capacity_envs, int32_t
     c->cap_trees = capacity_trees;
     c->cap_nodes = capacity_nodes;
     c->seed = seed;
+    if (const char *m = getenv("OMK_FC0")) c->fc0_mode = (strcmp(m, "simt") == 0) ? 0 : 1;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -191,7 +197,8 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
     void *ptrs[] = {c->envs, c->tree_hdrs, c->tree_nodes, c->remap, c->dev_error, c->dev_sims, w.nn_in, w.req_tree,
                     w.req_node, w.P, w.V, w.act0, w.act1, w.act2, w.logits, w.n_req, w.slot_base, w.slot_count, w.ids,
                     w.actions, w.modes, w.temps, w.status, w.policy_out, w.streams, c->net.heads_w, c->net.heads_b,
-                    c->sp_ply, c->sp_buf};
+                    c->sp_ply, c->sp_buf, w.act0_hi, w.act0_lo, c->net.fc0_wt_hi, c->net.fc0_wt_lo};
+    fc0_tc_free(c);
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < kNetTensors; ++i) cudaFree(c->net.t[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -220,6 +227,7 @@ extern "C" int32_t omk_net_load_params(omk_ctx *c, const float *const *tensors, 
     for (int i = 0; i < kNetTensors; ++i)
         CK(cudaMemcpyAsync(c->net.t[i], tensors[i], sizeof(float) * (size_t)kLens[i], cudaMemcpyHostToDevice, c->stream));
     net_pack_heads(c);
+    if (!fc0_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core fc0 weight preparation failed");
     CK(cudaStreamSynchronize(c->stream));
     c->net.loaded = true;
     return OMK_OK;
@@ -238,6 +246,7 @@ extern "C" int32_t omk_net_init_random(omk_ctx *c, uint64_t seed) {
     CK(cudaSetDevice(c->device));
     launch_net_init_random(c, seed);
     net_pack_heads(c);
+    if (!fc0_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core fc0 weight preparation failed");
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     c->net.loaded = true;
@@ -290,6 +299,22 @@ extern "C" int32_t omk_net_eval_images(omk_ctx *c, const float *images, int32_t 
     rc = net_eval_common(c, n, d_img, out_p, out_v);
     cudaFree(d_img);
     return rc;
+}
+
+// ------------------------------------------------------------------ diagnostics
+extern "C" int32_t omk_debug_set_fc0_mode(omk_ctx *c, int32_t mode) {
+    if (mode != 0 && mode != 1) return fail(OMK_ERR_INVALID, "fc0 mode must be 0 (fp32 CUDA cores) or 1 (tcgen05 3xTF32)");
+    c->fc0_mode = mode;
+    return OMK_OK;
+}
+extern "C" int32_t omk_debug_get_buffer(omk_ctx *c, int32_t which, float *out, int64_t count) {
+    CK(cudaSetDevice(c->device));
+    const float *src = which == 0 ? c->ws.act0 : which == 1 ? c->ws.act1 : which == 2 ? c->ws.act2 : which == 3 ? c->ws.logits
+                     : which == 4 ? c->ws.act0_hi : which == 5 ? c->ws.act0_lo : nullptr;
+    if (!src || !out || count < 0) return fail(OMK_ERR_INVALID, "bad buffer id");
+    CK(cudaMemcpyAsync(out, src, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return OMK_OK;
 }
 
 // ------------------------------------------------------------------ environment

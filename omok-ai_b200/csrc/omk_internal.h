@@ -18,6 +18,8 @@ struct NetWeights {
     float *t[kNetTensors] = {};  // device copies in checkpoint order
     float *heads_w = nullptr;    // [512][128]: cols 0..80 policy, col 81 value, rest 0
     float *heads_b = nullptr;    // [128]
+    float *fc0_wt_hi = nullptr;  // [512][10368] K-major TF32-exact high part of fc0_w (tensor-core path)
+    float *fc0_wt_lo = nullptr;  // [512][10368] residual low part
     bool loaded = false;
 };
 
@@ -28,7 +30,9 @@ struct Workspace {  // evaluator request/response buffers, sized for max_rows
     uint32_t *req_node = nullptr; // [max_rows]
     float *P = nullptr;           // [max_rows][96]
     float *V = nullptr;           // [max_rows]
-    float *act0 = nullptr;        // [max_rows][10368] tower output == fc0 input
+    float *act0 = nullptr;        // [max_rows][10368] tower output == fc0 input (fp32 CUDA-core path)
+    float *act0_hi = nullptr;     // [max_rows][10368] TF32-exact high part (tensor-core path)
+    float *act0_lo = nullptr;     // [max_rows][10368] residual low part
     float *act1 = nullptr;        // [max_rows][512]
     float *act2 = nullptr;        // [max_rows][512]
     float *logits = nullptr;      // [max_rows][128]
@@ -71,6 +75,8 @@ struct omk_ctx {
 
     omk::NetWeights net;
     omk::Workspace ws;
+    int fc0_mode = 1;               // 0: fp32 CUDA-core k_gemm, 1: tcgen05 3xTF32 k_fc0_tc
+    void *fc0_tc_state = nullptr;   // tensor maps of the tensor-core path (fc0_tc.cu)
 
     // self-play driver state
     omk_selfplay_config sp_cfg{};
@@ -126,5 +132,10 @@ void prof_end(omk_ctx *c, bool opened);
 void net_forward(omk_ctx *c, const float *images_dev /* or nullptr: use ws.nn_in */, int max_rows);
 void net_pack_heads(omk_ctx *c);
 void launch_net_init_random(omk_ctx *c, uint64_t seed);
+
+// fc0_tc.cu
+bool fc0_tc_prepare_weights(omk_ctx *c);
+bool launch_fc0_tc(omk_ctx *c, int rows_bound);
+void fc0_tc_free(omk_ctx *c);
 
 }  // namespace omk
