@@ -35,6 +35,7 @@ GAMES_PER_GPU = 1024
 COUNT, BATCH, EPS, ALPHA, TEMP, TEMP_THRESHOLD = 800, 16, 0.25, 0.03, 1.0, 30
 CAP_NODES = 4096
 FLOP_FC0 = 2 * 10368 * 512
+FLOP_TOWER = 2 * (81 * 3 * 128 + 3 * 81 * (128 * 32 + 9 * 32 + 32 * 32 + 32 * 128))
 FLOP_POSITION = 15_906_240
 CPU_SAMPLE_TREES = 64
 
@@ -193,6 +194,7 @@ def main():
     import torch
 
     omk = importlib.import_module("omok-ai_b200")
+    sharding = importlib.import_module("omok-ai_b200.sharding")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -205,7 +207,7 @@ def main():
     games = args.games
     warm = max(3, args.warmup)
     steps = max(1, args.steps)
-    ctx = omk.Context(device=local_rank, capacity_envs=4, capacity_trees=2 * games, capacity_nodes=CAP_NODES, seed=1000 + rank)
+    ctx = omk.Context(device=local_rank, capacity_envs=4, capacity_trees=2 * games, capacity_nodes=CAP_NODES, seed=sharding.rank_seed(1000, rank))
     ctx.net_init_random(0)  # same random-init weights on every rank (no broadcast needed)
     ctx.selfplay_begin(games, COUNT, BATCH, EPS, ALPHA, TEMP, TEMP_THRESHOLD, omk.EVAL_NET)
 
@@ -253,21 +255,40 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    # ---- aggregate over ranks: max time, summed work ----
-    if dist:
-        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
-        w = torch.tensor([sims, positions, nn_evals, launches, e2e_sims], device="cuda", dtype=torch.float64)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        sims, positions, nn_evals, launches, e2e_sims = (int(x) for x in w.tolist())
+    # ---- aggregate over ranks: max time, summed work (the only cross-rank traffic of the whole run) ----
+    times, work = sharding.reduce_measurements(
+        {"ms": ms, "e2e_s": e2e_s},
+        {"sims": sims, "positions": positions, "nn_evals": nn_evals, "launches": launches, "e2e_sims": e2e_sims},
+        device="cuda" if dist else "cpu")
+    ms, e2e_s = times["ms"], times["e2e_s"]
+    sims, positions, nn_evals, launches, e2e_sims = (work[k] for k in ("sims", "positions", "nn_evals", "launches", "e2e_sims"))
 
     if rank == 0:
         peaks = read_peaks()
+        kinds = stats.by_kind()
+        tower_ms, tower_launches = kinds["tower"]
         rows_per_launch = (int(stats.nn_evals) / max(1, fc0_launches))
-        # fc0 launches also cover the (small) ensure_action batches; algorithmic flops = rows actually evaluated
+        # launches also cover the (small) ensure_action batches; algorithmic flops = rows actually evaluated
         fc0_tflops = (int(stats.nn_evals) * FLOP_FC0) / (fc0_ms * 1e-3) / 1e12 if fc0_ms > 0 else 0.0
+        tower_tflops = (int(stats.nn_evals) * FLOP_TOWER) / (tower_ms * 1e-3) / 1e12 if tower_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        fc0_tc = os.environ.get("OMK_FC0", "tc") != "simt"
+        roof_fc0 = {"bound": "tensor",
+                    "kernel": "k_fc0_tc (fc0 10368->512, tcgen05 kind::tf32, 3-pass hi/lo split, TMEM chunk promotion)" if fc0_tc
+                              else "k_gemm (fc0 10368->512, fp32 CUDA cores)",
+                    "achieved": fc0_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fc0_tflops / peak,
+                    "tensor_pipe_tflops": 3 * fc0_tflops if fc0_tc else 0.0,
+                    "tf32_peak_estimate": peak / 2,
+                    "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); TF32 runs at half the bf16 rate and "
+                                   "the fp32-accurate path issues 3 MMAs per product, so frac <= 1/6 by construction (DESIGN.md 3)",
+                    "avg_launch_ms": fc0_ms / max(1, fc0_launches), "rows_per_launch": rows_per_launch,
+                    "share_of_step": fc0_ms / float(stats.gpu_ms) if stats.gpu_ms else None, "traffic": None}
+        roof_tower = {"bound": "tensor", "kernel": "k_tower (stem + 3 bottleneck blocks, fp32 CUDA cores in shared memory)",
+                      "achieved": tower_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tower_tflops / peak,
+                      "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json)",
+                      "avg_launch_ms": tower_ms / max(1, tower_launches), "rows_per_launch": rows_per_launch,
+                      "share_of_step": tower_ms / float(stats.gpu_ms) if stats.gpu_ms else None, "traffic": None}
+        dominant, other = (roof_tower, roof_fc0) if tower_ms >= fc0_ms else (roof_fc0, roof_tower)
         line = {
             "metric": "mcts_simulations_per_sec", "value": sims / (ms * 1e-3), "unit": "simulations/s",
             "positions_per_sec": positions / (ms * 1e-3), "nn_evals_per_sec": nn_evals / (ms * 1e-3),
@@ -279,12 +300,8 @@ def main():
                     "d2h_bytes_per_step": d2h // e2e_steps,
                     "path": "omk_pool_search/sample/play/ensure_action/play per ply with host id+action buffers"},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "k_gemm (fc0 10368->512, fp32 CUDA cores)",
-                         "achieved": fc0_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fc0_tflops / peak,
-                         "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); fp32-accurate path, see DESIGN.md",
-                         "avg_launch_ms": fc0_ms / max(1, fc0_launches), "rows_per_launch": rows_per_launch,
-                         "share_of_step": fc0_ms / float(stats.gpu_ms) if stats.gpu_ms else None,
-                         "traffic": None},
+            "roofline": dominant,
+            "roofline_second": other,
         }
         if not args.no_cpu_baseline and world == 1:
             r = cpu_selfplay_sample(1, 0)

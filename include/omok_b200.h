@@ -198,7 +198,7 @@ typedef struct {
     int64_t h2d_bytes, d2h_bytes;
     float gpu_ms;           /* CUDA-event time of the whole call on the context stream */
     /* per-kernel-family CUDA-event time and launch count inside the call, indexed by OMK_K_*;
-     * filled according to the `profile` level (0: none, 1: fc0 only, 2: every family) */
+     * filled according to the `profile` level (0: none, 1: tower + fc0 only, 2: every family) */
     float kind_ms[OMK_K_COUNT];
     int64_t kind_launches[OMK_K_COUNT];
 } omk_selfplay_stats;

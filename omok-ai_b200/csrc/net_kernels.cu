@@ -434,7 +434,7 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
         tw.b1[r] = c->net.t[b + 4]; tw.w2[r] = c->net.t[b + 5]; tw.b2[r] = c->net.t[b + 6];
     }
     const int tower_grid = max_rows < c->n_sms ? max_rows : c->n_sms;
-    bool sp = prof_begin(c, OMK_K_TOWER, 2);
+    bool sp = prof_begin(c, OMK_K_TOWER, 1);
     const bool tc = c->fc0_mode == 1;
     k_tower<<<tower_grid, kTowerThreads, kTowerSmemBytes, c->stream>>>(tw, c->ws.nn_in, images_dev, c->ws.n_req, max_rows,
                                                                       c->ws.act0, tc ? c->ws.act0_hi : nullptr,

@@ -1,0 +1,30 @@
+"""The C++ host mirror (include/omok_b200.hpp) compiles and links against libomok_b200.so (CPU),
+and passes the reference-shaped tests on a GPU."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "test_host_mirror")
+
+
+def build(omk):
+    omk.build()
+    libdir = os.path.dirname(omk.lib_path())
+    subprocess.check_call(
+        ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cpp"),
+         "-o", EXE, "-L", libdir, "-l:libomok_b200.so", f"-Wl,-rpath,{libdir}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+
+
+def test_cpp_mirror_compiles_and_links(omk):
+    build(omk)
+    out = subprocess.run([EXE], capture_output=True, text=True)
+    assert out.returncode == 0 and "linked ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_runs_reference_tests(omk):
+    build(omk)
+    out = subprocess.run([EXE, "--run"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "cpp host mirror ok" in out.stdout, out.stdout + out.stderr
