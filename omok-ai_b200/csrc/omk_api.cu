@@ -400,6 +400,7 @@ extern "C" int32_t omk_env_set(omk_ctx *c, const int32_t *ids, int32_t n, const 
 
 extern "C" int32_t omk_env_encode(omk_ctx *c, const int32_t *ids, int32_t n, int32_t mode, float *out) {
     CK(cudaSetDevice(c->device));
+    if (n == 0) return OMK_OK;
     if (!out) return fail(OMK_ERR_INVALID, "out is NULL");
     const int32_t *d_ids;
     int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_envs);
