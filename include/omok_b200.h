@@ -101,6 +101,8 @@ OMK_API int32_t omk_net_eval_images(omk_ctx *ctx, const float *images, int32_t n
  * env OMK_FC0=simt|tc at context creation).  omk_debug_get_buffer copies an intermediate activation buffer
  * (0 fc0 input, 1 fc0 output, 2 fc1 output, 3 head logits, 4/5 fc0 input hi/lo parts) to the host.        */
 OMK_API int32_t omk_debug_set_fc0_mode(omk_ctx *ctx, int32_t mode);
+/* tower kernel choice, same convention (env OMK_TOWER=simt|tc) */
+OMK_API int32_t omk_debug_set_tower_mode(omk_ctx *ctx, int32_t mode);
 OMK_API int32_t omk_debug_get_buffer(omk_ctx *ctx, int32_t which, float *out, int64_t count);
 
 /* ---------------------------------------------------------------- environment

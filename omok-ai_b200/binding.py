@@ -104,6 +104,7 @@ def load_library():
     L.omk_net_eval.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.omk_net_eval_images.argtypes = [vp, vp, i32, vp, vp]
     L.omk_debug_set_fc0_mode.argtypes = [vp, i32]
+    L.omk_debug_set_tower_mode.argtypes = [vp, i32]
     L.omk_debug_get_buffer.argtypes = [vp, i32, vp, i64]
     L.omk_env_reset.argtypes = [vp, vp, i32]
     L.omk_env_step.argtypes = [vp, vp, vp, i32, vp, vp]
@@ -215,6 +216,9 @@ class Context:
 
     def debug_set_fc0_mode(self, mode: int):
         self._check(self.L.omk_debug_set_fc0_mode(self.h, mode))
+
+    def debug_set_tower_mode(self, mode: int):
+        self._check(self.L.omk_debug_set_tower_mode(self.h, mode))
 
     def debug_get_buffer(self, which: int, count: int):
         out = np.zeros(count, dtype=np.float32)

@@ -436,9 +436,14 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     const int tower_grid = max_rows < c->n_sms ? max_rows : c->n_sms;
     bool sp = prof_begin(c, OMK_K_TOWER, 1);
     const bool tc = c->fc0_mode == 1;
-    k_tower<<<tower_grid, kTowerThreads, kTowerSmemBytes, c->stream>>>(tw, c->ws.nn_in, images_dev, c->ws.n_req, max_rows,
-                                                                      c->ws.act0, tc ? c->ws.act0_hi : nullptr,
-                                                                      tc ? c->ws.act0_lo : nullptr);
+    if (c->tower_mode == 1) {
+        launch_tower_tc(c, images_dev, max_rows, tc);
+        c->launches--;  // counted once below with the other network kernels
+    } else {
+        k_tower<<<tower_grid, kTowerThreads, kTowerSmemBytes, c->stream>>>(tw, c->ws.nn_in, images_dev, c->ws.n_req, max_rows,
+                                                                          c->ws.act0, tc ? c->ws.act0_hi : nullptr,
+                                                                          tc ? c->ws.act0_lo : nullptr);
+    }
     prof_end(c, sp);
     const int mt = (max_rows + GM - 1) / GM;
     sp = prof_begin(c, OMK_K_FC0, 1);

@@ -154,6 +154,7 @@ extern "C" int32_t omk_ctx_create(int32_t device, int32_t capacity_envs, int32_t
     c->cap_nodes = capacity_nodes;
     c->seed = seed;
     if (const char *m = getenv("OMK_FC0")) c->fc0_mode = (strcmp(m, "simt") == 0) ? 0 : 1;
+    if (const char *m = getenv("OMK_TOWER")) c->tower_mode = (strcmp(m, "simt") == 0) ? 0 : 1;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -197,7 +198,8 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
     void *ptrs[] = {c->envs, c->tree_hdrs, c->tree_nodes, c->remap, c->dev_error, c->dev_sims, w.nn_in, w.req_tree,
                     w.req_node, w.P, w.V, w.act0, w.act1, w.act2, w.logits, w.n_req, w.slot_base, w.slot_count, w.ids,
                     w.actions, w.modes, w.temps, w.status, w.policy_out, w.streams, c->net.heads_w, c->net.heads_b,
-                    c->sp_ply, c->sp_buf, w.act0_hi, w.act0_lo, c->net.fc0_wt_hi, c->net.fc0_wt_lo};
+                    c->sp_ply, c->sp_buf, w.act0_hi, w.act0_lo, c->net.fc0_wt_hi, c->net.fc0_wt_lo, c->net.tower_wimg,
+                    c->net.tower_pimg};
     fc0_tc_free(c);
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < kNetTensors; ++i) cudaFree(c->net.t[i]);
@@ -228,6 +230,7 @@ extern "C" int32_t omk_net_load_params(omk_ctx *c, const float *const *tensors, 
         CK(cudaMemcpyAsync(c->net.t[i], tensors[i], sizeof(float) * (size_t)kLens[i], cudaMemcpyHostToDevice, c->stream));
     net_pack_heads(c);
     if (!fc0_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core fc0 weight preparation failed");
+    if (!tower_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core tower weight preparation failed");
     CK(cudaStreamSynchronize(c->stream));
     c->net.loaded = true;
     return OMK_OK;
@@ -247,6 +250,7 @@ extern "C" int32_t omk_net_init_random(omk_ctx *c, uint64_t seed) {
     launch_net_init_random(c, seed);
     net_pack_heads(c);
     if (!fc0_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core fc0 weight preparation failed");
+    if (!tower_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core tower weight preparation failed");
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     c->net.loaded = true;
@@ -305,6 +309,11 @@ extern "C" int32_t omk_net_eval_images(omk_ctx *c, const float *images, int32_t 
 extern "C" int32_t omk_debug_set_fc0_mode(omk_ctx *c, int32_t mode) {
     if (mode != 0 && mode != 1) return fail(OMK_ERR_INVALID, "fc0 mode must be 0 (fp32 CUDA cores) or 1 (tcgen05 3xTF32)");
     c->fc0_mode = mode;
+    return OMK_OK;
+}
+extern "C" int32_t omk_debug_set_tower_mode(omk_ctx *c, int32_t mode) {
+    if (mode != 0 && mode != 1) return fail(OMK_ERR_INVALID, "tower mode must be 0 (fp32 CUDA cores) or 1 (tcgen05 3xTF32)");
+    c->tower_mode = mode;
     return OMK_OK;
 }
 extern "C" int32_t omk_debug_get_buffer(omk_ctx *c, int32_t which, float *out, int64_t count) {

@@ -20,6 +20,8 @@ struct NetWeights {
     float *heads_b = nullptr;    // [128]
     float *fc0_wt_hi = nullptr;  // [512][10368] K-major TF32-exact high part of fc0_w (tensor-core path)
     float *fc0_wt_lo = nullptr;  // [512][10368] residual low part
+    uint8_t *tower_wimg = nullptr;  // 3 x 72 KB pre-swizzled B-operand images of the tower weights (tower_tc.cu)
+    float *tower_pimg = nullptr;    // fp32 stem / bias / depthwise parameters
     bool loaded = false;
 };
 
@@ -77,6 +79,7 @@ struct omk_ctx {
     omk::Workspace ws;
     int fc0_mode = 1;               // 0: fp32 CUDA-core k_gemm, 1: tcgen05 3xTF32 k_fc0_tc
     void *fc0_tc_state = nullptr;   // tensor maps of the tensor-core path (fc0_tc.cu)
+    int tower_mode = 1;             // 0: fp32 CUDA-core k_tower, 1: tcgen05 3xTF32 k_tower_tc
 
     // self-play driver state
     omk_selfplay_config sp_cfg{};
@@ -137,5 +140,9 @@ void launch_net_init_random(omk_ctx *c, uint64_t seed);
 bool fc0_tc_prepare_weights(omk_ctx *c);
 bool launch_fc0_tc(omk_ctx *c, int rows_bound);
 void fc0_tc_free(omk_ctx *c);
+
+// tower_tc.cu
+bool tower_tc_prepare_weights(omk_ctx *c);
+void launch_tower_tc(omk_ctx *c, const float *images_dev, int rows_bound, bool split_out);
 
 }  // namespace omk
