@@ -104,6 +104,9 @@ __device__ __forceinline__ void tw_store_split16(uint32_t taddr_hi, uint32_t tad
     tw_st16(taddr_lo, lo);
 }
 __device__ __forceinline__ float tw_lrelu(float v) { return v > 0.0f ? v : 0.2f * v; }
+// column of the a-th 32-column partial accumulator used by conv0 / conv1: D12, four slices of the (then idle) D3
+// region, and the 32 spare columns at the top
+__device__ __forceinline__ constexpr uint32_t conv0_acc(int a) { return a == 0 ? C_D12 : (a < 5 ? C_D3 + 32u * (uint32_t)(a - 1) : 480u); }
 
 __device__ __forceinline__ void tw_bulk_load(uint32_t dst, const uint8_t *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
     if (t == 0) {
         tw_mbar_init(bar_w0, 1);
         tw_mbar_init(bar_w0 + 8, 1);
-        tw_mbar_init(bar_mma, 1);
+        tw_mbar_init(bar_mma, 8);  // one tcgen05.commit per warp: every warp's lane 0 issues its own MMA chain
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -196,17 +199,23 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             // ================= conv0: 1x1 128 -> 32 (A = X in TMEM) =================
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
-            if (t == 0) {
+            if (lane == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue_weights(g + 1);  // the other buffer's last reader (block g-1) has completed
-                tw_mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+                if (warp == 0) issue_weights(g + 1);  // the other buffer's last reader (block g-1) has completed
+                if (warp < 6) {
+                    // six independent accumulator chains (3 products x 2 K-halves), one per issuing warp: the single-thread
+                    // issue path costs ~60 clk per MMA, so the chains are issued in parallel from six threads
+                    tw_mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+                    const int pass = warp >> 1, h = warp & 1;
+                    const uint32_t acol = pass == 0 ? C_XLO : C_XHI;
+                    const uint32_t bimg = pass == 1 ? WI_W0LO : WI_W0HI;
 #pragma unroll 1
-                for (int ks = 0; ks < 16; ++ks) {
-                    const uint32_t boff = (uint32_t)((ks >> 2) * 4096 + (ks & 3) * 32);
-                    const uint64_t bhi = tw_desc_sw128(wb + WI_W0HI + boff), blo = tw_desc_sw128(wb + WI_W0LO + boff);
-                    tw_umma_ts(tmem_base + C_D12, tmem_base + C_XLO + ks * 8, bhi, TW_IDESC_N32, ks != 0);
-                    tw_umma_ts(tmem_base + C_D12, tmem_base + C_XHI + ks * 8, blo, TW_IDESC_N32, 1u);
-                    tw_umma_ts(tmem_base + C_D12, tmem_base + C_XHI + ks * 8, bhi, TW_IDESC_N32, 1u);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const int kk = ks + 8 * h;
+                        const uint32_t boff = (uint32_t)((kk >> 2) * 4096 + (kk & 3) * 32);
+                        tw_umma_ts(tmem_base + conv0_acc(warp), tmem_base + acol + kk * 8, tw_desc_sw128(wb + bimg + boff),
+                                   TW_IDESC_N32, ks != 0);
+                    }
                 }
                 tw_commit(bar_mma);
             }
@@ -217,7 +226,14 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             // epilogue 1: + b0, lrelu -> fp32 tile for the depthwise stencil (this thread: 16 channels of its pixel)
             {
                 float d[16];
-                tw_ld16(tlane + C_D12 + half * 16, d);
+                tw_ld16(tlane + conv0_acc(0) + half * 16, d);
+#pragma unroll
+                for (int a = 1; a < 6; ++a) {
+                    float e[16];
+                    tw_ld16(tlane + conv0_acc(a) + half * 16, e);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) d[c] += e[c];
+                }
 #pragma unroll
                 for (int c = 0; c < 16; c += 4) {
                     const float4 b = *reinterpret_cast<const float4 *>(bp + PI_B0 + half * 16 + c);
@@ -265,14 +281,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             // ================= conv1 pointwise: 1x1 32 -> 32 (A = H in TMEM) =================
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
-            if (t == 0) {
+            if (lane == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp < 3) {  // one product per issuing warp, three accumulators
+                    const uint32_t acol = warp == 0 ? C_HLO : C_HHI;
+                    const uint32_t bimg = warp == 1 ? WI_PWLO : WI_PWHI;
 #pragma unroll 1
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t bhi = tw_desc_sw128(wb + WI_PWHI + ks * 32), blo = tw_desc_sw128(wb + WI_PWLO + ks * 32);
-                    tw_umma_ts(tmem_base + C_D12, tmem_base + C_HLO + ks * 8, bhi, TW_IDESC_N32, ks != 0);
-                    tw_umma_ts(tmem_base + C_D12, tmem_base + C_HHI + ks * 8, blo, TW_IDESC_N32, 1u);
-                    tw_umma_ts(tmem_base + C_D12, tmem_base + C_HHI + ks * 8, bhi, TW_IDESC_N32, 1u);
+                    for (int ks = 0; ks < 4; ++ks)
+                        tw_umma_ts(tmem_base + conv0_acc(warp), tmem_base + acol + ks * 8, tw_desc_sw128(wb + bimg + ks * 32),
+                                   TW_IDESC_N32, ks != 0);
                 }
                 tw_commit(bar_mma);
             }
@@ -281,24 +298,28 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             {   // epilogue 2: + b1, lrelu -> A operand of conv2
-                float d[16];
-                tw_ld16(tlane + C_D12 + half * 16, d);
+                float d[16], e[16], f[16];
+                tw_ld16(tlane + conv0_acc(0) + half * 16, d);
+                tw_ld16(tlane + conv0_acc(1) + half * 16, e);
+                tw_ld16(tlane + conv0_acc(2) + half * 16, f);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) d[c] = tw_lrelu(d[c] + bp[PI_B1 + half * 16 + c]);
+                for (int c = 0; c < 16; ++c) d[c] = tw_lrelu((d[c] + e[c]) + f[c] + bp[PI_B1 + half * 16 + c]);
                 tw_store_split16(tlane + C_HHI + half * 16, tlane + C_HLO + half * 16, d);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             // ================= conv2: 1x1 32 -> 128 (A = H in TMEM), + x, lrelu =================
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
-            if (t == 0) {
+            if (lane == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp == 0) {  // N = 128 MMAs are tensor-bound (64 clk each): one chain
 #pragma unroll 1
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t bhi = tw_desc_sw128(wb + WI_W2HI + ks * 32), blo = tw_desc_sw128(wb + WI_W2LO + ks * 32);
-                    tw_umma_ts(tmem_base + C_D3, tmem_base + C_HLO + ks * 8, bhi, TW_IDESC_N128, ks != 0);
-                    tw_umma_ts(tmem_base + C_D3, tmem_base + C_HHI + ks * 8, blo, TW_IDESC_N128, 1u);
-                    tw_umma_ts(tmem_base + C_D3, tmem_base + C_HHI + ks * 8, bhi, TW_IDESC_N128, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t bhi = tw_desc_sw128(wb + WI_W2HI + ks * 32), blo = tw_desc_sw128(wb + WI_W2LO + ks * 32);
+                        tw_umma_ts(tmem_base + C_D3, tmem_base + C_HLO + ks * 8, bhi, TW_IDESC_N128, ks != 0);
+                        tw_umma_ts(tmem_base + C_D3, tmem_base + C_HHI + ks * 8, blo, TW_IDESC_N128, 1u);
+                        tw_umma_ts(tmem_base + C_D3, tmem_base + C_HHI + ks * 8, bhi, TW_IDESC_N128, 1u);
+                    }
                 }
                 tw_commit(bar_mma);
             }
