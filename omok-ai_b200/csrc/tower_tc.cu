@@ -74,17 +74,15 @@ __device__ __forceinline__ void tw_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
 __device__ __forceinline__ void tw_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// asynchronous TMEM load of 16 columns of this thread's lane; results are valid after tw_wait_ld()
 __device__ __forceinline__ void tw_ld16(uint32_t taddr, float *v) {
-    uint32_t r[16];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tw_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tw_st16(uint32_t taddr, const uint32_t *r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -123,7 +121,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
     if ((int)blockIdx.x >= rows) return;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int q = warp & 3, half = warp >> 2;
-    const int p = q * 32 + lane;  // pixel row owned by this thread (TMEM lane)
+    // pixel row owned by this thread == its TMEM lane (a warp reaches only its own lane quadrant).  Dealing pixels
+    // round-robin over the quadrants was measured slower: SIMT width is wasted either way, and it adds smem traffic.
+    const int p = q * 32 + lane;
     const bool real = p < kCells;
 
     uint8_t *sm = tw_smem_raw + ((1024u - (tw_smem_u32(tw_smem_raw) & 1023u)) & 1023u);
@@ -225,15 +225,13 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // epilogue 1: + b0, lrelu -> fp32 tile for the depthwise stencil (this thread: 16 channels of its pixel)
             {
-                float d[16];
+                float d[16], e[5][16];
                 tw_ld16(tlane + conv0_acc(0) + half * 16, d);
 #pragma unroll
-                for (int a = 1; a < 6; ++a) {
-                    float e[16];
-                    tw_ld16(tlane + conv0_acc(a) + half * 16, e);
+                for (int a = 1; a < 6; ++a) tw_ld16(tlane + conv0_acc(a) + half * 16, e[a - 1]);
+                tw_wait_ld();  // one wait for all six partial accumulators
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) d[c] += e[c];
-                }
+                for (int c = 0; c < 16; ++c) d[c] = ((d[c] + e[0][c]) + (e[1][c] + e[2][c])) + (e[3][c] + e[4][c]);
 #pragma unroll
                 for (int c = 0; c < 16; c += 4) {
                     const float4 b = *reinterpret_cast<const float4 *>(bp + PI_B0 + half * 16 + c);
@@ -302,6 +300,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                 tw_ld16(tlane + conv0_acc(0) + half * 16, d);
                 tw_ld16(tlane + conv0_acc(1) + half * 16, e);
                 tw_ld16(tlane + conv0_acc(2) + half * 16, f);
+                tw_wait_ld();
 #pragma unroll
                 for (int c = 0; c < 16; ++c) d[c] = tw_lrelu((d[c] + e[c]) + f[c] + bp[PI_B1 + half * 16 + c]);
                 tw_store_split16(tlane + C_HHI + half * 16, tlane + C_HLO + half * 16, d);
@@ -327,13 +326,17 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             ++mma_uses;
             __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {   // epilogue 3: x = lrelu(conv2 + b2 + x), next block's A operand
+                float d[64];
 #pragma unroll
-            for (int c = 0; c < 64; c += 16) {  // epilogue 3: x = lrelu(conv2 + b2 + x), next block's A operand
-                float d[16];
-                tw_ld16(tlane + C_D3 + half * 64 + c, d);
+                for (int c = 0; c < 64; c += 16) tw_ld16(tlane + C_D3 + half * 64 + c, d + c);
+                tw_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[c + i] = real ? tw_lrelu(d[i] + bp[PI_B2 + half * 64 + c + i] + x[c + i]) : 0.0f;
-                if (r < 2) tw_store_split16(tlane + C_XHI + half * 64 + c, tlane + C_XLO + half * 64 + c, x + c);
+                for (int c = 0; c < 64; c += 16) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) x[c + i] = real ? tw_lrelu(d[c + i] + bp[PI_B2 + half * 64 + c + i] + x[c + i]) : 0.0f;
+                    if (r < 2) tw_store_split16(tlane + C_XHI + half * 64 + c, tlane + C_XLO + half * 64 + c, x + c);
+                }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
