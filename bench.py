@@ -283,7 +283,11 @@ def main():
                                    "the fp32-accurate path issues 3 MMAs per product, so frac <= 1/6 by construction (DESIGN.md 3)",
                     "avg_launch_ms": fc0_ms / max(1, fc0_launches), "rows_per_launch": rows_per_launch,
                     "share_of_step": fc0_ms / float(stats.gpu_ms) if stats.gpu_ms else None, "traffic": None}
-        roof_tower = {"bound": "tensor", "kernel": "k_tower (stem + 3 bottleneck blocks, fp32 CUDA cores in shared memory)",
+        tower_tc = os.environ.get("OMK_TOWER", "tc") != "simt"
+        roof_tower = {"bound": "tensor",
+                      "kernel": "k_tower_tc (stem + 3 bottleneck blocks; 1x1 convs on tcgen05 kind::tf32 3-pass with activations as TMEM A operand, "
+                                "depthwise 3x3 + activations on CUDA cores)" if tower_tc
+                                else "k_tower (stem + 3 bottleneck blocks, fp32 CUDA cores in shared memory)",
                       "achieved": tower_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tower_tflops / peak,
                       "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json)",
                       "avg_launch_ms": tower_ms / max(1, tower_launches), "rows_per_launch": rows_per_launch,
