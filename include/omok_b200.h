@@ -103,6 +103,8 @@ OMK_API int32_t omk_net_eval_images(omk_ctx *ctx, const float *images, int32_t n
 OMK_API int32_t omk_debug_set_fc0_mode(omk_ctx *ctx, int32_t mode);
 /* tower kernel choice, same convention (env OMK_TOWER=simt|tc) */
 OMK_API int32_t omk_debug_set_tower_mode(omk_ctx *ctx, int32_t mode);
+/* clock64 phase timestamps of one position inside k_tower_tc (64 values; tools/check_tower_tc.py --timing) */
+OMK_API int32_t omk_debug_tower_timing(omk_ctx *ctx, int64_t *out64);
 OMK_API int32_t omk_debug_get_buffer(omk_ctx *ctx, int32_t which, float *out, int64_t count);
 
 /* ---------------------------------------------------------------- environment

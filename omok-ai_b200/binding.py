@@ -106,6 +106,7 @@ def load_library():
     L.omk_debug_set_fc0_mode.argtypes = [vp, i32]
     L.omk_debug_set_tower_mode.argtypes = [vp, i32]
     L.omk_debug_get_buffer.argtypes = [vp, i32, vp, i64]
+    L.omk_debug_tower_timing.argtypes = [vp, vp]
     L.omk_env_reset.argtypes = [vp, vp, i32]
     L.omk_env_step.argtypes = [vp, vp, vp, i32, vp, vp]
     L.omk_env_step_device.argtypes = [vp, vp, i32, vp, vp]
@@ -219,6 +220,11 @@ class Context:
 
     def debug_set_tower_mode(self, mode: int):
         self._check(self.L.omk_debug_set_tower_mode(self.h, mode))
+
+    def debug_tower_timing(self):
+        out = np.zeros(64, dtype=np.int64)
+        self._check(self.L.omk_debug_tower_timing(self.h, _ptr(out)))
+        return out
 
     def debug_get_buffer(self, which: int, count: int):
         out = np.zeros(count, dtype=np.float32)

@@ -316,6 +316,12 @@ extern "C" int32_t omk_debug_set_tower_mode(omk_ctx *c, int32_t mode) {
     c->tower_mode = mode;
     return OMK_OK;
 }
+extern "C" int32_t omk_debug_tower_timing(omk_ctx *c, int64_t *out64) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    tower_tc_read_timing(reinterpret_cast<long long *>(out64));
+    return OMK_OK;
+}
 extern "C" int32_t omk_debug_get_buffer(omk_ctx *c, int32_t which, float *out, int64_t count) {
     CK(cudaSetDevice(c->device));
     const float *src = which == 0 ? c->ws.act0 : which == 1 ? c->ws.act1 : which == 2 ? c->ws.act2 : which == 3 ? c->ws.logits

@@ -144,5 +144,6 @@ void fc0_tc_free(omk_ctx *c);
 // tower_tc.cu
 bool tower_tc_prepare_weights(omk_ctx *c);
 void launch_tower_tc(omk_ctx *c, const float *images_dev, int rows_bound, bool split_out);
+void tower_tc_read_timing(long long *out64);
 
 }  // namespace omk

@@ -101,7 +101,9 @@ __device__ __forceinline__ void tw_store_split16(uint32_t taddr_hi, uint32_t tad
     tw_st16(taddr_hi, hi);
     tw_st16(taddr_lo, lo);
 }
-__device__ __forceinline__ float tw_lrelu(float v) { return v > 0.0f ? v : 0.2f * v; }
+__device__ long long g_tw_dbg[64];  // phase timestamps of CTA 0's second position (omk_debug_tower_timing)
+#define TW_STAMP(i) do { if (dbg_on && t == 0) g_tw_dbg[(i)] = clock64(); } while (0)
+__device__ __forceinline__ float tw_lrelu(float v) { return fmaxf(v, 0.2f * v); }  // alpha < 1: max(v, alpha v)
 // column of the a-th 32-column partial accumulator used by conv0 / conv1: D12, four slices of the (then idle) D3
 // region, and the 32 spare columns at the top
 __device__ __forceinline__ constexpr uint32_t conv0_acc(int a) { return a == 0 ? C_D12 : (a < 5 ? C_D3 + 32u * (uint32_t)(a - 1) : 480u); }
@@ -161,21 +163,29 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
     };
     if (t == 0) issue_weights(0);
 
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    NNIn cur_in{};
+    if (!images) cur_in = nn_in[blockIdx.x];
+    int pos_iter = 0;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x, ++pos_iter) {
+        const bool dbg_on = blockIdx.x == 0 && pos_iter == 1;
+        TW_STAMP(0);
         // ---- input image (the reference's 243-float slot read as [81][3]) ----
         if (t < 243) {
             if (images) {
                 IMG[t] = images[(size_t)row * 243 + t];
             } else {
-                const NNIn in = nn_in[row];
-                IMG[t] = image_value(in.black, in.white, in.meta & 1u, (in.meta >> 1) & 1u, t);
+                IMG[t] = image_value(cur_in.black, cur_in.white, cur_in.meta & 1u, (cur_in.meta >> 1) & 1u, t);
             }
         }
+        // prefetch the next position's request row: its global-load latency hides behind this whole position
+        if (!images && row + (int)gridDim.x < rows) cur_in = nn_in[row + gridDim.x];
         __syncthreads();
+        TW_STAMP(40);
         // ---- stem 1x1 conv 3 -> 128 (network.rs:65-79): this thread's pixel, its 64 channels ----
         float x[64];
         {
-            const float v0 = real ? IMG[3 * p] : 0.0f, v1 = real ? IMG[3 * p + 1] : 0.0f, v2 = real ? IMG[3 * p + 2] : 0.0f;
+            const int pc = real ? p : 0;  // padded rows recompute pixel 0 (harmless, never stored)
+            const float v0 = IMG[3 * pc], v1 = IMG[3 * pc + 1], v2 = IMG[3 * pc + 2];
 #pragma unroll
             for (int c = 0; c < 64; c += 4) {
                 const int ch = half * 64 + c;
@@ -183,15 +193,18 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                 const float4 w0 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + ch);
                 const float4 w1 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + 128 + ch);
                 const float4 w2 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + 256 + ch);
-                x[c + 0] = real ? tw_lrelu(fmaf(v2, w2.x, fmaf(v1, w1.x, fmaf(v0, w0.x, b.x)))) : 0.0f;
-                x[c + 1] = real ? tw_lrelu(fmaf(v2, w2.y, fmaf(v1, w1.y, fmaf(v0, w0.y, b.y)))) : 0.0f;
-                x[c + 2] = real ? tw_lrelu(fmaf(v2, w2.z, fmaf(v1, w1.z, fmaf(v0, w0.z, b.z)))) : 0.0f;
-                x[c + 3] = real ? tw_lrelu(fmaf(v2, w2.w, fmaf(v1, w1.w, fmaf(v0, w0.w, b.w)))) : 0.0f;
+                x[c + 0] = tw_lrelu(fmaf(v2, w2.x, fmaf(v1, w1.x, fmaf(v0, w0.x, b.x))));
+                x[c + 1] = tw_lrelu(fmaf(v2, w2.y, fmaf(v1, w1.y, fmaf(v0, w0.y, b.y))));
+                x[c + 2] = tw_lrelu(fmaf(v2, w2.z, fmaf(v1, w1.z, fmaf(v0, w0.z, b.z))));
+                x[c + 3] = tw_lrelu(fmaf(v2, w2.w, fmaf(v1, w1.w, fmaf(v0, w0.w, b.w))));
             }
+            TW_STAMP(41);
 #pragma unroll
             for (int c = 0; c < 64; c += 16) tw_store_split16(tlane + C_XHI + half * 64 + c, tlane + C_XLO + half * 64 + c, x + c);
+            TW_STAMP(42);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        TW_STAMP(1);
 
         for (int r = 0; r < 3; ++r, ++g) {
             const float *bp = PAR + PI_BLK0 + r * PI_BLK;
@@ -223,6 +236,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             ++mma_uses;
             __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 0);
             // epilogue 1: + b0, lrelu -> fp32 tile for the depthwise stencil (this thread: 16 channels of its pixel)
             {
                 float d[16], e[5][16];
@@ -244,6 +258,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                 }
             }
             __syncthreads();
+            TW_STAMP(2 + r * 8 + 1);
             // conv1 depthwise 3x3, SAME zero padding, no bias (lib.rs:204-216) -> A operand of the pointwise conv
             {
                 float a[16];
@@ -276,6 +291,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                 tw_store_split16(tlane + C_HHI + half * 16, tlane + C_HLO + half * 16, a);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 2);
             // ================= conv1 pointwise: 1x1 32 -> 32 (A = H in TMEM) =================
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
@@ -295,6 +311,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             ++mma_uses;
             __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 3);
             {   // epilogue 2: + b1, lrelu -> A operand of conv2
                 float d[16], e[16], f[16];
                 tw_ld16(tlane + conv0_acc(0) + half * 16, d);
@@ -302,10 +319,17 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                 tw_ld16(tlane + conv0_acc(2) + half * 16, f);
                 tw_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 16; ++c) d[c] = tw_lrelu((d[c] + e[c]) + f[c] + bp[PI_B1 + half * 16 + c]);
+                for (int c = 0; c < 16; c += 4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(bp + PI_B1 + half * 16 + c);
+                    d[c + 0] = tw_lrelu((d[c + 0] + e[c + 0]) + f[c + 0] + b.x);
+                    d[c + 1] = tw_lrelu((d[c + 1] + e[c + 1]) + f[c + 1] + b.y);
+                    d[c + 2] = tw_lrelu((d[c + 2] + e[c + 2]) + f[c + 2] + b.z);
+                    d[c + 3] = tw_lrelu((d[c + 3] + e[c + 3]) + f[c + 3] + b.w);
+                }
                 tw_store_split16(tlane + C_HHI + half * 16, tlane + C_HLO + half * 16, d);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 4);
             // ================= conv2: 1x1 32 -> 128 (A = H in TMEM), + x, lrelu =================
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
@@ -326,6 +350,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             ++mma_uses;
             __syncwarp();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 5);
             {   // epilogue 3: x = lrelu(conv2 + b2 + x), next block's A operand
                 float d[64];
 #pragma unroll
@@ -334,13 +359,21 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
 #pragma unroll
                 for (int c = 0; c < 64; c += 16) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) x[c + i] = real ? tw_lrelu(d[c + i] + bp[PI_B2 + half * 64 + c + i] + x[c + i]) : 0.0f;
+                    for (int i = 0; i < 16; i += 4) {  // padded rows (p >= 81) carry harmless garbage; they are never stored
+                        const float4 b = *reinterpret_cast<const float4 *>(bp + PI_B2 + half * 64 + c + i);
+                        x[c + i + 0] = tw_lrelu(d[c + i + 0] + b.x + x[c + i + 0]);
+                        x[c + i + 1] = tw_lrelu(d[c + i + 1] + b.y + x[c + i + 1]);
+                        x[c + i + 2] = tw_lrelu(d[c + i + 2] + b.z + x[c + i + 2]);
+                        x[c + i + 3] = tw_lrelu(d[c + i + 3] + b.w + x[c + i + 3]);
+                    }
                     if (r < 2) tw_store_split16(tlane + C_XHI + half * 64 + c, tlane + C_XLO + half * 64 + c, x + c);
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 6);
         }
         // ---- flatten NHWC (network.rs:127-137): this thread's pixel row, its 64 channels ----
+        TW_STAMP(30);
         if (real) {
             const size_t off = (size_t)row * 10368 + (size_t)p * 128 + half * 64;
             if (act0_hi) {
@@ -361,6 +394,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             }
         }
     }
+    // (timestamps: 0 start, 1 stem done, then per block: conv0 done, E1+sync, dw stored, conv1 done, E2 stored, conv2 done, E3 stored)
     // drain the weight prefetch that was issued one block ahead, then release TMEM
     if (t == 0) tw_mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -435,6 +469,8 @@ bool tower_tc_prepare_weights(omk_ctx *c) {
     c->launches++;
     return true;
 }
+
+void tower_tc_read_timing(long long *out64) { cudaMemcpyFromSymbol(out64, g_tw_dbg, sizeof(long long) * 64); }
 
 void launch_tower_tc(omk_ctx *c, const float *images_dev, int rows_bound, bool split_out) {
     cudaFuncSetAttribute(k_tower_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM_BYTES);

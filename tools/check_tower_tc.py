@@ -44,3 +44,13 @@ for mode in (0, 1):
     p, v = out[mode][0][:64], out[mode][1][:64]
     big = rp > 1e-12
     print("tower mode", mode, "max rel P vs fp64", np.max(np.abs(p[big] - rp[big]) / rp[big]), "max rel V", np.max(np.abs(v - rv) / np.maximum(np.abs(rv), 1e-3)))
+
+# phase timing of one position (clock64 stamps inside k_tower_tc)
+ts = ctx.debug_tower_timing()
+names = ["start", "stem"] + [f"b{r}:{n}" for r in range(3) for n in ("conv0", "E1+sync", "dw+st", "conv1", "E2+st", "conv2", "E3+st", "-")]
+prev = ts[0]
+for i in list(range(0, 2)) + [2 + r * 8 + k for r in range(3) for k in range(7)] + [30]:
+    nm = names[i] if i < len(names) else "before store"
+    print(f"{nm:12s} +{int(ts[i] - prev):6d}  (t={int(ts[i] - ts[0])})")
+    prev = ts[i]
+print("stem detail: img+sync", int(ts[40]-ts[0]), "math", int(ts[41]-ts[40]), "split+st issue", int(ts[42]-ts[41]), "wait::st", int(ts[1]-ts[42]))
