@@ -99,7 +99,7 @@ OMK_API int32_t omk_net_eval_images(omk_ctx *ctx, const float *images, int32_t n
 /* ---------------------------------------------------------------- diagnostics (tests / A-B runs)
  * fc0 kernel choice: 0 = fp32 CUDA-core GEMM, 1 = tcgen05 kind::tf32 with 3-pass error compensation (default;
  * env OMK_FC0=simt|tc at context creation).  omk_debug_get_buffer copies an intermediate activation buffer
- * (0 fc0 input, 1 fc0 output, 2 fc1 output, 3 head logits, 4/5 fc0 input hi/lo parts) to the host.        */
+ * (0 fc0 input, 1 fc0 output [CUDA-core path], 2 fc1 output, 3 head logits, 4/5 fc0 input hi/lo parts, 6/7 fc0 output hi/lo parts) to the host.        */
 OMK_API int32_t omk_debug_set_fc0_mode(omk_ctx *ctx, int32_t mode);
 /* tower kernel choice, same convention (env OMK_TOWER=simt|tc) */
 OMK_API int32_t omk_debug_set_tower_mode(omk_ctx *ctx, int32_t mode);

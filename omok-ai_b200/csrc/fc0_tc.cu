@@ -29,17 +29,16 @@
 namespace omk {
 
 constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
-constexpr int TC_K = 10368, TC_N = 512;
-constexpr int TC_NKB = TC_K / TC_BK;  // 324
+constexpr int TC_K = 10368, TC_N = 512;   // fc0
+constexpr int TC_K1 = 512;                // fc1 (512 -> 512) runs through the same kernel template
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;  // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 96 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*barriers*/ + 1024 /*alignment slack*/;
 constexpr int TC_THREADS = 320;
 constexpr uint32_t TC_TMEM_COLS = 512;
-constexpr int TC_CHUNK = 9;                      // k-blocks accumulated in TMEM before promotion
-constexpr int TC_NCHUNK = TC_NKB / TC_CHUNK;     // 36
-static_assert(TC_NKB % TC_CHUNK == 0, "chunking must tile K");
+constexpr int TC_CHUNK0 = 9;   // fc0: k-blocks accumulated in TMEM before promotion (324 = 36 x 9)
+constexpr int TC_CHUNK1 = 8;   // fc1: 16 = 2 x 8
 // instruction descriptor: D=F32 (bit 4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
@@ -94,10 +93,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// K = inner dimension, CHUNK = k-blocks per TMEM accumulation chunk.  Output: C (fp32) and/or its TF32 hi/lo split
+// (C_hi/C_lo, the A operand of the next tensor-core layer); any of the three may be null.
+template <int K, int CHUNK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    k_fc0_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-             const float *__restrict__ bias, float *__restrict__ C, const uint32_t *n_req, int max_rows) {
+    k_fc_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+            const float *__restrict__ bias, float *__restrict__ C, float *__restrict__ C_hi, float *__restrict__ C_lo,
+            const uint32_t *n_req, int max_rows) {
+    constexpr int TC_NKB = K / TC_BK;
+    constexpr int TC_CHUNK = CHUNK;
+    constexpr int TC_NCHUNK = TC_NKB / TC_CHUNK;
+    static_assert(TC_NKB % TC_CHUNK == 0, "chunking must tile K");
     extern __shared__ uint8_t smem_raw[];
     const int rows = (int)min(*n_req, (uint32_t)max_rows);
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty0 + 8 * buf) : "memory");
         }
         const int row = m0 + q * 32 + lane;
-        float *crow = C + (size_t)row * TC_N + n0 + half * 128;
+        const size_t coff = (size_t)row * TC_N + n0 + half * 128;
         const float *brow = bias + n0 + half * 128;
 #pragma unroll
         for (int j = 0; j < 128; j += 4) {
@@ -220,11 +227,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             o.y = acc[j + 1] + b.y;
             o.z = acc[j + 2] + b.z;
             o.w = acc[j + 3] + b.w;
-            o.x = o.x > 0.0f ? o.x : 0.2f * o.x;
-            o.y = o.y > 0.0f ? o.y : 0.2f * o.y;
-            o.z = o.z > 0.0f ? o.z : 0.2f * o.z;
-            o.w = o.w > 0.0f ? o.w : 0.2f * o.w;
-            *reinterpret_cast<float4 *>(crow + j) = o;
+            o.x = fmaxf(o.x, 0.2f * o.x);
+            o.y = fmaxf(o.y, 0.2f * o.y);
+            o.z = fmaxf(o.z, 0.2f * o.z);
+            o.w = fmaxf(o.w, 0.2f * o.w);
+            if (C) *reinterpret_cast<float4 *>(C + coff + j) = o;
+            if (C_hi) {
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u); l.x = o.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u); l.y = o.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u); l.z = o.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u); l.w = o.w - h.w;
+                *reinterpret_cast<float4 *>(C_hi + coff + j) = h;
+                *reinterpret_cast<float4 *>(C_lo + coff + j) = l;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -236,7 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 }
 
 // W[10368][512] -> K-major transposed hi / lo parts Wt[512][10368]
-__global__ void k_fc0_split_weights(const float *__restrict__ W, float *__restrict__ hi, float *__restrict__ lo) {
+__global__ void k_fc0_split_weights(const float *__restrict__ W, float *__restrict__ hi, float *__restrict__ lo, int K) {
     __shared__ float tile[32][33];
     const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -245,8 +261,8 @@ __global__ void k_fc0_split_weights(const float *__restrict__ W, float *__restri
     for (int r = ty; r < 32; r += 8) {
         const float x = tile[tx][r];  // W[k0+tx][n0+r]
         const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-        hi[(size_t)(n0 + r) * TC_K + k0 + tx] = h;
-        lo[(size_t)(n0 + r) * TC_K + k0 + tx] = x - h;
+        hi[(size_t)(n0 + r) * K + k0 + tx] = h;
+        lo[(size_t)(n0 + r) * K + k0 + tx] = x - h;
     }
 }
 
@@ -254,7 +270,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool encode_map(CUtensorMap *map, float *ptr, uint64_t rows, uint32_t box_rows) {
+static bool encode_map(CUtensorMap *map, float *ptr, uint64_t rows, uint32_t box_rows, int K = TC_K) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -262,8 +278,8 @@ static bool encode_map(CUtensorMap *map, float *ptr, uint64_t rows, uint32_t box
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
         fn = (PFN_encodeTiled)p;
     }
-    const cuuint64_t dims[2] = {(cuuint64_t)TC_K, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)TC_K * sizeof(float)};
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -271,7 +287,8 @@ static bool encode_map(CUtensorMap *map, float *ptr, uint64_t rows, uint32_t box
 }
 
 struct Fc0TcState {
-    CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+    CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;      // fc0
+    CUtensorMap map1_a_hi, map1_a_lo, map1_b_hi, map1_b_lo;  // fc1
     float *a_hi_ptr = nullptr;
     int a_rows = 0;
     bool weights_ready = false;
@@ -287,34 +304,60 @@ void fc0_tc_free(omk_ctx *c) {
     c->fc0_tc_state = nullptr;
 }
 
-// (re)build the split transposed weights; call after the fc0 weights change
+// (re)build the split transposed weights of fc0 and fc1; call after the weights change
 bool fc0_tc_prepare_weights(omk_ctx *c) {
     Fc0TcState *s = state_of(c);
     if (!c->net.fc0_wt_hi) {
         if (cudaMalloc(&c->net.fc0_wt_hi, sizeof(float) * (size_t)TC_K * TC_N) != cudaSuccess) return false;
         if (cudaMalloc(&c->net.fc0_wt_lo, sizeof(float) * (size_t)TC_K * TC_N) != cudaSuccess) return false;
+        if (cudaMalloc(&c->net.fc1_wt_hi, sizeof(float) * (size_t)TC_K1 * TC_N) != cudaSuccess) return false;
+        if (cudaMalloc(&c->net.fc1_wt_lo, sizeof(float) * (size_t)TC_K1 * TC_N) != cudaSuccess) return false;
     }
-    k_fc0_split_weights<<<dim3(TC_K / 32, TC_N / 32), 256, 0, c->stream>>>(c->net.t[23], c->net.fc0_wt_hi, c->net.fc0_wt_lo);
-    c->launches++;
+    k_fc0_split_weights<<<dim3(TC_K / 32, TC_N / 32), 256, 0, c->stream>>>(c->net.t[23], c->net.fc0_wt_hi, c->net.fc0_wt_lo, TC_K);
+    k_fc0_split_weights<<<dim3(TC_K1 / 32, TC_N / 32), 256, 0, c->stream>>>(c->net.t[25], c->net.fc1_wt_hi, c->net.fc1_wt_lo, TC_K1);
+    c->launches += 2;
     if (!encode_map(&s->map_b_hi, c->net.fc0_wt_hi, TC_N, TC_BN)) return false;
     if (!encode_map(&s->map_b_lo, c->net.fc0_wt_lo, TC_N, TC_BN)) return false;
+    if (!encode_map(&s->map1_b_hi, c->net.fc1_wt_hi, TC_N, TC_BN, TC_K1)) return false;
+    if (!encode_map(&s->map1_b_lo, c->net.fc1_wt_lo, TC_N, TC_BN, TC_K1)) return false;
     s->weights_ready = true;
     return true;
 }
 
-bool launch_fc0_tc(omk_ctx *c, int rows_bound) {
+static bool refresh_activation_maps(omk_ctx *c, Fc0TcState *s) {
+    if (s->a_hi_ptr == c->ws.act0_hi && s->a_rows == c->ws.max_rows) return true;
+    if (!encode_map(&s->map_a_hi, c->ws.act0_hi, (uint64_t)c->ws.max_rows, TC_BM)) return false;
+    if (!encode_map(&s->map_a_lo, c->ws.act0_lo, (uint64_t)c->ws.max_rows, TC_BM)) return false;
+    if (!encode_map(&s->map1_a_hi, c->ws.act1_hi, (uint64_t)c->ws.max_rows, TC_BM, TC_K1)) return false;
+    if (!encode_map(&s->map1_a_lo, c->ws.act1_lo, (uint64_t)c->ws.max_rows, TC_BM, TC_K1)) return false;
+    s->a_hi_ptr = c->ws.act0_hi;
+    s->a_rows = c->ws.max_rows;
+    return true;
+}
+
+// fc0: act0_hi/lo -> act1 (fp32, for the CUDA-core fc1) and/or act1_hi/lo (for the tensor-core fc1)
+bool launch_fc0_tc(omk_ctx *c, int rows_bound, bool split_out) {
     Fc0TcState *s = state_of(c);
-    if (!s->weights_ready) return false;
-    if (s->a_hi_ptr != c->ws.act0_hi || s->a_rows != c->ws.max_rows) {
-        if (!encode_map(&s->map_a_hi, c->ws.act0_hi, (uint64_t)c->ws.max_rows, TC_BM)) return false;
-        if (!encode_map(&s->map_a_lo, c->ws.act0_lo, (uint64_t)c->ws.max_rows, TC_BM)) return false;
-        s->a_hi_ptr = c->ws.act0_hi;
-        s->a_rows = c->ws.max_rows;
-    }
-    cudaFuncSetAttribute(k_fc0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (!s->weights_ready || !refresh_activation_maps(c, s)) return false;
+    auto kern = k_fc_tc<TC_K, TC_CHUNK0>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     const int mt = (rows_bound + TC_BM - 1) / TC_BM;
-    k_fc0_tc<<<dim3(TC_N / TC_BN, mt), TC_THREADS, TC_SMEM_BYTES, c->stream>>>(s->map_a_hi, s->map_a_lo, s->map_b_hi, s->map_b_lo,
-                                                                            c->net.t[24], c->ws.act1, c->ws.n_req, rows_bound);
+    kern<<<dim3(TC_N / TC_BN, mt), TC_THREADS, TC_SMEM_BYTES, c->stream>>>(
+        s->map_a_hi, s->map_a_lo, s->map_b_hi, s->map_b_lo, c->net.t[24], split_out ? nullptr : c->ws.act1,
+        split_out ? c->ws.act1_hi : nullptr, split_out ? c->ws.act1_lo : nullptr, c->ws.n_req, rows_bound);
+    c->launches++;
+    return true;
+}
+
+// fc1: act1_hi/lo -> act2 (fp32)
+bool launch_fc1_tc(omk_ctx *c, int rows_bound) {
+    Fc0TcState *s = state_of(c);
+    if (!s->weights_ready || !refresh_activation_maps(c, s)) return false;
+    auto kern = k_fc_tc<TC_K1, TC_CHUNK1>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    const int mt = (rows_bound + TC_BM - 1) / TC_BM;
+    kern<<<dim3(TC_N / TC_BN, mt), TC_THREADS, TC_SMEM_BYTES, c->stream>>>(
+        s->map1_a_hi, s->map1_a_lo, s->map1_b_hi, s->map1_b_lo, c->net.t[26], c->ws.act2, nullptr, nullptr, c->ws.n_req, rows_bound);
     c->launches++;
     return true;
 }

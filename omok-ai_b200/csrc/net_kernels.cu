@@ -448,7 +448,7 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     const int mt = (max_rows + GM - 1) / GM;
     sp = prof_begin(c, OMK_K_FC0, 1);
     if (tc) {
-        launch_fc0_tc(c, max_rows);
+        launch_fc0_tc(c, max_rows, /*split_out=*/true);
         c->launches--;  // counted once below with the other network kernels
     } else {
         k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act0, c->net.t[23], c->net.t[24], c->ws.act1, c->ws.n_req,
@@ -456,8 +456,13 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     }
     prof_end(c, sp);
     sp = prof_begin(c, OMK_K_FC1, 2);
-    k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act1, c->net.t[25], c->net.t[26], c->ws.act2, c->ws.n_req,
-                                                      max_rows, kFc, kFc, 1);
+    if (tc) {
+        launch_fc1_tc(c, max_rows);
+        c->launches--;
+    } else {
+        k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act1, c->net.t[25], c->net.t[26], c->ws.act2, c->ws.n_req,
+                                                          max_rows, kFc, kFc, 1);
+    }
     prof_end(c, sp);
     sp = prof_begin(c, OMK_K_HEADS, 2);
     k_gemm<<<dim3(1, mt), 256, 0, c->stream>>>(c->ws.act2, c->net.heads_w, c->net.heads_b, c->ws.logits, c->ws.n_req, max_rows,

@@ -46,7 +46,8 @@ static int32_t ensure_workspace(omk_ctx *c, int rows) {
     Workspace &w = c->ws;
     cudaFree(w.nn_in); cudaFree(w.req_tree); cudaFree(w.req_node); cudaFree(w.P); cudaFree(w.V);
     cudaFree(w.act0); cudaFree(w.act1); cudaFree(w.act2); cudaFree(w.logits); cudaFree(w.act0_hi); cudaFree(w.act0_lo);
-    w.act0 = w.act0_hi = w.act0_lo = nullptr;
+    cudaFree(w.act1_hi); cudaFree(w.act1_lo);
+    w.act0 = w.act0_hi = w.act0_lo = w.act1_hi = w.act1_lo = nullptr;
     w.max_rows = 0;
     CK(cudaMalloc(&w.nn_in, sizeof(NNIn) * (size_t)rows));
     CK(cudaMalloc(&w.req_tree, sizeof(uint32_t) * (size_t)rows));
@@ -59,6 +60,10 @@ static int32_t ensure_workspace(omk_ctx *c, int rows) {
     CK(cudaMemsetAsync(w.act0_hi, 0, sizeof(float) * (size_t)rows * 10368, c->stream));
     CK(cudaMemsetAsync(w.act0_lo, 0, sizeof(float) * (size_t)rows * 10368, c->stream));
     CK(cudaMalloc(&w.act1, sizeof(float) * (size_t)rows * 512));
+    CK(cudaMalloc(&w.act1_hi, sizeof(float) * (size_t)rows * 512));
+    CK(cudaMalloc(&w.act1_lo, sizeof(float) * (size_t)rows * 512));
+    CK(cudaMemsetAsync(w.act1_hi, 0, sizeof(float) * (size_t)rows * 512, c->stream));
+    CK(cudaMemsetAsync(w.act1_lo, 0, sizeof(float) * (size_t)rows * 512, c->stream));
     CK(cudaMalloc(&w.act2, sizeof(float) * (size_t)rows * 512));
     CK(cudaMalloc(&w.logits, sizeof(float) * (size_t)rows * 128));
     CK(cudaMemsetAsync(w.act0, 0, sizeof(float) * (size_t)rows * 10368, c->stream));
@@ -198,7 +203,7 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
     void *ptrs[] = {c->envs, c->tree_hdrs, c->tree_nodes, c->remap, c->dev_error, c->dev_sims, w.nn_in, w.req_tree,
                     w.req_node, w.P, w.V, w.act0, w.act1, w.act2, w.logits, w.n_req, w.slot_base, w.slot_count, w.ids,
                     w.actions, w.modes, w.temps, w.status, w.policy_out, w.streams, c->net.heads_w, c->net.heads_b,
-                    c->sp_ply, c->sp_buf, w.act0_hi, w.act0_lo, c->net.fc0_wt_hi, c->net.fc0_wt_lo, c->net.tower_wimg,
+                    c->sp_ply, c->sp_buf, w.act0_hi, w.act0_lo, c->net.fc0_wt_hi, c->net.fc0_wt_lo, c->net.fc1_wt_hi, c->net.fc1_wt_lo, w.act1_hi, w.act1_lo, c->net.tower_wimg,
                     c->net.tower_pimg};
     fc0_tc_free(c);
     for (void *p : ptrs) cudaFree(p);
@@ -325,7 +330,7 @@ extern "C" int32_t omk_debug_tower_timing(omk_ctx *c, int64_t *out64) {
 extern "C" int32_t omk_debug_get_buffer(omk_ctx *c, int32_t which, float *out, int64_t count) {
     CK(cudaSetDevice(c->device));
     const float *src = which == 0 ? c->ws.act0 : which == 1 ? c->ws.act1 : which == 2 ? c->ws.act2 : which == 3 ? c->ws.logits
-                     : which == 4 ? c->ws.act0_hi : which == 5 ? c->ws.act0_lo : nullptr;
+                     : which == 4 ? c->ws.act0_hi : which == 5 ? c->ws.act0_lo : which == 6 ? c->ws.act1_hi : which == 7 ? c->ws.act1_lo : nullptr;
     if (!src || !out || count < 0) return fail(OMK_ERR_INVALID, "bad buffer id");
     CK(cudaMemcpyAsync(out, src, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

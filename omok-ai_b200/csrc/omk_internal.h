@@ -20,6 +20,7 @@ struct NetWeights {
     float *heads_b = nullptr;    // [128]
     float *fc0_wt_hi = nullptr;  // [512][10368] K-major TF32-exact high part of fc0_w (tensor-core path)
     float *fc0_wt_lo = nullptr;  // [512][10368] residual low part
+    float *fc1_wt_hi = nullptr, *fc1_wt_lo = nullptr;  // [512][512] same for fc1
     uint8_t *tower_wimg = nullptr;  // 3 x 72 KB pre-swizzled B-operand images of the tower weights (tower_tc.cu)
     float *tower_pimg = nullptr;    // fp32 stem / bias / depthwise parameters
     bool loaded = false;
@@ -36,6 +37,7 @@ struct Workspace {  // evaluator request/response buffers, sized for max_rows
     float *act0_hi = nullptr;     // [max_rows][10368] TF32-exact high part (tensor-core path)
     float *act0_lo = nullptr;     // [max_rows][10368] residual low part
     float *act1 = nullptr;        // [max_rows][512]
+    float *act1_hi = nullptr, *act1_lo = nullptr;  // [max_rows][512] hi/lo split of fc0's output (tensor-core fc1)
     float *act2 = nullptr;        // [max_rows][512]
     float *logits = nullptr;      // [max_rows][128]
     uint32_t *n_req = nullptr;    // device counter
@@ -138,7 +140,8 @@ void launch_net_init_random(omk_ctx *c, uint64_t seed);
 
 // fc0_tc.cu
 bool fc0_tc_prepare_weights(omk_ctx *c);
-bool launch_fc0_tc(omk_ctx *c, int rows_bound);
+bool launch_fc0_tc(omk_ctx *c, int rows_bound, bool split_out);
+bool launch_fc1_tc(omk_ctx *c, int rows_bound);
 void fc0_tc_free(omk_ctx *c);
 
 // tower_tc.cu

@@ -28,12 +28,14 @@ for mode in (0, 1):
     ctx.debug_set_fc0_mode(mode)
     t = time.time()
     p, v = ctx.net_eval(boards, turns)
-    out[mode] = (p, v, ctx.debug_get_buffer(1, n * 512).reshape(n, 512), time.time() - t)
+    a1 = ctx.debug_get_buffer(1, n * 512) if mode == 0 else ctx.debug_get_buffer(6, n * 512).astype(np.float64) + ctx.debug_get_buffer(7, n * 512)
+    out[mode] = (p, v, np.asarray(a1, np.float64).reshape(n, 512), time.time() - t, ctx.debug_get_buffer(2, n * 512).reshape(n, 512))
     print("mode", mode, "ok", out[mode][3], flush=True)
 a0, a1 = out[0][2], out[1][2]
 print("fc0 out: max|simt|", np.abs(a0).max(), "max abs diff", np.abs(a0 - a1).max(), "rel to max", np.abs(a0 - a1).max() / np.abs(a0).max())
 d = (a1.astype(np.float64) - a0) * np.sign(a0)
 print("signed diff toward larger magnitude: mean", d.mean(), "median", np.median(d), "frac negative", (d < 0).mean(), "rms", np.sqrt((d**2).mean()), "typical |a0|", np.median(np.abs(a0)))
+print("fc1 out: max abs diff", np.abs(out[0][4] - out[1][4]).max(), "max|.|", np.abs(out[0][4]).max())
 bad = np.argwhere(np.abs(a0 - a1) > 1e-3 * np.abs(a0).max())
 print("bad entries:", len(bad), bad[:10].tolist())
 rp, rv, _ = net_oracle.forward_boards(params, boards[:64], turns[:64], dtype=__import__("torch").float64)
