@@ -134,3 +134,57 @@ def test_search_with_real_net_vs_cpu_net_tolerance(net, omk, orc):
     pol_cpu = a.root_stats()[4]
     big = pol_cpu > 1e-12
     assert np.max(np.abs(pol_gpu[big] - pol_cpu[big]) / pol_cpu[big]) < REL
+
+
+@pytest.mark.parametrize("tower_mode,fc_mode", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_all_kernel_paths_hold_the_tolerance(net, tower_mode, fc_mode):
+    """fp32 CUDA-core kernels (mode 0) and tcgen05 3xTF32 kernels (mode 1) for the tower and for fc0/fc1, in every
+    combination, against the fp64 oracle; and the tensor-core paths against the CUDA-core paths layer by layer."""
+    import torch
+
+    ctx, params, no = net
+    boards, turns = random_positions(160, 11)
+    rp, rv, _ = no.forward_boards(params, boards, turns, dtype=torch.float64)
+    try:
+        ctx.debug_set_tower_mode(tower_mode)
+        ctx.debug_set_fc0_mode(fc_mode)
+        p, v = ctx.net_eval(boards, turns)
+        check(p, v, rp, rv)
+        if fc_mode == 1:  # fc0 input (tower output) as hi + lo must reproduce the fp32 activations to ~1e-6 of their scale
+            x = ctx.debug_get_buffer(4, 160 * 10368).astype(np.float64) + ctx.debug_get_buffer(5, 160 * 10368)
+            ctx.debug_set_tower_mode(0)
+            ctx.net_eval(boards, turns)
+            x0 = ctx.debug_get_buffer(4, 160 * 10368).astype(np.float64) + ctx.debug_get_buffer(5, 160 * 10368)
+            assert np.abs(x - x0).max() <= 2e-5 * np.abs(x0).max()
+    finally:
+        ctx.debug_set_tower_mode(1)
+        ctx.debug_set_fc0_mode(1)
+
+
+def test_fc0_single_cta_and_cta_pair_kernels_agree(omk):
+    """OMK_FC0_PAIR=0 (one CTA per 128x256 tile) and =1 (cta_group::2 CTA pair per 256x256 tile) give the same numbers:
+    the accumulation order per output element is identical, so the results must be bit-identical."""
+    import os
+
+    from oracle import net_oracle
+
+    params = net_oracle.random_params(0)
+    boards, turns = random_positions(300, 21)
+    res = []
+    for pair in ("0", "1"):
+        os.environ["OMK_FC0_PAIR"] = pair
+        c = omk.Context(device=0, capacity_envs=1, capacity_trees=1, capacity_nodes=16, seed=0)
+        c.net_load_params(params)
+        res.append(c.net_eval(boards, turns))
+        c.close()
+    del os.environ["OMK_FC0_PAIR"]
+    assert res[0][0].tobytes() == res[1][0].tobytes() and res[0][1].tobytes() == res[1][1].tobytes()
+
+
+def test_tensor_core_kernels_are_in_the_library(omk):
+    """SASS evidence: tcgen05.mma -> UTC*MMA, TMA -> UTMALDG / UBLKCP, tcgen05.ld/st -> LDTM / STTM."""
+    import subprocess
+
+    sass = subprocess.run(["cuobjdump", "-sass", omk.lib_path()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UBLKCP", "LDTM", "STTM"):
+        assert mnemonic in sass, mnemonic
