@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             o.y = fmaxf(o.y, 0.2f * o.y);
             o.z = fmaxf(o.z, 0.2f * o.z);
             o.w = fmaxf(o.w, 0.2f * o.w);
+            if (row >= rows) continue;  // rows past the batch are never stored (the tile may extend past the workspace)
             if (C) *reinterpret_cast<float4 *>(C + coff + j) = o;
             if (C_hi) {
                 float4 h, l;
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             o.y = fmaxf(o.y, 0.2f * o.y);
             o.z = fmaxf(o.z, 0.2f * o.z);
             o.w = fmaxf(o.w, 0.2f * o.w);
+            if (row >= rows) continue;  // rows past the batch are never stored (the tile may extend past the workspace)
             if (C) *reinterpret_cast<float4 *>(C + coff + j) = o;
             if (C_hi) {
                 float4 h, l;

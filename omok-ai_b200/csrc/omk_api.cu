@@ -40,7 +40,7 @@ extern "C" int32_t omk_version(void) { return 100; }
 
 // ------------------------------------------------------------------ workspace
 static int32_t ensure_workspace(omk_ctx *c, int rows) {
-    rows = (rows + 127) / 128 * 128;
+    rows = (rows + 255) / 256 * 256;  // whole 256-row CTA-pair tiles
     if (rows <= c->ws.max_rows) return OMK_OK;
     CK(cudaStreamSynchronize(c->stream));
     Workspace &w = c->ws;

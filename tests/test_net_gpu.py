@@ -77,6 +77,27 @@ def test_batch_invariance(net):
         assert q.tobytes() == p[lo:hi].tobytes() and w.tobytes() == v[lo:hi].tobytes()
 
 
+@pytest.mark.parametrize("n", [1, 7, 8, 127, 128, 129, 255, 256, 257, 513])
+def test_small_and_ragged_batches(omk, n):
+    """Tile edges: batches below / at / above the 128-row MMA tile and the 256-row CTA-pair tile, each in a FRESH context
+    so the workspace is sized by this very call (regression: a pair tile once stored past a 128-row workspace)."""
+    import torch
+
+    from oracle import net_oracle
+
+    params = net_oracle.random_params(0)
+    boards, turns = random_positions(n, 100 + n)
+    c = omk.Context(device=0, capacity_envs=1, capacity_trees=1, capacity_nodes=16, seed=0)
+    c.net_load_params(params)
+    p, v = c.net_eval(boards, turns)
+    p2, v2 = c.net_eval(boards, turns)  # same workspace again: results must not depend on stale rows
+    c.close()
+    assert p.tobytes() == p2.tobytes() and v.tobytes() == v2.tobytes()
+    m = min(n, 48)
+    rp, rv, _ = net_oracle.forward_boards(params, boards[-m:], turns[-m:], dtype=torch.float64)
+    check(p[-m:], v[-m:], rp, rv)
+
+
 def test_get_params_roundtrip_and_random_init(net, omk):
     ctx, params, no = net
     got = ctx.net_get_params()
