@@ -308,10 +308,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     static_assert(NKB % CHUNK == 0, "chunking must tile K");
     extern __shared__ uint8_t smem_raw[];
     const int rows = (int)min(*n_req, (uint32_t)max_rows);
-    const int pair = blockIdx.x >> 1;  // the CTA pair is a 2x1 cluster along x
+    // blockIdx.x = ((pair * 2 + n_tile) * 2 + rank): the CTA pair is a 2x1 cluster along x, and the two N tiles of one
+    // row pair are neighbours in launch order so that the second reads its A rows from L2, not from DRAM
+    const int pair = blockIdx.x >> 2;
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const int m0 = pair * 256 + (int)rank * TC_BM, n0 = blockIdx.y * TC_BN;
+    const int m0 = pair * 256 + (int)rank * TC_BM, n0 = (int)((blockIdx.x >> 1) & 1u) * TC_BN;
     if (pair * 256 >= rows) return;  // uniform for the whole cluster
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -560,7 +562,7 @@ bool launch_fc0_tc(omk_ctx *c, int rows_bound, bool split_out) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
         const int pairs = (rows_bound + 255) / 256;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * pairs, TC_N / TC_BN);
+        cfg.gridDim = dim3(2 * (TC_N / TC_BN) * pairs, 1);
         cfg.blockDim = dim3(TC_THREADS);
         cfg.dynamicSmemBytes = T2_SMEM_BYTES;
         cfg.stream = c->stream;
