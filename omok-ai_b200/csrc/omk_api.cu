@@ -160,6 +160,7 @@ extern "C" int32_t omk_ctx_create(int32_t device, int32_t capacity_envs, int32_t
     c->seed = seed;
     if (const char *m = getenv("OMK_FC0")) c->fc0_mode = (strcmp(m, "simt") == 0) ? 0 : 1;
     if (const char *m = getenv("OMK_FC0_PAIR")) c->fc0_pair = atoi(m) != 0;
+    if (const char *m = getenv("OMK_TOWER_PAIR")) c->tower_pair = atoi(m) != 0;
     if (const char *m = getenv("OMK_TOWER")) c->tower_mode = (strcmp(m, "simt") == 0) ? 0 : 1;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));

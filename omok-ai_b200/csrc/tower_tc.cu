@@ -16,6 +16,8 @@
 // channel half w/4.  Thread 0 issues the MMAs; completion is a tcgen05.commit on an mbarrier.
 //
 // TMEM columns: X_hi [0,128) X_lo [128,256) H_hi [256,288) H_lo [288,320) D12 [320,352) D3 [352,480).
+#include <cstdio>
+
 #include "omk_internal.h"
 
 namespace omk {
@@ -38,6 +40,11 @@ constexpr int SM_PAR = SM_H0 + 128 * TW_HSTRIDE * 4;       // 165888
 constexpr int SM_IMG = SM_PAR + PI_FLOATS * 4;             // 173696
 constexpr int SM_BAR = SM_IMG + 256 * 4;                   // 174720
 constexpr int TW_SMEM_BYTES = SM_BAR + 64 + 1024;
+// pair kernel: H tile = 2 buffers x 162 rows (two positions), IMG = 3 images
+constexpr int SM3_PAR = SM_H0 + 2 * 162 * TW_HSTRIDE * 4;   // 194112
+constexpr int SM3_IMG = SM3_PAR + PI_FLOATS * 4;             // 201920
+constexpr int SM3_BAR = SM3_IMG + 736 * 4;                   // 204864
+constexpr int TW3_SMEM_BYTES = SM3_BAR + 64 + 1024;
 constexpr uint32_t TW_IDESC_N32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t TW_IDESC_N128 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -108,6 +115,44 @@ __device__ __forceinline__ float tw_lrelu(float v) { return fmaxf(v, 0.2f * v); 
 // region, and the 32 spare columns at the top
 __device__ __forceinline__ constexpr uint32_t conv0_acc(int a) { return a == 0 ? C_D12 : (a < 5 ? C_D3 + 32u * (uint32_t)(a - 1) : 480u); }
 
+
+// Coalesced write-out of one warp's 32 pixel rows x 64 channels.  A thread owns a 256-byte row segment, so direct
+// per-thread stores make every warp instruction touch 32 different cache lines (measured: ~16k clk per iteration in
+// the LSU).  Instead each warp transposes through a 4.6 KB staging tile: rows in, 128-byte line segments out.
+// `off` = element offset of this lane's segment in the output arrays, or -1 for a padded / out-of-batch row.
+__device__ __forceinline__ void tw_store_part(float *stage, int lane, long long off, const float *v, float *dst) {
+#pragma unroll
+    for (int cp = 0; cp < 2; ++cp) {  // two passes of 32 channels
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4 *>(stage + lane * TW_HSTRIDE + k * 4) =
+                make_float4(v[cp * 32 + k * 4 + 0], v[cp * 32 + k * 4 + 1], v[cp * 32 + k * 4 + 2], v[cp * 32 + k * 4 + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), ch = lane & 7;
+            const float4 val = *reinterpret_cast<const float4 *>(stage + rr * TW_HSTRIDE + ch * 4);
+            const long long o = __shfl_sync(0xffffffffu, off, rr);
+            if (o >= 0) *reinterpret_cast<float4 *>(dst + o + cp * 32 + ch * 4) = val;
+        }
+        __syncwarp();
+    }
+}
+__device__ __forceinline__ void tw_store_out(float *stage, int lane, long long off, const float *x, float *act0, float *act0_hi,
+                                             float *act0_lo) {
+    if (act0_hi) {
+        float part[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) part[c] = __uint_as_float(__float_as_uint(x[c]) & 0xFFFFE000u);
+        tw_store_part(stage, lane, off, part, act0_hi);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) part[c] = x[c] - part[c];
+        tw_store_part(stage, lane, off, part, act0_lo);
+    } else {
+        tw_store_part(stage, lane, off, x, act0);
+    }
+}
+
 __device__ __forceinline__ void tw_bulk_load(uint32_t dst, const uint8_t *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
@@ -157,6 +202,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
     uint32_t mma_uses = 0;   // completed uses of bar_mma
     auto issue_weights = [&](uint32_t gg) {  // thread 0 only
         const uint32_t buf = gg & 1u, bar = bar_w0 + 8 * buf;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer may have served as a staging tile (generic proxy)
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WI_BYTES) : "memory");
         const uint8_t *src = wimg + (size_t)(gg % 3u) * WI_BYTES;
         for (int c = 0; c < WI_BYTES; c += 8192) tw_bulk_load(sbase + SM_W + buf * WI_BYTES + c, src + c, 8192, bar);
@@ -374,24 +420,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
         }
         // ---- flatten NHWC (network.rs:127-137): this thread's pixel row, its 64 channels ----
         TW_STAMP(30);
-        if (real) {
-            const size_t off = (size_t)row * 10368 + (size_t)p * 128 + half * 64;
-            if (act0_hi) {
-#pragma unroll
-                for (int c = 0; c < 64; c += 4) {
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(x[c + 0]) & 0xFFFFE000u); l.x = x[c + 0] - h.x;
-                    h.y = __uint_as_float(__float_as_uint(x[c + 1]) & 0xFFFFE000u); l.y = x[c + 1] - h.y;
-                    h.z = __uint_as_float(__float_as_uint(x[c + 2]) & 0xFFFFE000u); l.z = x[c + 2] - h.z;
-                    h.w = __uint_as_float(__float_as_uint(x[c + 3]) & 0xFFFFE000u); l.w = x[c + 3] - h.w;
-                    *reinterpret_cast<float4 *>(act0_hi + off + c) = h;
-                    *reinterpret_cast<float4 *>(act0_lo + off + c) = l;
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 64; c += 4)
-                    *reinterpret_cast<float4 *>(act0 + off + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
-            }
+        {   // the weight buffer of the block just finished is idle until the next conv0 phase: staging tiles live there
+            float *stage = reinterpret_cast<float *>(sm + SM_W + ((g - 1u) & 1u) * WI_BYTES) + warp * (32 * TW_HSTRIDE);
+            const long long off = real ? (long long)row * 10368 + (long long)p * 128 + half * 64 : -1ll;
+            tw_store_out(stage, lane, off, x, act0, act0_hi, act0_lo);
         }
     }
     // (timestamps: 0 start, 1 stem done, then per block: conv0 done, E1+sync, dw stored, conv1 done, E2 stored, conv2 done, E3 stored)
@@ -404,6 +436,317 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TW_TMEM_COLS) : "memory");
     }
 }
+
+__global__ void __launch_bounds__(TW_THREADS, 1)
+    k_tower_tc3(const uint8_t *__restrict__ wimg, const float *__restrict__ pimg, const NNIn *__restrict__ nn_in,
+               const float *__restrict__ images, const uint32_t *n_req, int max_rows, float *__restrict__ act0,
+               float *__restrict__ act0_hi, float *__restrict__ act0_lo) {
+    extern __shared__ uint8_t tw_smem_raw[];
+    const int rows = (int)min(*n_req, (uint32_t)max_rows);
+    const int n_triples = (rows + 2) / 3, n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
+    if (pair >= n_triples) return;  // uniform for both CTAs of the pair, before any cluster barrier
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int q = warp & 3, half = warp >> 2;
+    // A CTA PAIR walks position TRIPLES: the 243 pixel rows of three positions fill 243 of the pair's 256 TMEM lanes
+    // (one position alone fills only 81 of a CTA's 128).  Row R of the pair = 128*rank + TMEM lane; position j = R/81.
+    const int R = (int)rank * 128 + q * 32 + lane;
+    const int j = R / kCells, p = R - j * kCells;       // position within the triple, pixel within the position
+    const int slot = j - (int)rank;                      // H tile slot: CTA r keeps positions r and r+1 (162 rows)
+
+    uint8_t *sm = tw_smem_raw + ((1024u - (tw_smem_u32(tw_smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = tw_smem_u32(sm);
+    float *H0 = reinterpret_cast<float *>(sm + SM_H0);
+    float *PAR = reinterpret_cast<float *>(sm + SM3_PAR);
+    float *IMG = reinterpret_cast<float *>(sm + SM3_IMG);
+    const uint32_t bar_w0 = sbase + SM3_BAR, bar_mma = sbase + SM3_BAR + 16, tmem_slot = sbase + SM3_BAR + 24;
+    // the pair's middle position straddles the two CTAs: its H rows are mirrored into the peer's tile through DSMEM
+    uint32_t peer_h0;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_h0) : "r"(sbase + SM_H0), "r"(rank ^ 1u));
+
+    for (int i = t; i < PI_FLOATS; i += TW_THREADS) PAR[i] = pimg[i];
+    if (t == 0) {
+        tw_mbar_init(bar_w0, 1);
+        tw_mbar_init(bar_w0 + 8, 1);
+        tw_mbar_init(bar_mma, 8);  // one tcgen05.commit per warp: every warp's lane 0 issues its own MMA chain
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TW_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);  // this warp's lane quadrant
+
+    uint32_t g = 0;          // running block counter: weight buffer = g & 1, its phase parity = (g >> 1) & 1
+    uint32_t mma_uses = 0;   // completed uses of bar_mma
+    auto issue_weights = [&](uint32_t gg) {  // thread 0 only
+        const uint32_t buf = gg & 1u, bar = bar_w0 + 8 * buf;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer may have served as a staging tile (generic proxy)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WI_BYTES) : "memory");
+        const uint8_t *src = wimg + (size_t)(gg % 3u) * WI_BYTES;
+        for (int c = 0; c < WI_BYTES; c += 8192) tw_bulk_load(sbase + SM_W + buf * WI_BYTES + c, src + c, 8192, bar);
+    };
+    if (t == 0) issue_weights(0);
+
+    NNIn cur0{}, cur1{}, cur2{};
+    if (!images) {
+        cur0 = nn_in[min(pair * 3 + 0, rows - 1)];
+        cur1 = nn_in[min(pair * 3 + 1, rows - 1)];
+        cur2 = nn_in[min(pair * 3 + 2, rows - 1)];
+    }
+    int pos_iter = 0;
+    for (int tr = pair; tr < n_triples; tr += n_pairs, ++pos_iter) {
+        const bool dbg_on = blockIdx.x == 0 && pos_iter == 1;
+        const int row = tr * 3 + j;                       // this thread's position (global row of the batch)
+        const bool real = R < 3 * kCells && row < rows;   // 13 padding lanes per pair; the last triple may be partial
+        TW_STAMP(0);
+        // ---- input images of the triple (the reference's 243-float slot read as [81][3]) ----
+        if (t < 243) {
+            if (images) {
+                IMG[t] = images[(size_t)min(tr * 3 + 0, rows - 1) * 243 + t];
+                IMG[243 + t] = images[(size_t)min(tr * 3 + 1, rows - 1) * 243 + t];
+                IMG[486 + t] = images[(size_t)min(tr * 3 + 2, rows - 1) * 243 + t];
+            } else {
+                IMG[t] = image_value(cur0.black, cur0.white, cur0.meta & 1u, (cur0.meta >> 1) & 1u, t);
+                IMG[243 + t] = image_value(cur1.black, cur1.white, cur1.meta & 1u, (cur1.meta >> 1) & 1u, t);
+                IMG[486 + t] = image_value(cur2.black, cur2.white, cur2.meta & 1u, (cur2.meta >> 1) & 1u, t);
+            }
+        }
+        // prefetch the next triple's request rows: their global-load latency hides behind this whole iteration
+        if (!images && tr + n_pairs < n_triples) {
+            cur0 = nn_in[min((tr + n_pairs) * 3 + 0, rows - 1)];
+            cur1 = nn_in[min((tr + n_pairs) * 3 + 1, rows - 1)];
+            cur2 = nn_in[min((tr + n_pairs) * 3 + 2, rows - 1)];
+        }
+        __syncthreads();
+        TW_STAMP(40);
+        // ---- stem 1x1 conv 3 -> 128 (network.rs:65-79): this thread's pixel, its 64 channels ----
+        float x[64];
+        {
+            const int pc = real ? p : 0;  // padded rows recompute pixel 0 (harmless, never stored)
+            const float *im = IMG + (real ? j : 0) * 243;
+            const float v0 = im[3 * pc], v1 = im[3 * pc + 1], v2 = im[3 * pc + 2];
+#pragma unroll
+            for (int c = 0; c < 64; c += 4) {
+                const int ch = half * 64 + c;
+                const float4 b = *reinterpret_cast<const float4 *>(PAR + PI_BSTEM + ch);
+                const float4 w0 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + ch);
+                const float4 w1 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + 128 + ch);
+                const float4 w2 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + 256 + ch);
+                x[c + 0] = tw_lrelu(fmaf(v2, w2.x, fmaf(v1, w1.x, fmaf(v0, w0.x, b.x))));
+                x[c + 1] = tw_lrelu(fmaf(v2, w2.y, fmaf(v1, w1.y, fmaf(v0, w0.y, b.y))));
+                x[c + 2] = tw_lrelu(fmaf(v2, w2.z, fmaf(v1, w1.z, fmaf(v0, w0.z, b.z))));
+                x[c + 3] = tw_lrelu(fmaf(v2, w2.w, fmaf(v1, w1.w, fmaf(v0, w0.w, b.w))));
+            }
+            TW_STAMP(41);
+#pragma unroll
+            for (int c = 0; c < 64; c += 16) tw_store_split16(tlane + C_XHI + half * 64 + c, tlane + C_XLO + half * 64 + c, x + c);
+            TW_STAMP(42);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        TW_STAMP(1);
+
+        for (int r = 0; r < 3; ++r, ++g) {
+            const float *bp = PAR + PI_BLK0 + r * PI_BLK;
+            float *H0b = H0 + (r & 1) * (162 * TW_HSTRIDE);      // double-buffered: the peer may still read the other one
+            const uint32_t peer_h0b = peer_h0 + (uint32_t)((r & 1) * (162 * TW_HSTRIDE * 4));
+            const uint32_t wb = sbase + SM_W + (g & 1u) * WI_BYTES;
+            // ================= conv0: 1x1 128 -> 32 (A = X in TMEM) =================
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (lane == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp == 0) issue_weights(g + 1);  // the other buffer's last reader (block g-1) has completed
+                if (warp < 6) {
+                    // six independent accumulator chains (3 products x 2 K-halves), one per issuing warp: the single-thread
+                    // issue path costs ~60 clk per MMA, so the chains are issued in parallel from six threads
+                    tw_mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+                    const int pass = warp >> 1, h = warp & 1;
+                    const uint32_t acol = pass == 0 ? C_XLO : C_XHI;
+                    const uint32_t bimg = pass == 1 ? WI_W0LO : WI_W0HI;
+#pragma unroll 1
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const int kk = ks + 8 * h;
+                        const uint32_t boff = (uint32_t)((kk >> 2) * 4096 + (kk & 3) * 32);
+                        tw_umma_ts(tmem_base + conv0_acc(warp), tmem_base + acol + kk * 8, tw_desc_sw128(wb + bimg + boff),
+                                   TW_IDESC_N32, ks != 0);
+                    }
+                }
+                tw_commit(bar_mma);
+            }
+            tw_mbar_wait(bar_mma, mma_uses & 1u);
+            ++mma_uses;
+            __syncwarp();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 0);
+            // epilogue 1: + b0, lrelu -> fp32 tile for the depthwise stencil (this thread: 16 channels of its pixel)
+            {
+                float d[16], e[5][16];
+                tw_ld16(tlane + conv0_acc(0) + half * 16, d);
+#pragma unroll
+                for (int a = 1; a < 6; ++a) tw_ld16(tlane + conv0_acc(a) + half * 16, e[a - 1]);
+                tw_wait_ld();  // one wait for all six partial accumulators
+#pragma unroll
+                for (int c = 0; c < 16; ++c) d[c] = ((d[c] + e[0][c]) + (e[1][c] + e[2][c])) + (e[3][c] + e[4][c]);
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(bp + PI_B0 + half * 16 + c);
+                    float4 o;
+                    o.x = tw_lrelu(d[c + 0] + b.x);
+                    o.y = tw_lrelu(d[c + 1] + b.y);
+                    o.z = tw_lrelu(d[c + 2] + b.z);
+                    o.w = tw_lrelu(d[c + 3] + b.w);
+                    if (real) {
+                        *reinterpret_cast<float4 *>(H0b + (slot * kCells + p) * TW_HSTRIDE + half * 16 + c) = o;
+                        if (j == 1) {  // the peer keeps this position in its slot 1 - peer_rank = rank
+                            const uint32_t ra = peer_h0b + (uint32_t)((((int)rank * kCells + p) * TW_HSTRIDE + half * 16 + c) * 4);
+                            asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                        }
+                    }
+                }
+            }
+            // both CTAs' rows (local and mirrored) must be visible before the stencil: cluster-wide barrier
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 1);
+            // conv1 depthwise 3x3, SAME zero padding, no bias (lib.rs:204-216) -> A operand of the pointwise conv
+            {
+                float a[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) a[c] = 0.0f;
+                if (real) {
+                    const int y = p / kSide, xx0 = p % kSide;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int yy = y + ky - 1;
+                        if (yy < 0 || yy >= kSide) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int xx = xx0 + kx - 1;
+                            if (xx < 0 || xx >= kSide) continue;
+                            const float *hp = H0b + (slot * kCells + yy * kSide + xx) * TW_HSTRIDE + half * 16;
+                            const float *wp = bp + PI_DW + (ky * 3 + kx) * 32 + half * 16;
+#pragma unroll
+                            for (int c = 0; c < 16; c += 4) {
+                                const float4 h = *reinterpret_cast<const float4 *>(hp + c);
+                                const float4 w = *reinterpret_cast<const float4 *>(wp + c);
+                                a[c + 0] = fmaf(h.x, w.x, a[c + 0]);
+                                a[c + 1] = fmaf(h.y, w.y, a[c + 1]);
+                                a[c + 2] = fmaf(h.z, w.z, a[c + 2]);
+                                a[c + 3] = fmaf(h.w, w.w, a[c + 3]);
+                            }
+                        }
+                    }
+                }
+                tw_store_split16(tlane + C_HHI + half * 16, tlane + C_HLO + half * 16, a);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 2);
+            // ================= conv1 pointwise: 1x1 32 -> 32 (A = H in TMEM) =================
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (lane == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp < 3) {  // one product per issuing warp, three accumulators
+                    const uint32_t acol = warp == 0 ? C_HLO : C_HHI;
+                    const uint32_t bimg = warp == 1 ? WI_PWLO : WI_PWHI;
+#pragma unroll 1
+                    for (int ks = 0; ks < 4; ++ks)
+                        tw_umma_ts(tmem_base + conv0_acc(warp), tmem_base + acol + ks * 8, tw_desc_sw128(wb + bimg + ks * 32),
+                                   TW_IDESC_N32, ks != 0);
+                }
+                tw_commit(bar_mma);
+            }
+            tw_mbar_wait(bar_mma, mma_uses & 1u);
+            ++mma_uses;
+            __syncwarp();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 3);
+            {   // epilogue 2: + b1, lrelu -> A operand of conv2
+                float d[16], e[16], f[16];
+                tw_ld16(tlane + conv0_acc(0) + half * 16, d);
+                tw_ld16(tlane + conv0_acc(1) + half * 16, e);
+                tw_ld16(tlane + conv0_acc(2) + half * 16, f);
+                tw_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(bp + PI_B1 + half * 16 + c);
+                    d[c + 0] = tw_lrelu((d[c + 0] + e[c + 0]) + f[c + 0] + b.x);
+                    d[c + 1] = tw_lrelu((d[c + 1] + e[c + 1]) + f[c + 1] + b.y);
+                    d[c + 2] = tw_lrelu((d[c + 2] + e[c + 2]) + f[c + 2] + b.z);
+                    d[c + 3] = tw_lrelu((d[c + 3] + e[c + 3]) + f[c + 3] + b.w);
+                }
+                tw_store_split16(tlane + C_HHI + half * 16, tlane + C_HLO + half * 16, d);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 4);
+            // ================= conv2: 1x1 32 -> 128 (A = H in TMEM), + x, lrelu =================
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (lane == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp == 0) {  // N = 128 MMAs are tensor-bound (64 clk each): one chain
+#pragma unroll 1
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t bhi = tw_desc_sw128(wb + WI_W2HI + ks * 32), blo = tw_desc_sw128(wb + WI_W2LO + ks * 32);
+                        tw_umma_ts(tmem_base + C_D3, tmem_base + C_HLO + ks * 8, bhi, TW_IDESC_N128, ks != 0);
+                        tw_umma_ts(tmem_base + C_D3, tmem_base + C_HHI + ks * 8, blo, TW_IDESC_N128, 1u);
+                        tw_umma_ts(tmem_base + C_D3, tmem_base + C_HHI + ks * 8, bhi, TW_IDESC_N128, 1u);
+                    }
+                }
+                tw_commit(bar_mma);
+            }
+            tw_mbar_wait(bar_mma, mma_uses & 1u);
+            ++mma_uses;
+            __syncwarp();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 5);
+            {   // epilogue 3: x = lrelu(conv2 + b2 + x), next block's A operand
+                float d[64];
+#pragma unroll
+                for (int c = 0; c < 64; c += 16) tw_ld16(tlane + C_D3 + half * 64 + c, d + c);
+                tw_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 64; c += 16) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {  // padded rows (p >= 81) carry harmless garbage; they are never stored
+                        const float4 b = *reinterpret_cast<const float4 *>(bp + PI_B2 + half * 64 + c + i);
+                        x[c + i + 0] = tw_lrelu(d[c + i + 0] + b.x + x[c + i + 0]);
+                        x[c + i + 1] = tw_lrelu(d[c + i + 1] + b.y + x[c + i + 1]);
+                        x[c + i + 2] = tw_lrelu(d[c + i + 2] + b.z + x[c + i + 2]);
+                        x[c + i + 3] = tw_lrelu(d[c + i + 3] + b.w + x[c + i + 3]);
+                    }
+                    if (r < 2) tw_store_split16(tlane + C_XHI + half * 64 + c, tlane + C_XLO + half * 64 + c, x + c);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TW_STAMP(2 + r * 8 + 6);
+        }
+        // ---- flatten NHWC (network.rs:127-137): this thread's pixel row, its 64 channels ----
+        TW_STAMP(30);
+        {   // the weight buffer of the block just finished is idle until the next conv0 phase: staging tiles live there
+            float *stage = reinterpret_cast<float *>(sm + SM_W + ((g - 1u) & 1u) * WI_BYTES) + warp * (32 * TW_HSTRIDE);
+            const long long off = real ? (long long)row * 10368 + (long long)p * 128 + half * 64 : -1ll;
+            tw_store_out(stage, lane, off, x, act0, act0_hi, act0_lo);
+        }
+    }
+    // (timestamps: 0 start, 1 stem done, then per block: conv0 done, E1+sync, dw stored, conv1 done, E2 stored, conv2 done, E3 stored)
+    // drain the weight prefetch that was issued one block ahead, then release TMEM
+    if (t == 0) tw_mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TW_TMEM_COLS) : "memory");
+    }
+}
+
 
 // Build the per-block B-operand images (K-major SWIZZLE_128B, hi/lo) and the fp32 parameter image.
 __device__ __forceinline__ uint32_t swz128(int n, int k) {  // byte offset of element (row n, k in [0,32)) inside an atom
@@ -473,6 +816,32 @@ bool tower_tc_prepare_weights(omk_ctx *c) {
 void tower_tc_read_timing(long long *out64) { cudaMemcpyFromSymbol(out64, g_tw_dbg, sizeof(long long) * 64); }
 
 void launch_tower_tc(omk_ctx *c, const float *images_dev, int rows_bound, bool split_out) {
+    if (c->tower_pair) {  // CTA pairs walking position triples (243 of 256 TMEM lanes busy)
+        cudaFuncSetAttribute(k_tower_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, TW3_SMEM_BYTES);
+        const int triples = (rows_bound + 2) / 3;
+        const int pairs = triples < c->n_sms / 2 ? triples : c->n_sms / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(TW_THREADS);
+        cfg.dynamicSmemBytes = TW3_SMEM_BYTES;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const uint8_t *wimg = c->net.tower_wimg;
+        const float *pimg = c->net.tower_pimg;
+        const NNIn *nn_in = c->ws.nn_in;
+        const uint32_t *n_req = c->ws.n_req;
+        float *a0 = c->ws.act0, *ah = split_out ? c->ws.act0_hi : nullptr, *al = split_out ? c->ws.act0_lo : nullptr;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower_tc3, wimg, pimg, nn_in, images_dev, n_req, rows_bound, a0, ah, al);
+        if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_tower_tc3): %s\n", cudaGetErrorString(e));
+        c->launches++;
+        return;
+    }
     cudaFuncSetAttribute(k_tower_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM_BYTES);
     const int grid = rows_bound < c->n_sms ? rows_bound : c->n_sms;
     k_tower_tc<<<grid, TW_THREADS, TW_SMEM_BYTES, c->stream>>>(c->net.tower_wimg, c->net.tower_pimg, c->ws.nn_in, images_dev,
