@@ -82,7 +82,7 @@ struct omk_ctx {
     int fc0_mode = 1;               // 0: fp32 CUDA-core k_gemm, 1: tcgen05 3xTF32 k_fc0_tc
     void *fc0_tc_state = nullptr;   // tensor maps of the tensor-core path (fc0_tc.cu)
     int fc0_pair = 1;               // 1: fc0 runs the cta_group::2 (CTA pair, 256x256 tile) kernel; 0: one CTA per 128x256 tile
-    int tower_pair = 0;             // 1: k_tower_tc3 (CTA pair, three positions per iteration)
+    int tower_pair = 1;             // 1: k_tower_tc3 (CTA pair, three positions per iteration); 0: k_tower_tc (one position per CTA)
     int tower_mode = 1;             // 0: fp32 CUDA-core k_tower, 1: tcgen05 3xTF32 k_tower_tc
 
     // self-play driver state

@@ -425,6 +425,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             const long long off = real ? (long long)row * 10368 + (long long)p * 128 + half * 64 : -1ll;
             tw_store_out(stage, lane, off, x, act0, act0_hi, act0_lo);
         }
+        TW_STAMP(31);
     }
     // (timestamps: 0 start, 1 stem done, then per block: conv0 done, E1+sync, dw stored, conv1 done, E2 stored, conv2 done, E3 stored)
     // drain the weight prefetch that was issued one block ahead, then release TMEM
@@ -604,7 +605,8 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                     o.w = tw_lrelu(d[c + 3] + b.w);
                     if (real) {
                         *reinterpret_cast<float4 *>(H0b + (slot * kCells + p) * TW_HSTRIDE + half * 16 + c) = o;
-                        if (j == 1) {  // the peer keeps this position in its slot 1 - peer_rank = rank
+                        // only the band the peer's stencil can reach (pixels 37..46 from CTA 0, 47..56 from CTA 1) is mirrored
+                        if (j == 1 && (rank == 0 ? p >= 37 : p <= 56)) {  // the peer keeps this position in its slot 1 - peer_rank = rank
                             const uint32_t ra = peer_h0b + (uint32_t)((((int)rank * kCells + p) * TW_HSTRIDE + half * 16 + c) * 4);
                             asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
                         }
@@ -735,6 +737,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
             const long long off = real ? (long long)row * 10368 + (long long)p * 128 + half * 64 : -1ll;
             tw_store_out(stage, lane, off, x, act0, act0_hi, act0_lo);
         }
+        TW_STAMP(31);
     }
     // (timestamps: 0 start, 1 stem done, then per block: conv0 done, E1+sync, dw stored, conv1 done, E2 stored, conv2 done, E3 stored)
     // drain the weight prefetch that was issued one block ahead, then release TMEM

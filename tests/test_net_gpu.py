@@ -202,6 +202,28 @@ def test_fc0_single_cta_and_cta_pair_kernels_agree(omk):
     assert res[0][0].tobytes() == res[1][0].tobytes() and res[0][1].tobytes() == res[1][1].tobytes()
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 80, 443, 444, 445, 1000])
+def test_tower_single_cta_and_cta_pair_kernels_agree(omk, n):
+    """OMK_TOWER_PAIR=0 (one position per CTA) and =1 (a CTA pair walks position triples, the middle position's stencil
+    band mirrored through DSMEM) must give bit-identical outputs, including partial last triples and more triples than
+    SM pairs."""
+    import os
+
+    from oracle import net_oracle
+
+    params = net_oracle.random_params(0)
+    boards, turns = random_positions(n, 300 + n)
+    res = []
+    for pair in ("0", "1"):
+        os.environ["OMK_TOWER_PAIR"] = pair
+        c = omk.Context(device=0, capacity_envs=1, capacity_trees=1, capacity_nodes=16, seed=0)
+        c.net_load_params(params)
+        res.append(c.net_eval(boards, turns))
+        c.close()
+    del os.environ["OMK_TOWER_PAIR"]
+    assert res[0][0].tobytes() == res[1][0].tobytes() and res[0][1].tobytes() == res[1][1].tobytes()
+
+
 def test_tensor_core_kernels_are_in_the_library(omk):
     """SASS evidence: tcgen05.mma -> UTC*MMA, TMA -> UTMALDG / UBLKCP, tcgen05.ld/st -> LDTM / STTM."""
     import subprocess

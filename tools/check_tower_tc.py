@@ -54,3 +54,4 @@ for i in list(range(0, 2)) + [2 + r * 8 + k for r in range(3) for k in range(7)]
     print(f"{nm:12s} +{int(ts[i] - prev):6d}  (t={int(ts[i] - ts[0])})")
     prev = ts[i]
 print("stem detail: img+sync", int(ts[40]-ts[0]), "math", int(ts[41]-ts[40]), "split+st issue", int(ts[42]-ts[41]), "wait::st", int(ts[1]-ts[42]))
+print("store phase", int(ts[31] - ts[30]))
