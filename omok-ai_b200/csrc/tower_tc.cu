@@ -120,7 +120,7 @@ __device__ __forceinline__ constexpr uint32_t conv0_acc(int a) { return a == 0 ?
 // per-thread stores make every warp instruction touch 32 different cache lines (measured: ~16k clk per iteration in
 // the LSU).  Instead each warp transposes through a 4.6 KB staging tile: rows in, 128-byte line segments out.
 // `off` = element offset of this lane's segment in the output arrays, or -1 for a padded / out-of-batch row.
-__device__ __forceinline__ void tw_store_part(float *stage, int lane, long long off, const float *v, float *dst) {
+__device__ __forceinline__ void tw_store_part(float *stage, int lane, const long long *orow, const float *v, float *dst) {
 #pragma unroll
     for (int cp = 0; cp < 2; ++cp) {  // two passes of 32 channels
 #pragma unroll
@@ -132,7 +132,7 @@ __device__ __forceinline__ void tw_store_part(float *stage, int lane, long long 
         for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + (lane >> 3), ch = lane & 7;
             const float4 val = *reinterpret_cast<const float4 *>(stage + rr * TW_HSTRIDE + ch * 4);
-            const long long o = __shfl_sync(0xffffffffu, off, rr);
+            const long long o = orow[it];
             if (o >= 0) *reinterpret_cast<float4 *>(dst + o + cp * 32 + ch * 4) = val;
         }
         __syncwarp();
@@ -140,16 +140,19 @@ __device__ __forceinline__ void tw_store_part(float *stage, int lane, long long 
 }
 __device__ __forceinline__ void tw_store_out(float *stage, int lane, long long off, const float *x, float *act0, float *act0_hi,
                                              float *act0_lo) {
+    long long orow[8];  // output offsets of the eight rows this lane writes (row it*4 + lane/8), fetched once
+#pragma unroll
+    for (int it = 0; it < 8; ++it) orow[it] = __shfl_sync(0xffffffffu, off, it * 4 + (lane >> 3));
     if (act0_hi) {
         float part[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c) part[c] = __uint_as_float(__float_as_uint(x[c]) & 0xFFFFE000u);
-        tw_store_part(stage, lane, off, part, act0_hi);
+        tw_store_part(stage, lane, orow, part, act0_hi);
 #pragma unroll
         for (int c = 0; c < 64; ++c) part[c] = x[c] - part[c];
-        tw_store_part(stage, lane, off, part, act0_lo);
+        tw_store_part(stage, lane, orow, part, act0_lo);
     } else {
-        tw_store_part(stage, lane, off, x, act0);
+        tw_store_part(stage, lane, orow, x, act0);
     }
 }
 
@@ -239,10 +242,16 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                 const float4 w0 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + ch);
                 const float4 w1 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + 128 + ch);
                 const float4 w2 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + 256 + ch);
-                x[c + 0] = tw_lrelu(fmaf(v2, w2.x, fmaf(v1, w1.x, fmaf(v0, w0.x, b.x))));
-                x[c + 1] = tw_lrelu(fmaf(v2, w2.y, fmaf(v1, w1.y, fmaf(v0, w0.y, b.y))));
-                x[c + 2] = tw_lrelu(fmaf(v2, w2.z, fmaf(v1, w1.z, fmaf(v0, w0.z, b.z))));
-                x[c + 3] = tw_lrelu(fmaf(v2, w2.w, fmaf(v1, w1.w, fmaf(v0, w0.w, b.w))));
+                float2 s01 = __ffma2_rn(make_float2(v0, v0), make_float2(w0.x, w0.y), make_float2(b.x, b.y));
+                float2 s23 = __ffma2_rn(make_float2(v0, v0), make_float2(w0.z, w0.w), make_float2(b.z, b.w));
+                s01 = __ffma2_rn(make_float2(v1, v1), make_float2(w1.x, w1.y), s01);
+                s23 = __ffma2_rn(make_float2(v1, v1), make_float2(w1.z, w1.w), s23);
+                s01 = __ffma2_rn(make_float2(v2, v2), make_float2(w2.x, w2.y), s01);
+                s23 = __ffma2_rn(make_float2(v2, v2), make_float2(w2.z, w2.w), s23);
+                x[c + 0] = tw_lrelu(s01.x);
+                x[c + 1] = tw_lrelu(s01.y);
+                x[c + 2] = tw_lrelu(s23.x);
+                x[c + 3] = tw_lrelu(s23.y);
             }
             TW_STAMP(41);
 #pragma unroll
@@ -326,10 +335,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                             for (int c = 0; c < 16; c += 4) {
                                 const float4 h = *reinterpret_cast<const float4 *>(hp + c);
                                 const float4 w = *reinterpret_cast<const float4 *>(wp + c);
-                                a[c + 0] = fmaf(h.x, w.x, a[c + 0]);
-                                a[c + 1] = fmaf(h.y, w.y, a[c + 1]);
-                                a[c + 2] = fmaf(h.z, w.z, a[c + 2]);
-                                a[c + 3] = fmaf(h.w, w.w, a[c + 3]);
+                                // packed fp32x2 FMA (sm_100): same results as two FFMAs, half the issue slots
+                                float2 lo2 = __ffma2_rn(make_float2(h.x, h.y), make_float2(w.x, w.y), make_float2(a[c + 0], a[c + 1]));
+                                float2 hi2 = __ffma2_rn(make_float2(h.z, h.w), make_float2(w.z, w.w), make_float2(a[c + 2], a[c + 3]));
+                                a[c + 0] = lo2.x; a[c + 1] = lo2.y; a[c + 2] = hi2.x; a[c + 3] = hi2.y;
                             }
                         }
                     }
@@ -407,10 +416,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {  // padded rows (p >= 81) carry harmless garbage; they are never stored
                         const float4 b = *reinterpret_cast<const float4 *>(bp + PI_B2 + half * 64 + c + i);
-                        x[c + i + 0] = tw_lrelu(d[c + i + 0] + b.x + x[c + i + 0]);
-                        x[c + i + 1] = tw_lrelu(d[c + i + 1] + b.y + x[c + i + 1]);
-                        x[c + i + 2] = tw_lrelu(d[c + i + 2] + b.z + x[c + i + 2]);
-                        x[c + i + 3] = tw_lrelu(d[c + i + 3] + b.w + x[c + i + 3]);
+                        const float2 t01 = __fadd2_rn(__fadd2_rn(make_float2(d[c + i + 0], d[c + i + 1]), make_float2(b.x, b.y)),
+                                                      make_float2(x[c + i + 0], x[c + i + 1]));
+                        const float2 t23 = __fadd2_rn(__fadd2_rn(make_float2(d[c + i + 2], d[c + i + 3]), make_float2(b.z, b.w)),
+                                                      make_float2(x[c + i + 2], x[c + i + 3]));
+                        const float2 u01 = __fmul2_rn(t01, make_float2(0.2f, 0.2f)), u23 = __fmul2_rn(t23, make_float2(0.2f, 0.2f));
+                        x[c + i + 0] = fmaxf(t01.x, u01.x);
+                        x[c + i + 1] = fmaxf(t01.y, u01.y);
+                        x[c + i + 2] = fmaxf(t23.x, u23.x);
+                        x[c + i + 3] = fmaxf(t23.y, u23.y);
                     }
                     if (r < 2) tw_store_split16(tlane + C_XHI + half * 64 + c, tlane + C_XLO + half * 64 + c, x + c);
                 }
@@ -540,10 +554,16 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                 const float4 w0 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + ch);
                 const float4 w1 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + 128 + ch);
                 const float4 w2 = *reinterpret_cast<const float4 *>(PAR + PI_WSTEM + 256 + ch);
-                x[c + 0] = tw_lrelu(fmaf(v2, w2.x, fmaf(v1, w1.x, fmaf(v0, w0.x, b.x))));
-                x[c + 1] = tw_lrelu(fmaf(v2, w2.y, fmaf(v1, w1.y, fmaf(v0, w0.y, b.y))));
-                x[c + 2] = tw_lrelu(fmaf(v2, w2.z, fmaf(v1, w1.z, fmaf(v0, w0.z, b.z))));
-                x[c + 3] = tw_lrelu(fmaf(v2, w2.w, fmaf(v1, w1.w, fmaf(v0, w0.w, b.w))));
+                float2 s01 = __ffma2_rn(make_float2(v0, v0), make_float2(w0.x, w0.y), make_float2(b.x, b.y));
+                float2 s23 = __ffma2_rn(make_float2(v0, v0), make_float2(w0.z, w0.w), make_float2(b.z, b.w));
+                s01 = __ffma2_rn(make_float2(v1, v1), make_float2(w1.x, w1.y), s01);
+                s23 = __ffma2_rn(make_float2(v1, v1), make_float2(w1.z, w1.w), s23);
+                s01 = __ffma2_rn(make_float2(v2, v2), make_float2(w2.x, w2.y), s01);
+                s23 = __ffma2_rn(make_float2(v2, v2), make_float2(w2.z, w2.w), s23);
+                x[c + 0] = tw_lrelu(s01.x);
+                x[c + 1] = tw_lrelu(s01.y);
+                x[c + 2] = tw_lrelu(s23.x);
+                x[c + 3] = tw_lrelu(s23.y);
             }
             TW_STAMP(41);
 #pragma unroll
@@ -638,10 +658,10 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
                             for (int c = 0; c < 16; c += 4) {
                                 const float4 h = *reinterpret_cast<const float4 *>(hp + c);
                                 const float4 w = *reinterpret_cast<const float4 *>(wp + c);
-                                a[c + 0] = fmaf(h.x, w.x, a[c + 0]);
-                                a[c + 1] = fmaf(h.y, w.y, a[c + 1]);
-                                a[c + 2] = fmaf(h.z, w.z, a[c + 2]);
-                                a[c + 3] = fmaf(h.w, w.w, a[c + 3]);
+                                // packed fp32x2 FMA (sm_100): same results as two FFMAs, half the issue slots
+                                float2 lo2 = __ffma2_rn(make_float2(h.x, h.y), make_float2(w.x, w.y), make_float2(a[c + 0], a[c + 1]));
+                                float2 hi2 = __ffma2_rn(make_float2(h.z, h.w), make_float2(w.z, w.w), make_float2(a[c + 2], a[c + 3]));
+                                a[c + 0] = lo2.x; a[c + 1] = lo2.y; a[c + 2] = hi2.x; a[c + 3] = hi2.y;
                             }
                         }
                     }
@@ -719,10 +739,15 @@ __global__ void __launch_bounds__(TW_THREADS, 1)
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {  // padded rows (p >= 81) carry harmless garbage; they are never stored
                         const float4 b = *reinterpret_cast<const float4 *>(bp + PI_B2 + half * 64 + c + i);
-                        x[c + i + 0] = tw_lrelu(d[c + i + 0] + b.x + x[c + i + 0]);
-                        x[c + i + 1] = tw_lrelu(d[c + i + 1] + b.y + x[c + i + 1]);
-                        x[c + i + 2] = tw_lrelu(d[c + i + 2] + b.z + x[c + i + 2]);
-                        x[c + i + 3] = tw_lrelu(d[c + i + 3] + b.w + x[c + i + 3]);
+                        const float2 t01 = __fadd2_rn(__fadd2_rn(make_float2(d[c + i + 0], d[c + i + 1]), make_float2(b.x, b.y)),
+                                                      make_float2(x[c + i + 0], x[c + i + 1]));
+                        const float2 t23 = __fadd2_rn(__fadd2_rn(make_float2(d[c + i + 2], d[c + i + 3]), make_float2(b.z, b.w)),
+                                                      make_float2(x[c + i + 2], x[c + i + 3]));
+                        const float2 u01 = __fmul2_rn(t01, make_float2(0.2f, 0.2f)), u23 = __fmul2_rn(t23, make_float2(0.2f, 0.2f));
+                        x[c + i + 0] = fmaxf(t01.x, u01.x);
+                        x[c + i + 1] = fmaxf(t01.y, u01.y);
+                        x[c + i + 2] = fmaxf(t23.x, u23.x);
+                        x[c + i + 3] = fmaxf(t23.y, u23.y);
                     }
                     if (r < 2) tw_store_split16(tlane + C_XHI + half * 64 + c, tlane + C_XLO + half * 64 + c, x + c);
                 }
