@@ -1,0 +1,410 @@
+// fc_f16.cu -- K3 tensor-core path for the fully connected layers fc0 (10368 -> 512, 67 % of the network's flops)
+// and fc1 (512 -> 512), fp16-split ("3 x FP16") edition.
+//
+//   C[M x 512] = lrelu( A[M x K] . W[K x 512] + b )        (alpha-zero/src/network.rs:139-163)
+//
+// fp32-class accuracy on the 5th-gen tensor cores at the FP16 rate: every operand is split x = hi + lo with
+// hi = fp16(x) and lo = fp16(x - hi) (22 significant bits; weights are pre-scaled by a power of two so that
+// their low parts stay in fp16's normal range) and each k-step issues three tcgen05.mma kind::f16 into one
+// TMEM accumulator:    lo.hi + hi.lo + hi.hi     (the dropped lo.lo term is ~2^-22 relative).
+// Measured on the CPU (tools/emulate_split.py): priors within 9e-5 of fp64, the same as plain fp32; one-pass
+// TF32 misses the 1e-3 bar by 50x and a bf16 split by 1.2x.  Against the 3 x TF32 kernels this replaces
+// (fc0_tc.cu) every MMA carries twice the K, operand bytes halve, and the MMA count halves.
+//
+// The tensor-core accumulator truncates (measured on the TF32 path: 86 % of outputs biased toward zero), so K is
+// accumulated in TMEM only over chunks of CHUNK k-blocks; each chunk is drained into fp32 registers with
+// round-to-nearest adds while the tensor cores fill the other TMEM buffer.
+//
+// PAIR = true  (fc0): a CTA pair (2x1 cluster) owns a 256 x 256 tile: each CTA TMA-loads its own 128 rows of A
+//                     and HALF of the B tile, tcgen05.mma.cta_group::2 reads both CTAs' shared memory; 3-stage
+//                     ring of 64 KB stages; the leader CTA issues, commits multicast to both CTAs.
+// PAIR = false (fc1): one CTA per 128 x 256 tile, 2-stage ring of 96 KB stages.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = drain / epilogue (two per lane quadrant).
+#include <cstdio>
+#include <cuda.h>
+
+#include "omk_internal.h"
+#include "tc_ptx.cuh"
+
+namespace omk {
+
+using namespace tc;
+
+constexpr int F_BM = 128, F_BN = 256, F_BK = 64;  // BK fp16 elements = one 128-byte swizzle row
+constexpr int F_N = 512;
+constexpr int F_K0 = 10368, F_K1 = 512;
+constexpr int F_A_BYTES = F_BM * F_BK * 2;        // 16 KB
+constexpr int F_THREADS = 320;
+constexpr uint32_t F_TMEM_COLS = 512;             // two 256-column accumulator buffers
+constexpr int F_CHUNK0 = 9;                       // fc0: 162 k-blocks = 18 x 9
+constexpr int F_CHUNK1 = 8;                       // fc1: 8 k-blocks = 1 x 8
+
+template <bool PAIR>
+struct FcCfg {
+    static constexpr int kStages = PAIR ? 3 : 2;
+    static constexpr int kBRows = PAIR ? 128 : 256;               // B rows loaded by one CTA
+    static constexpr int kBBytes = kBRows * F_BK * 2;             // 16 / 32 KB
+    static constexpr int kStageBytes = 2 * F_A_BYTES + 2 * kBBytes;  // 64 / 96 KB
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+    static constexpr uint32_t kIdesc = idesc_f16(PAIR ? 256 : 128, F_BN);
+};
+
+template <int K, int CHUNK, bool PAIR>
+__global__ void __launch_bounds__(F_THREADS, 1)
+    k_fc16(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+           const float *__restrict__ bias, const float *__restrict__ inv_scale_p, float *__restrict__ C,
+           __half *__restrict__ C_hi, __half *__restrict__ C_lo, const uint32_t *n_req, int max_rows) {
+    using Cfg = FcCfg<PAIR>;
+    constexpr int CG = PAIR ? 2 : 1;
+    constexpr int NKB = K / F_BK;
+    constexpr int NCHUNK = NKB / CHUNK;
+    static_assert(K % F_BK == 0 && NKB % CHUNK == 0, "chunking must tile K");
+    extern __shared__ uint8_t smem_raw[];
+    const int rows = (int)min(*n_req, (uint32_t)max_rows);
+    uint32_t rank = 0;
+    int m0, n0;
+    if constexpr (PAIR) {
+        // blockIdx.x = ((pair * 2 + n_tile) * 2 + rank): the two N tiles of one row pair are neighbours in launch order so
+        // that the second reads its A rows from L2, not from DRAM
+        rank = cluster_rank();
+        const int pair = blockIdx.x >> 2;
+        m0 = pair * 256 + (int)rank * F_BM;
+        n0 = (int)((blockIdx.x >> 1) & 1u) * F_BN;
+        if (pair * 256 >= rows) return;  // uniform for the whole cluster
+    } else {
+        m0 = blockIdx.y * F_BM;
+        n0 = blockIdx.x * F_BN;
+        if (m0 >= rows) return;  // uniform for the whole CTA, before any barrier or TMEM use
+    }
+    const bool leader = rank == 0;
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bars = base + Cfg::kStages * Cfg::kStageBytes;
+    const uint32_t full0 = bars, empty0 = bars + 8 * Cfg::kStages, tmem_full0 = bars + 16 * Cfg::kStages,
+                   tmem_empty0 = tmem_full0 + 16, tmem_slot = tmem_empty0 + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_map(&map_a_hi);
+        prefetch_map(&map_a_lo);
+        prefetch_map(&map_b_hi);
+        prefetch_map(&map_b_lo);
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tmem_full0 + 8 * b, 1);
+            mbar_init(tmem_empty0 + 8 * b, PAIR ? 16 : 8);  // one arrival per drain warp (of both CTAs)
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<CG>(tmem_slot, F_TMEM_COLS);
+    fence_before();
+    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before anything crosses the pair
+    fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            for (int kb = 0; kb < NKB; ++kb) {
+                const int s = kb % Cfg::kStages;
+                const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const uint32_t st = base + s * Cfg::kStageBytes;
+                if constexpr (PAIR) {  // both CTAs load; the transaction bytes of both land on the leader's barrier
+                    const uint32_t lbar = mapa(full0 + 8 * s, 0);
+                    if (leader) mbar_expect_tx(full0 + 8 * s, 2 * Cfg::kStageBytes);
+                    tma_load_2d_2sm(st, &map_a_hi, lbar, kb * F_BK, m0);
+                    tma_load_2d_2sm(st + F_A_BYTES, &map_a_lo, lbar, kb * F_BK, m0);
+                    tma_load_2d_2sm(st + 2 * F_A_BYTES, &map_b_hi, lbar, kb * F_BK, n0 + (int)rank * 128);
+                    tma_load_2d_2sm(st + 2 * F_A_BYTES + Cfg::kBBytes, &map_b_lo, lbar, kb * F_BK, n0 + (int)rank * 128);
+                } else {
+                    const uint32_t bar = full0 + 8 * s;
+                    mbar_expect_tx(bar, Cfg::kStageBytes);
+                    tma_load_2d(st, &map_a_hi, bar, kb * F_BK, m0);
+                    tma_load_2d(st + F_A_BYTES, &map_a_lo, bar, kb * F_BK, m0);
+                    tma_load_2d(st + 2 * F_A_BYTES, &map_b_hi, bar, kb * F_BK, n0);
+                    tma_load_2d(st + 2 * F_A_BYTES + Cfg::kBBytes, &map_b_lo, bar, kb * F_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {  // ===== MMA issuer (the leader CTA of a pair) =====
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+                const int buf = ch & 1;
+                const uint32_t use = (uint32_t)(ch >> 1);
+                mbar_wait(tmem_empty0 + 8 * buf, (use & 1u) ^ 1u);  // drained (passes at once for the first use)
+                fence_after();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * F_BN);
+                for (int kc = 0; kc < CHUNK; ++kc) {
+                    const int kb = ch * CHUNK + kc;
+                    const int s = kb % Cfg::kStages;
+                    const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);
+                    fence_after();
+                    const uint32_t st = base + s * Cfg::kStageBytes;
+                    const uint64_t a_hi = desc_sw128(st), a_lo = desc_sw128(st + F_A_BYTES);
+                    const uint64_t b_hi = desc_sw128(st + 2 * F_A_BYTES), b_lo = desc_sw128(st + 2 * F_A_BYTES + Cfg::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < F_BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);  // 16 fp16 = 32 bytes per k-step inside the swizzle atom
+                        umma_f16_ss<CG>(tmem_acc, a_lo + adv, b_hi + adv, Cfg::kIdesc, (kc | k) != 0 ? 1u : 0u);
+                        umma_f16_ss<CG>(tmem_acc, a_hi + adv, b_lo + adv, Cfg::kIdesc, 1u);
+                        umma_f16_ss<CG>(tmem_acc, a_hi + adv, b_hi + adv, Cfg::kIdesc, 1u);
+                    }
+                    if constexpr (PAIR) umma_commit_2sm(empty0 + 8 * s); else umma_commit(empty0 + 8 * s);
+                }
+                if constexpr (PAIR) umma_commit_2sm(tmem_full0 + 8 * buf); else umma_commit(tmem_full0 + 8 * buf);
+            }
+        }
+    } else {  // ===== drain + epilogue: warps 2..9; lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        float acc[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) acc[j] = 0.0f;
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+            const int buf = ch & 1;
+            const uint32_t use = (uint32_t)(ch >> 1);
+            mbar_wait(tmem_full0 + 8 * buf, use & 1u);
+            fence_after();
+#pragma unroll
+            for (int c = 0; c < 128; c += 32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * F_BN + half * 128 + c), v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c + j] += v[j];
+            }
+            fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_cluster(mapa(tmem_empty0 + 8 * buf, 0)); else mbar_arrive(tmem_empty0 + 8 * buf);
+            }
+        }
+        const int row = m0 + q * 32 + lane;
+        const size_t coff = (size_t)row * F_N + n0 + half * 128;
+        const float *brow = bias + n0 + half * 128;
+        const float inv_scale = *inv_scale_p;  // undo the power-of-two weight scaling (exact)
+        if (row < rows) {  // rows past the batch are never stored (the tile may extend past the workspace)
+#pragma unroll
+            for (int j = 0; j < 128; j += 8) {
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; i += 4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(brow + j + i);
+                    o[i + 0] = fmaf(acc[j + i + 0], inv_scale, b.x);
+                    o[i + 1] = fmaf(acc[j + i + 1], inv_scale, b.y);
+                    o[i + 2] = fmaf(acc[j + i + 2], inv_scale, b.z);
+                    o[i + 3] = fmaf(acc[j + i + 3], inv_scale, b.w);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.2f * o[i]);
+                if (C) {
+                    *reinterpret_cast<float4 *>(C + coff + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4 *>(C + coff + j + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                }
+                if (C_hi) {
+                    uint4 h, l;
+                    split2_f16(o[0], o[1], h.x, l.x);
+                    split2_f16(o[2], o[3], h.y, l.y);
+                    split2_f16(o[4], o[5], h.z, l.z);
+                    split2_f16(o[6], o[7], h.w, l.w);
+                    *reinterpret_cast<uint4 *>(C_hi + coff + j) = h;
+                    *reinterpret_cast<uint4 *>(C_lo + coff + j) = l;
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();  // the peer's shared memory and TMEM stay alive until every MMA and drain has finished
+    if (warp == 1) {
+        fence_after();
+        tmem_dealloc<CG>(tmem_base, F_TMEM_COLS);
+    }
+}
+
+// max |w| of a tensor as fp32 bits (non-negative floats order like their bit patterns)
+__global__ void k_absmax_bits(const float *__restrict__ w, long long n, uint32_t *out) {
+    uint32_t m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(w[i]) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// W[K][512] -> K-major transposed fp16 hi / lo parts Wt[512][K] of W * 2^s; writes 2^-s to *inv_scale
+__global__ void k_fc16_split_weights(const float *__restrict__ W, const uint32_t *absmax_bits, __half *__restrict__ hi,
+                                     __half *__restrict__ lo, float *inv_scale, int K) {
+    __shared__ float tile[32][33];
+    const float scale = f16_split_scale(*absmax_bits);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *inv_scale = 1.0f / scale;
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = W[(size_t)(k0 + r) * F_N + n0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const float x = tile[tx][r] * scale;  // W[k0+tx][n0+r]
+        const __half h = __float2half_rn(x);
+        hi[(size_t)(n0 + r) * K + k0 + tx] = h;
+        lo[(size_t)(n0 + r) * K + k0 + tx] = __float2half_rn(x - __half2float(h));
+    }
+}
+
+// debug / A-B helpers: fp32 activations <-> fp16 hi/lo split (lets either half of the network run on another path)
+__global__ void k_f32_to_split16(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const __half h = __float2half_rn(x[i]);
+        hi[i] = h;
+        lo[i] = __float2half_rn(x[i] - __half2float(h));
+    }
+}
+__global__ void k_split16_to_f32(const __half *__restrict__ hi, const __half *__restrict__ lo, float *__restrict__ x, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] = __half2float(hi[i]) + __half2float(lo[i]);
+}
+void launch_f32_to_split16(omk_ctx *c, const float *x, __half *hi, __half *lo, long long n) {
+    k_f32_to_split16<<<1184, 256, 0, c->stream>>>(x, hi, lo, n);
+    c->launches++;
+}
+void launch_split16_to_f32(omk_ctx *c, const __half *hi, const __half *lo, float *x, long long n) {
+    k_split16_to_f32<<<1184, 256, 0, c->stream>>>(hi, lo, x, n);
+    c->launches++;
+}
+
+typedef CUresult (*PFN_encodeTiled16)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D fp16 [rows][K] row-major, boxes of box_rows x 64 elements (128-byte rows), SWIZZLE_128B
+static bool encode_map16(CUtensorMap *map, __half *ptr, uint64_t rows, uint32_t box_rows, int K) {
+    static PFN_encodeTiled16 fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+        fn = (PFN_encodeTiled16)p;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(__half)};
+    const cuuint32_t box[2] = {(cuuint32_t)F_BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Fc16State {
+    CUtensorMap map0_a_hi, map0_a_lo, map0_b_hi, map0_b_lo;  // fc0 (B boxes of 128 rows: the pair kernel loads half tiles)
+    CUtensorMap map1_a_hi, map1_a_lo, map1_b_hi, map1_b_lo;  // fc1 (B boxes of 256 rows)
+    __half *a_ptr = nullptr;
+    int a_rows = 0;
+    bool weights_ready = false;
+};
+
+static Fc16State *state16_of(omk_ctx *c) {
+    if (!c->fc16_state) c->fc16_state = new Fc16State();
+    return reinterpret_cast<Fc16State *>(c->fc16_state);
+}
+
+void fc16_free(omk_ctx *c) {
+    delete reinterpret_cast<Fc16State *>(c->fc16_state);
+    c->fc16_state = nullptr;
+}
+
+// (re)build the scaled, split, transposed weights of fc0 and fc1; call after the weights change
+bool fc16_prepare_weights(omk_ctx *c) {
+    Fc16State *s = state16_of(c);
+    NetWeights &w = c->net;
+    if (!w.fc0_wt_h16) {
+        if (cudaMalloc(&w.fc0_wt_h16, sizeof(__half) * (size_t)F_K0 * F_N) != cudaSuccess) return false;
+        if (cudaMalloc(&w.fc0_wt_l16, sizeof(__half) * (size_t)F_K0 * F_N) != cudaSuccess) return false;
+        if (cudaMalloc(&w.fc1_wt_h16, sizeof(__half) * (size_t)F_K1 * F_N) != cudaSuccess) return false;
+        if (cudaMalloc(&w.fc1_wt_l16, sizeof(__half) * (size_t)F_K1 * F_N) != cudaSuccess) return false;
+        if (cudaMalloc(&w.fc_inv_scale, sizeof(float) * 2) != cudaSuccess) return false;
+        if (cudaMalloc(&w.fc_absmax, sizeof(uint32_t) * 2) != cudaSuccess) return false;
+    }
+    cudaMemsetAsync(w.fc_absmax, 0, sizeof(uint32_t) * 2, c->stream);
+    k_absmax_bits<<<592, 256, 0, c->stream>>>(w.t[23], (long long)F_K0 * F_N, w.fc_absmax);
+    k_absmax_bits<<<148, 256, 0, c->stream>>>(w.t[25], (long long)F_K1 * F_N, w.fc_absmax + 1);
+    k_fc16_split_weights<<<dim3(F_K0 / 32, F_N / 32), 256, 0, c->stream>>>(w.t[23], w.fc_absmax, w.fc0_wt_h16, w.fc0_wt_l16,
+                                                                           w.fc_inv_scale, F_K0);
+    k_fc16_split_weights<<<dim3(F_K1 / 32, F_N / 32), 256, 0, c->stream>>>(w.t[25], w.fc_absmax + 1, w.fc1_wt_h16, w.fc1_wt_l16,
+                                                                           w.fc_inv_scale + 1, F_K1);
+    c->launches += 4;
+    if (!encode_map16(&s->map0_b_hi, w.fc0_wt_h16, F_N, 128, F_K0)) return false;
+    if (!encode_map16(&s->map0_b_lo, w.fc0_wt_l16, F_N, 128, F_K0)) return false;
+    if (!encode_map16(&s->map1_b_hi, w.fc1_wt_h16, F_N, F_BN, F_K1)) return false;
+    if (!encode_map16(&s->map1_b_lo, w.fc1_wt_l16, F_N, F_BN, F_K1)) return false;
+    s->weights_ready = true;
+    return true;
+}
+
+static bool refresh_maps16(omk_ctx *c, Fc16State *s) {
+    if (s->a_ptr == c->ws.act0_h16 && s->a_rows == c->ws.max_rows) return true;
+    if (!encode_map16(&s->map0_a_hi, c->ws.act0_h16, (uint64_t)c->ws.max_rows, F_BM, F_K0)) return false;
+    if (!encode_map16(&s->map0_a_lo, c->ws.act0_l16, (uint64_t)c->ws.max_rows, F_BM, F_K0)) return false;
+    if (!encode_map16(&s->map1_a_hi, c->ws.act1_h16, (uint64_t)c->ws.max_rows, F_BM, F_K1)) return false;
+    if (!encode_map16(&s->map1_a_lo, c->ws.act1_l16, (uint64_t)c->ws.max_rows, F_BM, F_K1)) return false;
+    s->a_ptr = c->ws.act0_h16;
+    s->a_rows = c->ws.max_rows;
+    return true;
+}
+
+static bool check_launch(const char *what) {
+    const cudaError_t le = cudaPeekAtLastError();
+    if (le == cudaSuccess) return true;
+    fprintf(stderr, "omok_b200: %s launch failed: %s\n", what, cudaGetErrorString(le));
+    return false;
+}
+
+// fc0: act0_h16/l16 -> act1_h16/l16 (the A operand of fc1)
+bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
+    Fc16State *s = state16_of(c);
+    if (!s->weights_ready || !refresh_maps16(c, s)) return false;
+    auto kern = k_fc16<F_K0, F_CHUNK0, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<true>::kSmemBytes);
+    const int pairs = (rows_bound + 255) / 256;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (F_N / F_BN) * pairs, 1);
+    cfg.blockDim = dim3(F_THREADS);
+    cfg.dynamicSmemBytes = FcCfg<true>::kSmemBytes;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float *bias_p = c->net.t[24];
+    const float *inv_p = c->net.fc_inv_scale;
+    float *c_f32 = nullptr;
+    __half *c_hi = c->ws.act1_h16, *c_lo = c->ws.act1_l16;
+    const uint32_t *nreq_p = c->ws.n_req;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, s->map0_a_hi, s->map0_a_lo, s->map0_b_hi, s->map0_b_lo, bias_p, inv_p, c_f32,
+                                             c_hi, c_lo, nreq_p, rows_bound);
+    if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_fc16 pair): %s\n", cudaGetErrorString(e));
+    c->launches++;
+    return e == cudaSuccess && check_launch("fc0 (fp16 split)");
+}
+
+// fc1: act1_h16/l16 -> act2 (fp32, read by the heads GEMM)
+bool launch_fc1_f16(omk_ctx *c, int rows_bound) {
+    Fc16State *s = state16_of(c);
+    if (!s->weights_ready || !refresh_maps16(c, s)) return false;
+    auto kern = k_fc16<F_K1, F_CHUNK1, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<false>::kSmemBytes);
+    const int mt = (rows_bound + F_BM - 1) / F_BM;
+    kern<<<dim3(F_N / F_BN, mt), F_THREADS, FcCfg<false>::kSmemBytes, c->stream>>>(
+        s->map1_a_hi, s->map1_a_lo, s->map1_b_hi, s->map1_b_lo, c->net.t[26], c->net.fc_inv_scale + 1, c->ws.act2, nullptr, nullptr,
+        c->ws.n_req, rows_bound);
+    c->launches++;
+    return check_launch("fc1 (fp16 split)");
+}
+
+}  // namespace omk

@@ -421,6 +421,19 @@ void launch_net_init_random(omk_ctx *c, uint64_t seed) {
     }
 }
 
+// A/B helper: TF32 hi/lo split of act0 (tower on another path, fc0 on the 3xTF32 kernels)
+__global__ void k_split_tf32(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float h = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = x[i] - h;
+    }
+}
+static void launch_tower_split_tf32(omk_ctx *c, int rows) {
+    k_split_tf32<<<1184, 256, 0, c->stream>>>(c->ws.act0, c->ws.act0_hi, c->ws.act0_lo, (long long)rows * kFlat);
+    c->launches++;
+}
+
 void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     cudaFuncSetAttribute(k_tower, cudaFuncAttributeMaxDynamicSharedMemorySize, kTowerSmemBytes);
     if (max_rows > c->ws.max_rows) max_rows = c->ws.max_rows;
@@ -434,29 +447,48 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
         tw.b1[r] = c->net.t[b + 4]; tw.w2[r] = c->net.t[b + 5]; tw.b2[r] = c->net.t[b + 6];
     }
     const int tower_grid = max_rows < c->n_sms ? max_rows : c->n_sms;
+    const int mt = (max_rows + GM - 1) / GM;
+    const long long n0 = (long long)max_rows * kFlat;
+    // fc0_mode / tower_mode: 0 = fp32 CUDA cores, 1 = tcgen05 3xTF32, 2 = tcgen05 3xFP16 (default).  Mixed modes exist
+    // for A/B checks only and go through an explicit conversion pass.
     bool sp = prof_begin(c, OMK_K_TOWER, 1);
-    const bool tc = c->fc0_mode == 1;
-    if (c->tower_mode == 1) {
-        launch_tower_tc(c, images_dev, max_rows, tc);
+    if (c->tower_mode == 2) {
+        launch_tower_f16(c, images_dev, max_rows);
         c->launches--;  // counted once below with the other network kernels
+        if (c->fc0_mode != 2) {
+            launch_split16_to_f32(c, c->ws.act0_h16, c->ws.act0_l16, c->ws.act0, n0);
+            if (c->fc0_mode == 1) launch_tower_split_tf32(c, max_rows);
+        }
     } else {
-        k_tower<<<tower_grid, kTowerThreads, kTowerSmemBytes, c->stream>>>(tw, c->ws.nn_in, images_dev, c->ws.n_req, max_rows,
-                                                                          c->ws.act0, tc ? c->ws.act0_hi : nullptr,
-                                                                          tc ? c->ws.act0_lo : nullptr);
+        const bool tc = c->fc0_mode == 1;
+        if (c->tower_mode == 1) {
+            launch_tower_tc(c, images_dev, max_rows, tc);
+            c->launches--;
+        } else {
+            k_tower<<<tower_grid, kTowerThreads, kTowerSmemBytes, c->stream>>>(tw, c->ws.nn_in, images_dev, c->ws.n_req, max_rows,
+                                                                              c->ws.act0, tc ? c->ws.act0_hi : nullptr,
+                                                                              tc ? c->ws.act0_lo : nullptr);
+        }
+        if (c->fc0_mode == 2) launch_f32_to_split16(c, c->ws.act0, c->ws.act0_h16, c->ws.act0_l16, n0);
     }
     prof_end(c, sp);
-    const int mt = (max_rows + GM - 1) / GM;
     sp = prof_begin(c, OMK_K_FC0, 1);
-    if (tc) {
+    if (c->fc0_mode == 2) {
+        launch_fc0_f16(c, max_rows);
+        c->launches--;
+    } else if (c->fc0_mode == 1) {
         launch_fc0_tc(c, max_rows, /*split_out=*/true);
-        c->launches--;  // counted once below with the other network kernels
+        c->launches--;
     } else {
         k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act0, c->net.t[23], c->net.t[24], c->ws.act1, c->ws.n_req,
                                                           max_rows, kFc, kFlat, 1);
     }
     prof_end(c, sp);
     sp = prof_begin(c, OMK_K_FC1, 2);
-    if (tc) {
+    if (c->fc0_mode == 2) {
+        launch_fc1_f16(c, max_rows);
+        c->launches--;
+    } else if (c->fc0_mode == 1) {
         launch_fc1_tc(c, max_rows);
         c->launches--;
     } else {

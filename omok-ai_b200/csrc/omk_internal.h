@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <vector>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/omok_b200.h"
@@ -23,6 +24,14 @@ struct NetWeights {
     float *fc1_wt_hi = nullptr, *fc1_wt_lo = nullptr;  // [512][512] same for fc1
     uint8_t *tower_wimg = nullptr;  // 3 x 72 KB pre-swizzled B-operand images of the tower weights (tower_tc.cu)
     float *tower_pimg = nullptr;    // fp32 stem / bias / depthwise parameters
+    // fp16-split tensor-core path (fc_f16.cu, tower_f16.cu): weights scaled by a power of two, then split hi/lo
+    __half *fc0_wt_h16 = nullptr, *fc0_wt_l16 = nullptr;  // [512][10368] K-major
+    __half *fc1_wt_h16 = nullptr, *fc1_wt_l16 = nullptr;  // [512][512]
+    float *fc_inv_scale = nullptr;     // [2] 2^-s of fc0, fc1
+    uint32_t *fc_absmax = nullptr;     // [2] max |w| bits
+    uint8_t *tower16_wimg = nullptr;   // 3 x 36 KB pre-swizzled B-operand images
+    float *tower16_pimg = nullptr;     // fp32 stem / bias / depthwise parameters + inverse scales
+    uint32_t *tower16_absmax = nullptr;  // [9]
     bool loaded = false;
 };
 
@@ -38,6 +47,8 @@ struct Workspace {  // evaluator request/response buffers, sized for max_rows
     float *act0_lo = nullptr;     // [max_rows][10368] residual low part
     float *act1 = nullptr;        // [max_rows][512]
     float *act1_hi = nullptr, *act1_lo = nullptr;  // [max_rows][512] hi/lo split of fc0's output (tensor-core fc1)
+    __half *act0_h16 = nullptr, *act0_l16 = nullptr;  // [max_rows][10368] fp16 hi/lo split of the tower output (fp16-split path)
+    __half *act1_h16 = nullptr, *act1_l16 = nullptr;  // [max_rows][512] fp16 hi/lo split of fc0's output
     float *act2 = nullptr;        // [max_rows][512]
     float *logits = nullptr;      // [max_rows][128]
     uint32_t *n_req = nullptr;    // device counter
@@ -79,11 +90,13 @@ struct omk_ctx {
 
     omk::NetWeights net;
     omk::Workspace ws;
-    int fc0_mode = 1;               // 0: fp32 CUDA-core k_gemm, 1: tcgen05 3xTF32 k_fc0_tc
+    int fc0_mode = 2;               // 0: fp32 CUDA-core k_gemm, 1: tcgen05 3xTF32 k_fc_tc, 2: tcgen05 3xFP16 k_fc16 (default)
+    void *fc16_state = nullptr;     // tensor maps of the fp16-split path (fc_f16.cu)
+    int tower16_pairs = 0;          // resident CTA pairs of k_tower16 (0 = not queried yet)
     void *fc0_tc_state = nullptr;   // tensor maps of the tensor-core path (fc0_tc.cu)
     int fc0_pair = 1;               // 1: fc0 runs the cta_group::2 (CTA pair, 256x256 tile) kernel; 0: one CTA per 128x256 tile
     int tower_pair = 1;             // 1: k_tower_tc3 (CTA pair, three positions per iteration); 0: k_tower_tc (one position per CTA)
-    int tower_mode = 1;             // 0: fp32 CUDA-core k_tower, 1: tcgen05 3xTF32 k_tower_tc
+    int tower_mode = 2;             // 0: fp32 CUDA-core k_tower, 1: tcgen05 3xTF32 k_tower_tc, 2: tcgen05 3xFP16 k_tower16 (default)
 
     // self-play driver state
     omk_selfplay_config sp_cfg{};
@@ -150,5 +163,19 @@ void fc0_tc_free(omk_ctx *c);
 bool tower_tc_prepare_weights(omk_ctx *c);
 void launch_tower_tc(omk_ctx *c, const float *images_dev, int rows_bound, bool split_out);
 void tower_tc_read_timing(long long *out64);
+
+
+// fc_f16.cu
+bool fc16_prepare_weights(omk_ctx *c);
+bool launch_fc0_f16(omk_ctx *c, int rows_bound);
+bool launch_fc1_f16(omk_ctx *c, int rows_bound);
+void fc16_free(omk_ctx *c);
+void launch_f32_to_split16(omk_ctx *c, const float *x, __half *hi, __half *lo, long long n);
+void launch_split16_to_f32(omk_ctx *c, const __half *hi, const __half *lo, float *x, long long n);
+
+// tower_f16.cu
+bool tower16_prepare_weights(omk_ctx *c);
+bool launch_tower_f16(omk_ctx *c, const float *images_dev, int rows_bound);
+void tower16_read_timing(long long *out64);
 
 }  // namespace omk

@@ -1,0 +1,576 @@
+// tower_f16.cu -- K3 tensor-core path for the residual tower (stem + 3 bottleneck blocks), fp16-split edition.
+//
+// Replaces the fp32 CUDA-core GEMMs of the tower (network.rs:65-125, network-utils lib.rs:386-461) with
+// tcgen05.mma kind::f16, 3-pass hi/lo error compensation (x = fp16(x) + fp16(x - fp16(x)); lo.hi + hi.lo + hi.hi; see
+// fc_f16.cu).  Per position the three 1x1 convolutions of a block are [81 x K] . [K x N] GEMMs with tiny K and N, so
+// the design is about latency and data placement, not MMA throughput:
+//   * the ACTIVATIONS are the A operand and live in TENSOR MEMORY (lane = pixel row, two fp16 channels per 32-bit
+//     column, hi and lo parts of a 16-channel group side by side); threads write them with tcgen05.st straight
+//     from registers -- no swizzled shared-memory stores at all;
+//   * the WEIGHTS are the B operand in shared memory, K-major SWIZZLE_128B, hi and lo parts, scaled by a power of
+//     two and pre-swizzled once on the device (k_tower16_pack), so one block's 36 KB image arrives by plain bulk
+//     copies (cp.async.bulk) into a double buffer, one block ahead;
+//   * the residual stream x stays in REGISTERS (a thread owns one pixel row x 64 channels) across all three blocks;
+//     the depthwise 3x3 goes through a small fp32 shared tile;
+//   * a CTA PAIR (2x1 cluster) walks position TRIPLES: the 243 pixel rows of three positions fill 243 of the pair's
+//     256 TMEM lanes.  The middle position straddles the two CTAs; the stencil band it needs from the peer is
+//     mirrored through distributed shared memory;
+//   * a CTA needs 256 TMEM columns, 107 KB of shared memory and <= 128 registers per thread, so TWO CTAs are
+//     resident per SM: one CTA's MMA / barrier latencies hide behind the other's CUDA-core epilogues (the 3 x TF32
+//     kernel this replaces needed all 512 columns and ran one 8-warp CTA per SM, every phase exposed).
+// Warp w works on TMEM lane quadrant w%4 and channel half w/4.  Lane 0 of warps 0..2 issues the MMA chains.
+//
+// TMEM columns: X/D3 [0,128)  16-channel group kk of x: hi [16kk,16kk+8) lo [16kk+8,16kk+16); the conv2 accumulator
+//                             D3 (fp32, 128 columns) aliases it: x's TMEM copy is dead once conv0 has read it
+//               H    [128,160) 16-channel group g of the block's hidden activations, same hi/lo packing
+//               ACC  [160,256) three 32-column partial accumulators (one per product) of conv0 / conv1
+#include <cstdio>
+
+#include "omk_internal.h"
+#include "tc_ptx.cuh"
+
+namespace omk {
+
+using namespace tc;
+
+constexpr int T16_THREADS = 256;
+constexpr uint32_t T16_TMEM_COLS = 256;
+constexpr uint32_t TC_X = 0, TC_D3 = 0, TC_H = 128, TC_ACC = 160;
+// per-block weight image (bytes).  W0^T [32 n][128 k]: hi and lo, each two k-atoms of [32 rows x 128 B];
+// PW^T [32 n][32 k] and W2^T [128 n][32 k]: hi in bytes [0,64) and lo in bytes [64,128) of each 128-byte row
+constexpr int W16_W0HI = 0, W16_W0LO = 8192, W16_PW = 16384, W16_W2 = 20480;
+constexpr int W16_BYTES = 36864;
+// fp32 parameter image (floats): stem W[3][128], stem b[128], then per block b0[32] dw[9][32] b1[32] b2[128] inv_scale[3] pad
+constexpr int P16_WSTEM = 0, P16_BSTEM = 384, P16_BLK0 = 512, P16_BLK = 484;
+constexpr int P16_B0 = 0, P16_DW = 32, P16_B1 = 320, P16_B2 = 352, P16_INV = 480;
+constexpr int P16_FLOATS = P16_BLK0 + 3 * P16_BLK;  // 1964
+constexpr int T16_HSTRIDE = 36;                     // fp32 depthwise tile row stride (floats): conflict-free float4 rows
+// shared memory map (bytes from the 1024-aligned base)
+constexpr int S16_W = 0;                                      // 2 x 36 KB weight images
+constexpr int S16_H = 2 * W16_BYTES;                          // 73728: [162 rows (two positions)][36] fp32
+constexpr int S16_PAR = S16_H + 162 * T16_HSTRIDE * 4;        // 97056
+constexpr int S16_IMG = S16_PAR + P16_FLOATS * 4;             // 104912: three 243-float input images
+constexpr int S16_BAR = S16_IMG + 736 * 4;                    // 107856
+constexpr int T16_SMEM_BYTES = S16_BAR + 64 + 1024;           // 108944: two CTAs per SM
+constexpr uint32_t T16_IDESC_N32 = idesc_f16(128, 32), T16_IDESC_N128 = idesc_f16(128, 128);
+static_assert(W16_BYTES == 8 * 32 * T16_HSTRIDE * 4, "the idle weight buffer doubles as eight per-warp staging tiles");
+
+__device__ long long g_t16_dbg[64];  // phase timestamps of CTA 0's second iteration (omk_debug_tower_timing)
+#define T16_STAMP(i) do { if (dbg_on && t == 0) g_t16_dbg[(i)] = clock64(); } while (0)
+__device__ __forceinline__ float t16_lrelu(float v) { return fmaxf(v, 0.2f * v); }  // alpha < 1: max(v, alpha v)
+
+// split 16 fp32 values (one 16-channel group) into 8 packed hi words + 8 packed lo words and store them as A-operand columns
+__device__ __forceinline__ void t16_store_group(uint32_t taddr, const float *v) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split2_f16(v[2 * i], v[2 * i + 1], w[i], w[8 + i]);
+    tmem_st16(taddr, w);
+}
+
+// Coalesced write-out of one warp's 32 pixel rows x 64 channels as fp16 hi / lo (the A operand of fc0).  A thread owns a
+// 128-byte segment of a row in each array, so direct per-thread stores would make every warp instruction touch 32
+// different cache lines.  Instead each warp transposes through a 4.6 KB staging tile, 32 channels at a time: a tile row
+// is [hi 64 B | lo 64 B]; on the way out four lanes cover one 64-byte run.
+// off16 = offset (16-byte units) of this lane's row segment in the fp16 arrays, or 0xFFFFFFFF for a padded / out-of-batch row.
+__device__ __forceinline__ void t16_store_out(uint32_t *stage, int lane, uint32_t off16, const float *x, __half *act_hi,
+                                              __half *act_lo) {
+    uint32_t orow[8];  // offsets of the eight rows this lane writes (row it*4 + lane/8), fetched once
+#pragma unroll
+    for (int it = 0; it < 8; ++it) orow[it] = __shfl_sync(0xffffffffu, off16, it * 4 + (lane >> 3));
+    uint4 *dst = reinterpret_cast<uint4 *>((lane & 4) ? act_lo : act_hi);
+#pragma unroll
+    for (int cp = 0; cp < 2; ++cp) {  // two passes of 32 channels
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint4 h, l;
+            const float *v = x + cp * 32 + k * 8;
+            split2_f16(v[0], v[1], h.x, l.x);
+            split2_f16(v[2], v[3], h.y, l.y);
+            split2_f16(v[4], v[5], h.z, l.z);
+            split2_f16(v[6], v[7], h.w, l.w);
+            *reinterpret_cast<uint4 *>(stage + lane * T16_HSTRIDE + k * 4) = h;
+            *reinterpret_cast<uint4 *>(stage + lane * T16_HSTRIDE + 16 + k * 4) = l;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), seg = lane & 7;  // seg 0..3: hi 16-byte pieces, 4..7: lo pieces
+            const uint4 val = *reinterpret_cast<const uint4 *>(stage + rr * T16_HSTRIDE + seg * 4);
+            if (orow[it] != 0xFFFFFFFFu) dst[(size_t)orow[it] + cp * 4 + (seg & 3)] = val;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(T16_THREADS, 2)
+    k_tower16(const uint8_t *__restrict__ wimg, const float *__restrict__ pimg, const NNIn *__restrict__ nn_in,
+              const float *__restrict__ images, const uint32_t *n_req, int max_rows, __half *__restrict__ act_hi,
+              __half *__restrict__ act_lo) {
+    extern __shared__ uint8_t t16_smem_raw[];
+    const int rows = (int)min(*n_req, (uint32_t)max_rows);
+    const int n_triples = (rows + 2) / 3, n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
+    if (pair >= n_triples) return;  // uniform for both CTAs of the pair, before any cluster barrier
+    const uint32_t rank = cluster_rank();
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int q = warp & 3, half = warp >> 2;
+    // Row R of the pair = 128*rank + TMEM lane; position j = R/81, pixel p = R%81.
+    const int R = (int)rank * 128 + q * 32 + lane;
+    const int j = R / kCells, p = R - j * kCells;
+    const int slot = j - (int)rank;  // H tile slot: CTA r keeps positions r and r+1 (162 rows)
+
+    uint8_t *sm = t16_smem_raw + ((1024u - (smem_u32(t16_smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(sm);
+    float *H0 = reinterpret_cast<float *>(sm + S16_H);
+    float *PAR = reinterpret_cast<float *>(sm + S16_PAR);
+    float *IMG = reinterpret_cast<float *>(sm + S16_IMG);
+    const uint32_t bar_w0 = sbase + S16_BAR, bar_mma = sbase + S16_BAR + 16, tmem_slot = sbase + S16_BAR + 24;
+    // the pair's middle position straddles the two CTAs: the H rows the peer's stencil reaches are mirrored into its tile
+    const uint32_t peer_h0 = mapa(sbase + S16_H, rank ^ 1u);
+
+    for (int i = t; i < P16_FLOATS; i += T16_THREADS) PAR[i] = pimg[i];
+    if (t == 0) {
+        mbar_init(bar_w0, 1);
+        mbar_init(bar_w0 + 8, 1);
+        mbar_init(bar_mma, 8);  // one tcgen05.commit per warp
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<1>(tmem_slot, T16_TMEM_COLS);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);  // this warp's lane quadrant
+    // Cluster barrier protocol for the single-buffered H tile: phase A ("my stencil reads are done, you may overwrite
+    // my mirror rows") is arrived after each stencil and waited before the next E1; phase B ("my E1 rows, local and
+    // mirrored, are written") is an arrive+wait between E1 and the stencil.  This arrive opens the first phase A.
+    cluster_arrive();
+
+    uint32_t g = 0;          // running block counter: weight buffer = g & 1, its phase parity = (g >> 1) & 1
+    uint32_t mma_uses = 0;   // completed uses of bar_mma
+    auto issue_weights = [&](uint32_t gg) {  // one thread
+        const uint32_t buf = gg & 1u, bar = bar_w0 + 8 * buf;
+        fence_proxy_async_smem();  // the buffer may have served as a staging tile (generic proxy)
+        mbar_expect_tx(bar, (uint32_t)W16_BYTES);
+        const uint8_t *src = wimg + (size_t)(gg % 3u) * W16_BYTES;
+        for (int c = 0; c < W16_BYTES; c += 9216) bulk_load(sbase + S16_W + buf * W16_BYTES + c, src + c, 9216, bar);
+    };
+    if (t == 0) issue_weights(0);
+
+    NNIn cur0{}, cur1{}, cur2{};
+    if (!images) {
+        cur0 = nn_in[min(pair * 3 + 0, rows - 1)];
+        cur1 = nn_in[min(pair * 3 + 1, rows - 1)];
+        cur2 = nn_in[min(pair * 3 + 2, rows - 1)];
+    }
+    int pos_iter = 0;
+    for (int tr = pair; tr < n_triples; tr += n_pairs, ++pos_iter) {
+        const bool dbg_on = blockIdx.x == 0 && pos_iter == 1;
+        const int row = tr * 3 + j;                       // this thread's position (global row of the batch)
+        const bool real = R < 3 * kCells && row < rows;   // 13 padding lanes per pair; the last triple may be partial
+        T16_STAMP(0);
+        // ---- input images of the triple (the reference's 243-float slot read as [81][3]) ----
+        if (t < 243) {
+            if (images) {
+                IMG[t] = images[(size_t)min(tr * 3 + 0, rows - 1) * 243 + t];
+                IMG[243 + t] = images[(size_t)min(tr * 3 + 1, rows - 1) * 243 + t];
+                IMG[486 + t] = images[(size_t)min(tr * 3 + 2, rows - 1) * 243 + t];
+            } else {
+                IMG[t] = image_value(cur0.black, cur0.white, cur0.meta & 1u, (cur0.meta >> 1) & 1u, t);
+                IMG[243 + t] = image_value(cur1.black, cur1.white, cur1.meta & 1u, (cur1.meta >> 1) & 1u, t);
+                IMG[486 + t] = image_value(cur2.black, cur2.white, cur2.meta & 1u, (cur2.meta >> 1) & 1u, t);
+            }
+        }
+        // prefetch the next triple's request rows: their global-load latency hides behind this whole iteration
+        if (!images && tr + n_pairs < n_triples) {
+            cur0 = nn_in[min((tr + n_pairs) * 3 + 0, rows - 1)];
+            cur1 = nn_in[min((tr + n_pairs) * 3 + 1, rows - 1)];
+            cur2 = nn_in[min((tr + n_pairs) * 3 + 2, rows - 1)];
+        }
+        __syncthreads();
+        // ---- stem 1x1 conv 3 -> 128 (network.rs:65-79): this thread's pixel, its 64 channels ----
+        float x[64];
+        {
+            const int pc = real ? p : 0;  // padded rows recompute pixel 0 (harmless, never stored)
+            const float *im = IMG + (real ? j : 0) * 243;
+            const float v0 = im[3 * pc], v1 = im[3 * pc + 1], v2 = im[3 * pc + 2];
+#pragma unroll
+            for (int c = 0; c < 64; c += 4) {
+                const int ch = half * 64 + c;
+                const float4 b = *reinterpret_cast<const float4 *>(PAR + P16_BSTEM + ch);
+                const float4 w0 = *reinterpret_cast<const float4 *>(PAR + P16_WSTEM + ch);
+                const float4 w1 = *reinterpret_cast<const float4 *>(PAR + P16_WSTEM + 128 + ch);
+                const float4 w2 = *reinterpret_cast<const float4 *>(PAR + P16_WSTEM + 256 + ch);
+                float2 s01 = __ffma2_rn(make_float2(v0, v0), make_float2(w0.x, w0.y), make_float2(b.x, b.y));
+                float2 s23 = __ffma2_rn(make_float2(v0, v0), make_float2(w0.z, w0.w), make_float2(b.z, b.w));
+                s01 = __ffma2_rn(make_float2(v1, v1), make_float2(w1.x, w1.y), s01);
+                s23 = __ffma2_rn(make_float2(v1, v1), make_float2(w1.z, w1.w), s23);
+                s01 = __ffma2_rn(make_float2(v2, v2), make_float2(w2.x, w2.y), s01);
+                s23 = __ffma2_rn(make_float2(v2, v2), make_float2(w2.z, w2.w), s23);
+                x[c + 0] = t16_lrelu(s01.x);
+                x[c + 1] = t16_lrelu(s01.y);
+                x[c + 2] = t16_lrelu(s23.x);
+                x[c + 3] = t16_lrelu(s23.y);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c * 16), x + c * 16);
+        }
+        tmem_wait_st();
+        T16_STAMP(1);
+
+        for (int r = 0; r < 3; ++r, ++g) {
+            const float *bp = PAR + P16_BLK0 + r * P16_BLK;
+            const uint32_t wb = sbase + S16_W + (g & 1u) * W16_BYTES;
+            // ================= conv0: 1x1 128 -> 32 (A = X in TMEM) =================
+            fence_before();
+            __syncthreads();
+            if (lane == 0) {
+                fence_after();
+                if (warp == 3) issue_weights(g + 1);  // the other buffer's last reader (block g-1, or the write-out) has completed
+                if (warp < 3) {
+                    // one accumulator chain per product (lo.hi, hi.lo, hi.hi), issued in parallel from three threads: the
+                    // single-thread issue path costs ~60 clk per small MMA
+                    mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+                    const uint32_t acol = tmem_base + TC_X + (warp == 0 ? 8u : 0u);
+                    const uint32_t bimg = wb + (warp == 1 ? W16_W0LO : W16_W0HI);
+#pragma unroll 1
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_f16_ts(tmem_base + TC_ACC + 32u * warp, acol + 16u * kk,
+                                    desc_sw128(bimg + (uint32_t)((kk >> 2) * 4096 + (kk & 3) * 32)), T16_IDESC_N32, kk != 0);
+                }
+                umma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, mma_uses & 1u);
+            ++mma_uses;
+            __syncwarp();
+            fence_after();
+            T16_STAMP(2 + r * 8 + 0);
+            // epilogue 1: + b0, lrelu -> fp32 tile for the depthwise stencil (this thread: 16 channels of its pixel)
+            {
+                float d[16], e[16], f[16];
+                tmem_ld16(tlane + TC_ACC + half * 16, d);
+                tmem_ld16(tlane + TC_ACC + 32 + half * 16, e);
+                tmem_ld16(tlane + TC_ACC + 64 + half * 16, f);
+                cluster_wait();  // phase A: the peer has finished the previous stencil, its mirror rows may be overwritten
+                tmem_wait_ld();
+                const float inv = bp[P16_INV + 0];
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(bp + P16_B0 + half * 16 + c);
+                    float4 o;
+                    o.x = t16_lrelu(fmaf((d[c + 0] + e[c + 0]) + f[c + 0], inv, b.x));
+                    o.y = t16_lrelu(fmaf((d[c + 1] + e[c + 1]) + f[c + 1], inv, b.y));
+                    o.z = t16_lrelu(fmaf((d[c + 2] + e[c + 2]) + f[c + 2], inv, b.z));
+                    o.w = t16_lrelu(fmaf((d[c + 3] + e[c + 3]) + f[c + 3], inv, b.w));
+                    if (real) {
+                        *reinterpret_cast<float4 *>(H0 + (slot * kCells + p) * T16_HSTRIDE + half * 16 + c) = o;
+                        // only the band the peer's stencil can reach (pixels 37..46 from CTA 0, 47..56 from CTA 1) is mirrored
+                        if (j == 1 && (rank == 0 ? p >= 37 : p <= 56)) {  // the peer keeps this position in its slot 1 - peer_rank = rank
+                            const uint32_t ra = peer_h0 + (uint32_t)((((int)rank * kCells + p) * T16_HSTRIDE + half * 16 + c) * 4);
+                            asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                        }
+                    }
+                }
+            }
+            // phase B: both CTAs' rows (local and mirrored) must be visible before the stencil
+            cluster_arrive();
+            cluster_wait();
+            T16_STAMP(2 + r * 8 + 1);
+            // conv1 depthwise 3x3, SAME zero padding, no bias (lib.rs:204-216) -> A operand of the pointwise conv
+            {
+                float a[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) a[c] = 0.0f;
+                if (real) {
+                    const int y = p / kSide, xx0 = p % kSide;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int yy = y + ky - 1;
+                        if (yy < 0 || yy >= kSide) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int xx = xx0 + kx - 1;
+                            if (xx < 0 || xx >= kSide) continue;
+                            const float *hp = H0 + (slot * kCells + yy * kSide + xx) * T16_HSTRIDE + half * 16;
+                            const float *wp = bp + P16_DW + (ky * 3 + kx) * 32 + half * 16;
+#pragma unroll
+                            for (int c = 0; c < 16; c += 4) {
+                                const float4 h = *reinterpret_cast<const float4 *>(hp + c);
+                                const float4 w = *reinterpret_cast<const float4 *>(wp + c);
+                                // packed fp32x2 FMA (sm_100): same results as two FFMAs, half the issue slots
+                                float2 lo2 = __ffma2_rn(make_float2(h.x, h.y), make_float2(w.x, w.y), make_float2(a[c + 0], a[c + 1]));
+                                float2 hi2 = __ffma2_rn(make_float2(h.z, h.w), make_float2(w.z, w.w), make_float2(a[c + 2], a[c + 3]));
+                                a[c + 0] = lo2.x; a[c + 1] = lo2.y; a[c + 2] = hi2.x; a[c + 3] = hi2.y;
+                            }
+                        }
+                    }
+                }
+                cluster_arrive();  // phase A of the next block: this CTA's stencil reads are done
+                t16_store_group(tlane + TC_H + (uint32_t)(half * 16), a);
+            }
+            tmem_wait_st();
+            T16_STAMP(2 + r * 8 + 2);
+            // ================= conv1 pointwise: 1x1 32 -> 32 (A = H in TMEM) =================
+            fence_before();
+            __syncthreads();
+            if (lane == 0) {
+                fence_after();
+                if (warp < 3) {
+                    const uint32_t acol = tmem_base + TC_H + (warp == 0 ? 8u : 0u);
+                    const uint32_t bimg = wb + W16_PW + (warp == 1 ? 64u : 0u);
+#pragma unroll 1
+                    for (int ks = 0; ks < 2; ++ks)
+                        umma_f16_ts(tmem_base + TC_ACC + 32u * warp, acol + 16u * ks, desc_sw128(bimg + ks * 32), T16_IDESC_N32, ks != 0);
+                }
+                umma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, mma_uses & 1u);
+            ++mma_uses;
+            __syncwarp();
+            fence_after();
+            T16_STAMP(2 + r * 8 + 3);
+            {   // epilogue 2: + b1, lrelu -> A operand of conv2
+                float d[16], e[16], f[16];
+                tmem_ld16(tlane + TC_ACC + half * 16, d);
+                tmem_ld16(tlane + TC_ACC + 32 + half * 16, e);
+                tmem_ld16(tlane + TC_ACC + 64 + half * 16, f);
+                tmem_wait_ld();
+                const float inv = bp[P16_INV + 1];
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(bp + P16_B1 + half * 16 + c);
+                    d[c + 0] = t16_lrelu(fmaf((d[c + 0] + e[c + 0]) + f[c + 0], inv, b.x));
+                    d[c + 1] = t16_lrelu(fmaf((d[c + 1] + e[c + 1]) + f[c + 1], inv, b.y));
+                    d[c + 2] = t16_lrelu(fmaf((d[c + 2] + e[c + 2]) + f[c + 2], inv, b.z));
+                    d[c + 3] = t16_lrelu(fmaf((d[c + 3] + e[c + 3]) + f[c + 3], inv, b.w));
+                }
+                t16_store_group(tlane + TC_H + (uint32_t)(half * 16), d);
+            }
+            tmem_wait_st();
+            T16_STAMP(2 + r * 8 + 4);
+            // ================= conv2: 1x1 32 -> 128 (A = H in TMEM), + x, lrelu =================
+            fence_before();
+            __syncthreads();
+            if (lane == 0) {
+                fence_after();
+                if (warp == 0) {  // N = 128 MMAs are tensor-bound (64 clk each): one chain
+#pragma unroll 1
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint64_t bhi = desc_sw128(wb + W16_W2 + ks * 32), blo = desc_sw128(wb + W16_W2 + 64 + ks * 32);
+                        const uint32_t ahi = tmem_base + TC_H + 16u * ks;
+                        umma_f16_ts(tmem_base + TC_D3, ahi + 8u, bhi, T16_IDESC_N128, ks != 0);
+                        umma_f16_ts(tmem_base + TC_D3, ahi, blo, T16_IDESC_N128, 1u);
+                        umma_f16_ts(tmem_base + TC_D3, ahi, bhi, T16_IDESC_N128, 1u);
+                    }
+                }
+                umma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, mma_uses & 1u);
+            ++mma_uses;
+            __syncwarp();
+            fence_after();
+            T16_STAMP(2 + r * 8 + 5);
+            {   // epilogue 3: x = lrelu(conv2 + b2 + x); the next block's A operand is written in place over D3
+                const float inv = bp[P16_INV + 2];
+#pragma unroll
+                for (int c2 = 0; c2 < 4; c2 += 2) {
+                    float d[32];
+                    tmem_ld16(tlane + TC_D3 + half * 64 + c2 * 16, d);
+                    tmem_ld16(tlane + TC_D3 + half * 64 + c2 * 16 + 16, d + 16);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {  // padded rows carry harmless garbage; they are never stored
+                        const int c = c2 * 16 + i;
+                        const float4 b = *reinterpret_cast<const float4 *>(bp + P16_B2 + half * 64 + c);
+                        const float2 s01 = __ffma2_rn(make_float2(d[i + 0], d[i + 1]), make_float2(inv, inv), make_float2(b.x, b.y));
+                        const float2 s23 = __ffma2_rn(make_float2(d[i + 2], d[i + 3]), make_float2(inv, inv), make_float2(b.z, b.w));
+                        const float2 t01 = __fadd2_rn(s01, make_float2(x[c + 0], x[c + 1]));
+                        const float2 t23 = __fadd2_rn(s23, make_float2(x[c + 2], x[c + 3]));
+                        const float2 u01 = __fmul2_rn(t01, make_float2(0.2f, 0.2f)), u23 = __fmul2_rn(t23, make_float2(0.2f, 0.2f));
+                        x[c + 0] = fmaxf(t01.x, u01.x);
+                        x[c + 1] = fmaxf(t01.y, u01.y);
+                        x[c + 2] = fmaxf(t23.x, u23.x);
+                        x[c + 3] = fmaxf(t23.y, u23.y);
+                    }
+                    if (r < 2) {
+                        t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16), x + c2 * 16);
+                        t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16 + 16), x + c2 * 16 + 16);
+                    }
+                }
+            }
+            tmem_wait_st();
+            T16_STAMP(2 + r * 8 + 6);
+        }
+        // ---- flatten NHWC (network.rs:127-137): this thread's pixel row, its 64 channels, as fp16 hi / lo ----
+        T16_STAMP(30);
+        {   // the weight buffer of the block just finished is idle until the next conv0 phase: staging tiles live there
+            uint32_t *stage = reinterpret_cast<uint32_t *>(sm + S16_W + ((g - 1u) & 1u) * W16_BYTES) + warp * (32 * T16_HSTRIDE);
+            const uint32_t off16 = real ? (uint32_t)row * 1296u + (uint32_t)(p * 16 + half * 8) : 0xFFFFFFFFu;
+            t16_store_out(stage, lane, off16, x, act_hi, act_lo);
+        }
+        T16_STAMP(31);
+    }
+    // (timestamps: 0 start, 1 stem done, then per block: conv0 done, E1+sync, dw stored, conv1 done, E2 stored, conv2 done, E3 stored)
+    cluster_wait();  // consume the last phase-A arrive: no distributed-shared-memory traffic is in flight past this point
+    // drain the weight prefetch that was issued one block ahead, then release TMEM
+    if (t == 0) mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+    fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after();
+        tmem_dealloc<1>(tmem_base, T16_TMEM_COLS);
+    }
+}
+
+// Build the per-block B-operand images (K-major SWIZZLE_128B, scaled fp16 hi/lo) and the fp32 parameter image.
+// byte offset of (row n, byte b in [0,128)) inside a SWIZZLE_128B K-major tile
+__device__ __forceinline__ uint32_t swz128b(int n, int b) {
+    return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((b >> 4) ^ (n & 7)) & 7) << 4) + (b & 15));
+}
+struct Tower16PackArgs {
+    const float *conv_w, *conv_b;
+    const float *w0[3], *b0[3], *dw[3], *pw[3], *b1[3], *w2[3], *b2[3];
+};
+__global__ void k_tower16_absmax(Tower16PackArgs a, uint32_t *absmax /*[9]*/) {
+    const int which = blockIdx.x;  // 3 * r + {0: w0, 1: pw, 2: w2}
+    const int r = which / 3, m = which % 3;
+    const float *w = m == 0 ? a.w0[r] : (m == 1 ? a.pw[r] : a.w2[r]);
+    const int n = m == 1 ? 1024 : 4096;
+    uint32_t mx = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = max(mx, __float_as_uint(w[i]) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(absmax + which, mx);
+}
+__device__ __forceinline__ void put_split(uint8_t *img, uint32_t off_hi, uint32_t off_lo, float v) {
+    const __half h = __float2half_rn(v);
+    *reinterpret_cast<__half *>(img + off_hi) = h;
+    *reinterpret_cast<__half *>(img + off_lo) = __float2half_rn(v - __half2float(h));
+}
+__global__ void k_tower16_pack(Tower16PackArgs a, const uint32_t *absmax, uint8_t *wimg, float *pimg) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    for (int r = 0; r < 3; ++r) {
+        uint8_t *img = wimg + (size_t)r * W16_BYTES;
+        const float s0 = f16_split_scale(absmax[3 * r + 0]), s1 = f16_split_scale(absmax[3 * r + 1]),
+                    s2 = f16_split_scale(absmax[3 * r + 2]);
+        for (int i = tid; i < 128 * 32; i += nth) {  // W0[k][n]: k = cin 0..127, n = cout 0..31
+            const int k = i >> 5, n = i & 31;
+            const uint32_t off = (uint32_t)(k >> 6) * 4096u + swz128b(n, (k & 63) * 2);
+            put_split(img, W16_W0HI + off, W16_W0LO + off, a.w0[r][k * 32 + n] * s0);
+        }
+        for (int i = tid; i < 32 * 32; i += nth) {  // PW[k][n]
+            const int k = i >> 5, n = i & 31;
+            put_split(img, W16_PW + swz128b(n, k * 2), W16_PW + swz128b(n, 64 + k * 2), a.pw[r][k * 32 + n] * s1);
+        }
+        for (int i = tid; i < 32 * 128; i += nth) {  // W2[k][n]: k = cin 0..31, n = cout 0..127
+            const int k = i >> 7, n = i & 127;
+            put_split(img, W16_W2 + swz128b(n, k * 2), W16_W2 + swz128b(n, 64 + k * 2), a.w2[r][k * 128 + n] * s2);
+        }
+        float *pb = pimg + P16_BLK0 + r * P16_BLK;
+        for (int i = tid; i < 32; i += nth) {
+            pb[P16_B0 + i] = a.b0[r][i];
+            pb[P16_B1 + i] = a.b1[r][i];
+        }
+        for (int i = tid; i < 288; i += nth) pb[P16_DW + i] = a.dw[r][i];
+        for (int i = tid; i < 128; i += nth) pb[P16_B2 + i] = a.b2[r][i];
+        if (tid == 0) {
+            pb[P16_INV + 0] = 1.0f / s0;
+            pb[P16_INV + 1] = 1.0f / s1;
+            pb[P16_INV + 2] = 1.0f / s2;
+            pb[P16_INV + 3] = 0.0f;
+        }
+    }
+    for (int i = tid; i < 384; i += nth) pimg[P16_WSTEM + i] = a.conv_w[i];
+    for (int i = tid; i < 128; i += nth) pimg[P16_BSTEM + i] = a.conv_b[i];
+}
+
+bool tower16_prepare_weights(omk_ctx *c) {
+    NetWeights &w = c->net;
+    if (!w.tower16_wimg) {
+        if (cudaMalloc(&w.tower16_wimg, 3 * W16_BYTES) != cudaSuccess) return false;
+        if (cudaMalloc(&w.tower16_pimg, sizeof(float) * P16_FLOATS) != cudaSuccess) return false;
+        if (cudaMalloc(&w.tower16_absmax, sizeof(uint32_t) * 9) != cudaSuccess) return false;
+    }
+    Tower16PackArgs a;
+    a.conv_w = w.t[0];
+    a.conv_b = w.t[1];
+    for (int r = 0; r < 3; ++r) {
+        const int b = 2 + 7 * r;
+        a.w0[r] = w.t[b + 0]; a.b0[r] = w.t[b + 1]; a.dw[r] = w.t[b + 2]; a.pw[r] = w.t[b + 3];
+        a.b1[r] = w.t[b + 4]; a.w2[r] = w.t[b + 5]; a.b2[r] = w.t[b + 6];
+    }
+    cudaMemsetAsync(w.tower16_absmax, 0, sizeof(uint32_t) * 9, c->stream);
+    cudaMemsetAsync(w.tower16_wimg, 0, 3 * W16_BYTES, c->stream);
+    k_tower16_absmax<<<9, 256, 0, c->stream>>>(a, w.tower16_absmax);
+    k_tower16_pack<<<16, 256, 0, c->stream>>>(a, w.tower16_absmax, w.tower16_wimg, w.tower16_pimg);
+    c->launches += 2;
+    return true;
+}
+
+void tower16_read_timing(long long *out64) { cudaMemcpyFromSymbol(out64, g_t16_dbg, sizeof(long long) * 64); }
+
+// resident CTA pairs the device can hold (two CTAs per SM when shared memory, registers and TMEM allow)
+static int tower16_max_pairs(omk_ctx *c) {
+    if (c->tower16_pairs > 0) return c->tower16_pairs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * 2 * c->n_sms);
+    cfg.blockDim = dim3(T16_THREADS);
+    cfg.dynamicSmemBytes = T16_SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // Two CTAs per SM: 2 x (107 KB, 256 x 128 registers, 256 TMEM columns) fit an SM exactly.  The occupancy API answers
+    // one block per SM for this kernel (measured) while the hardware co-schedules two (tower 1.29 -> 0.87 ms with
+    // n_sms pairs instead of n_sms / 2), so the grid is sized from the SM count; surplus CTAs would simply queue.
+    int n = c->n_sms;
+    int api = 0;
+    if (cudaOccupancyMaxActiveClusters(&api, k_tower16, &cfg) != cudaSuccess) cudaGetLastError();
+    if (getenv("OMK_DEBUG")) {
+        int per_sm = -1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tower16, T16_THREADS, T16_SMEM_BYTES);
+        cudaFuncAttributes fa{};
+        cudaFuncGetAttributes(&fa, k_tower16);
+        fprintf(stderr, "omok_b200: k_tower16 CTA pairs: %d (%d SMs); occupancy API: %d clusters, %d blocks/SM; regs %d, static smem %zu, max dyn smem %d, carveout %d\n",
+                n, c->n_sms, api, per_sm, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
+    }
+    if (const char *e = getenv("OMK_TOWER_PAIRS")) n = atoi(e) > 0 ? atoi(e) : n;
+    c->tower16_pairs = n;
+    return n;
+}
+
+bool launch_tower_f16(omk_ctx *c, const float *images_dev, int rows_bound) {
+    cudaFuncSetAttribute(k_tower16, cudaFuncAttributeMaxDynamicSharedMemorySize, T16_SMEM_BYTES);
+    // two 107 KB CTAs per SM need the full shared-memory carve-out; the default heuristic sizes it for one block
+    cudaFuncSetAttribute(k_tower16, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const int triples = (rows_bound + 2) / 3;
+    const int max_pairs = tower16_max_pairs(c);
+    const int pairs = triples < max_pairs ? triples : max_pairs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(T16_THREADS);
+    cfg.dynamicSmemBytes = T16_SMEM_BYTES;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const uint8_t *wimg = c->net.tower16_wimg;
+    const float *pimg = c->net.tower16_pimg;
+    const NNIn *nn_in = c->ws.nn_in;
+    const uint32_t *n_req = c->ws.n_req;
+    __half *ah = c->ws.act0_h16, *al = c->ws.act0_l16;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower16, wimg, pimg, nn_in, images_dev, n_req, rows_bound, ah, al);
+    if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_tower16): %s\n", cudaGetErrorString(e));
+    c->launches++;
+    return e == cudaSuccess;
+}
+
+}  // namespace omk
