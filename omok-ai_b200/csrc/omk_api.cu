@@ -222,6 +222,7 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
                     c->net.tower16_pimg, c->net.tower16_absmax};
     fc0_tc_free(c);
     fc16_free(c);
+    free(c->tower16_params_host);
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < kNetTensors; ++i) cudaFree(c->net.t[i]);
     if (c->pinned) cudaFreeHost(c->pinned);

@@ -93,6 +93,7 @@ struct omk_ctx {
     int fc0_mode = 2;               // 0: fp32 CUDA-core k_gemm, 1: tcgen05 3xTF32 k_fc_tc, 2: tcgen05 3xFP16 k_fc16 (default)
     void *fc16_state = nullptr;     // tensor maps of the fp16-split path (fc_f16.cu)
     int tower16_pairs = 0;          // resident CTA pairs of k_tower16 (0 = not queried yet)
+    void *tower16_params_host = nullptr;  // host copy of the tower's fp32 parameter image (kernel argument of k_tower16)
     void *fc0_tc_state = nullptr;   // tensor maps of the tensor-core path (fc0_tc.cu)
     int fc0_pair = 1;               // 1: fc0 runs the cta_group::2 (CTA pair, 256x256 tile) kernel; 0: one CTA per 128x256 tile
     int tower_pair = 1;             // 1: k_tower_tc3 (CTA pair, three positions per iteration); 0: k_tower_tc (one position per CTA)

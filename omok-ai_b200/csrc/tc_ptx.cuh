@@ -183,7 +183,8 @@ __host__ __device__ inline float f16_split_scale(uint32_t absmax_bits) {
 __device__ __forceinline__ void split2_f16(float a, float b, uint32_t &hi, uint32_t &lo) {
     const __half2 h = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    const float2 r = __ffma2_rn(hf, make_float2(-1.0f, -1.0f), make_float2(a, b));  // exact residual, one packed FMA
+    const __half2 l = __floats2half2_rn(r.x, r.y);
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }

@@ -25,6 +25,7 @@
 //               H    [128,160) 16-channel group g of the block's hidden activations, same hi/lo packing
 //               ACC  [160,256) three 32-column partial accumulators (one per product) of conv0 / conv1
 #include <cstdio>
+#include <cstdlib>
 
 #include "omk_internal.h"
 #include "tc_ptx.cuh"
@@ -40,20 +41,34 @@ constexpr uint32_t TC_X = 0, TC_D3 = 0, TC_H = 128, TC_ACC = 160;
 // PW^T [32 n][32 k] and W2^T [128 n][32 k]: hi in bytes [0,64) and lo in bytes [64,128) of each 128-byte row
 constexpr int W16_W0HI = 0, W16_W0LO = 8192, W16_PW = 16384, W16_W2 = 20480;
 constexpr int W16_BYTES = 36864;
-// fp32 parameter image (floats): stem W[3][128], stem b[128], then per block b0[32] dw[9][32] b1[32] b2[128] inv_scale[3] pad
+// The small fp32 parameters travel as a KERNEL ARGUMENT (7.9 KB of the constant bank): every use is warp-uniform, so
+// biases, stem and depthwise weights become constant-bank operands of the FMAs instead of shared-memory loads.
+struct alignas(16) Tower16Block {
+    float b0[32], dw[9][32], b1[32], b2[128];
+    float inv[4];  // 2^-s of w0, pw, w2 (undo the power-of-two weight scaling; exact)
+};
+struct alignas(16) Tower16Params {
+    float wstem[3][128], bstem[128];
+    Tower16Block blk[3];
+};
+// the same image as plain floats (k_tower16_pack writes it on the device; the host keeps a copy to pass by value)
 constexpr int P16_WSTEM = 0, P16_BSTEM = 384, P16_BLK0 = 512, P16_BLK = 484;
 constexpr int P16_B0 = 0, P16_DW = 32, P16_B1 = 320, P16_B2 = 352, P16_INV = 480;
 constexpr int P16_FLOATS = P16_BLK0 + 3 * P16_BLK;  // 1964
+static_assert(sizeof(Tower16Params) == P16_FLOATS * 4 && sizeof(Tower16Block) == P16_BLK * 4, "parameter image layout");
 constexpr int T16_HSTRIDE = 36;                     // fp32 depthwise tile row stride (floats): conflict-free float4 rows
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int S16_W = 0;                                      // 2 x 36 KB weight images
 constexpr int S16_H = 2 * W16_BYTES;                          // 73728: [162 rows (two positions)][36] fp32
-constexpr int S16_PAR = S16_H + 162 * T16_HSTRIDE * 4;        // 97056
-constexpr int S16_IMG = S16_PAR + P16_FLOATS * 4;             // 104912: three 243-float input images
-constexpr int S16_BAR = S16_IMG + 736 * 4;                    // 107856
-constexpr int T16_SMEM_BYTES = S16_BAR + 64 + 1024;           // 108944: two CTAs per SM
+constexpr int S16_IMG = S16_H + 162 * T16_HSTRIDE * 4;        // 97056: three 243-float input images
+constexpr int S16_TAB = S16_IMG + 736 * 4;                    // 100000: stem tables, 8 input combinations x 132 words, fp32 and packed hi/lo
+constexpr int T16_TABSTRIDE = 132;                            // words per combination: 128 + 4, so the 8 rows start 4 banks apart
+constexpr int S16_BAR = S16_TAB + 2 * 8 * T16_TABSTRIDE * 4;  // 108448
+constexpr int T16_SMEM_BYTES = S16_BAR + 64 + 1024;           // 109536: two CTAs per SM
+constexpr uint32_t T16_BAND_BYTES = 10 * 32 * 4;              // mirrored stencil band: 10 pixel rows x 32 channels fp32
 constexpr uint32_t T16_IDESC_N32 = idesc_f16(128, 32), T16_IDESC_N128 = idesc_f16(128, 128);
 static_assert(W16_BYTES == 8 * 32 * T16_HSTRIDE * 4, "the idle weight buffer doubles as eight per-warp staging tiles");
+static_assert(S16_BAR % 8 == 0, "mbarriers are 8-byte aligned");
 
 __device__ long long g_t16_dbg[64];  // phase timestamps of CTA 0's second iteration (omk_debug_tower_timing)
 #define T16_STAMP(i) do { if (dbg_on && t == 0) g_t16_dbg[(i)] = clock64(); } while (0)
@@ -102,8 +117,81 @@ __device__ __forceinline__ void t16_store_out(uint32_t *stage, int lane, uint32_
     }
 }
 
+// ---- per-phase CUDA-core work, templated on the channel half so that every parameter offset is a compile-time
+//      constant-bank address (the half is warp-uniform but the compiler cannot prove it) ----
+// stem 1x1 conv 3 -> 128 (network.rs:65-79): this thread's pixel, its 64 channels
+template <int HALF>
+__device__ __forceinline__ void t16_stem(const Tower16Params &P, float v0, float v1, float v2, float *x) {
+#pragma unroll
+    for (int c = 0; c < 64; c += 2) {
+        const int ch = HALF * 64 + c;
+        float2 s = __ffma2_rn(make_float2(v0, v0), make_float2(P.wstem[0][ch], P.wstem[0][ch + 1]),
+                              make_float2(P.bstem[ch], P.bstem[ch + 1]));
+        s = __ffma2_rn(make_float2(v1, v1), make_float2(P.wstem[1][ch], P.wstem[1][ch + 1]), s);
+        s = __ffma2_rn(make_float2(v2, v2), make_float2(P.wstem[2][ch], P.wstem[2][ch + 1]), s);
+        x[c + 0] = t16_lrelu(s.x);
+        x[c + 1] = t16_lrelu(s.y);
+    }
+}
+// epilogue 1 / 2 arithmetic: three partial accumulators (lo.hi, hi.lo, hi.hi) -> lrelu(sum * 2^-s + bias)
+template <int HALF>
+__device__ __forceinline__ void t16_bias_lrelu16(const float *bias32, float inv, const float *d, const float *e, const float *f,
+                                                 float *o) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = t16_lrelu(fmaf((d[c] + e[c]) + f[c], inv, bias32[HALF * 16 + c]));
+}
+// depthwise 3x3, SAME zero padding, no bias (lib.rs:204-216): 16 channels of pixel (y, x0) from the fp32 tile.
+// (Measured and rejected: a branch-free variant whose off-board taps read all-zero tile rows -- no faster, the phase is
+// bound by the 144 shared-memory wavefronts per warp of the neighbour rows, not by load -> use latency.)
+template <int HALF>
+__device__ __forceinline__ void t16_stencil(const Tower16Block &B, const float *Hpos /* tile rows of this position */, int y, int xx0,
+                                            float *a) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= kSide) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = xx0 + kx - 1;
+            if (xx < 0 || xx >= kSide) continue;
+            const float *hp = Hpos + (yy * kSide + xx) * T16_HSTRIDE + HALF * 16;
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) {
+                const float4 h = *reinterpret_cast<const float4 *>(hp + c);
+                const float *w = &B.dw[ky * 3 + kx][HALF * 16 + c];
+                // packed fp32x2 FMA (sm_100): same results as two FFMAs, half the issue slots
+                const float2 lo2 = __ffma2_rn(make_float2(h.x, h.y), make_float2(w[0], w[1]), make_float2(a[c + 0], a[c + 1]));
+                const float2 hi2 = __ffma2_rn(make_float2(h.z, h.w), make_float2(w[2], w[3]), make_float2(a[c + 2], a[c + 3]));
+                a[c + 0] = lo2.x; a[c + 1] = lo2.y; a[c + 2] = hi2.x; a[c + 3] = hi2.y;
+            }
+        }
+    }
+}
+// epilogue 3 arithmetic on 32 channels [c0, c0+32) of this thread's 64: x = lrelu(d * 2^-s + b2 + x)
+template <int HALF>
+__device__ __forceinline__ void t16_residual32(const Tower16Block &B, int c0, const float *d, float *x) {
+    const float inv = B.inv[2];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        const int c = c0 + i;
+        const float2 s = __ffma2_rn(make_float2(d[i], d[i + 1]), make_float2(inv, inv),
+                                    make_float2(B.b2[HALF * 64 + c], B.b2[HALF * 64 + c + 1]));
+        const float2 tt = __fadd2_rn(s, make_float2(x[c], x[c + 1]));
+        const float2 u = __fmul2_rn(tt, make_float2(0.2f, 0.2f));
+        x[c + 0] = fmaxf(tt.x, u.x);
+        x[c + 1] = fmaxf(tt.y, u.y);
+    }
+}
+// one float of the reference's 243-float input slot (encoder.rs:22-43) as a bit: same values as image_value()
+__device__ __forceinline__ uint32_t t16_image_bit(const NNIn &in, int f) {
+    if (f >= 2 * kCells) return (in.meta & 1u) ^ 1u;  // turn plane: 1.0 when black is to move
+    const uint32_t persp = (in.meta ^ (in.meta >> 1)) & 1u;  // EnvTurnMode::Opponent flips the perspective
+    return ((uint32_t)(f & 1) == persp ? bit81(in.black, f >> 1) : bit81(in.white, f >> 1)) ? 1u : 0u;
+}
+#define T16_HALF(call_0, call_1) do { if (half == 0) { call_0; } else { call_1; } } while (0)
+
 __global__ void __launch_bounds__(T16_THREADS, 2)
-    k_tower16(const uint8_t *__restrict__ wimg, const float *__restrict__ pimg, const NNIn *__restrict__ nn_in,
+    k_tower16(const uint8_t *__restrict__ wimg, const __grid_constant__ Tower16Params P, const NNIn *__restrict__ nn_in,
               const float *__restrict__ images, const uint32_t *n_req, int max_rows, __half *__restrict__ act_hi,
               __half *__restrict__ act_lo) {
     extern __shared__ uint8_t t16_smem_raw[];
@@ -117,34 +205,57 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     const int R = (int)rank * 128 + q * 32 + lane;
     const int j = R / kCells, p = R - j * kCells;
     const int slot = j - (int)rank;  // H tile slot: CTA r keeps positions r and r+1 (162 rows)
+    const bool in_tile = R < 3 * kCells;
+    // The pair's middle position straddles the two CTAs.  The H rows of it that the PEER's stencil reaches (pixels 37..46
+    // held by CTA 0, 47..56 held by CTA 1) are mirrored into the peer's tile with st.async, which signals the peer's
+    // "band" mbarrier by transaction bytes: no cluster-wide barrier and no fence in the loop.
+    const bool band = j == 1 && (rank == 0 ? p >= 37 : p <= 56);
 
     uint8_t *sm = t16_smem_raw + ((1024u - (smem_u32(t16_smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(sm);
     float *H0 = reinterpret_cast<float *>(sm + S16_H);
-    float *PAR = reinterpret_cast<float *>(sm + S16_PAR);
     float *IMG = reinterpret_cast<float *>(sm + S16_IMG);
-    const uint32_t bar_w0 = sbase + S16_BAR, bar_mma = sbase + S16_BAR + 16, tmem_slot = sbase + S16_BAR + 24;
-    // the pair's middle position straddles the two CTAs: the H rows the peer's stencil reaches are mirrored into its tile
+    float *T32 = reinterpret_cast<float *>(sm + S16_TAB);
+    uint32_t *TW = reinterpret_cast<uint32_t *>(sm + S16_TAB + 8 * T16_TABSTRIDE * 4);
+    const uint32_t bar_w0 = sbase + S16_BAR, bar_mma = sbase + S16_BAR + 16, bar_band = sbase + S16_BAR + 24,
+                   bar_free = sbase + S16_BAR + 32, tmem_slot = sbase + S16_BAR + 40;
     const uint32_t peer_h0 = mapa(sbase + S16_H, rank ^ 1u);
+    const uint32_t peer_band = mapa(bar_band, rank ^ 1u), peer_free = mapa(bar_free, rank ^ 1u);
 
-    for (int i = t; i < P16_FLOATS; i += T16_THREADS) PAR[i] = pimg[i];
     if (t == 0) {
         mbar_init(bar_w0, 1);
         mbar_init(bar_w0 + 8, 1);
-        mbar_init(bar_mma, 8);  // one tcgen05.commit per warp
+        mbar_init(bar_mma, 8);   // one tcgen05.commit per warp
+        mbar_init(bar_band, 1);  // one arrive.expect_tx per block + the peer's 1280 mirrored bytes
+        mbar_init(bar_free, 1);  // the peer's "I have read your band" arrival
         mbar_fence_init();
+    }
+    // Stem tables.  A board's input pixel is one of 8 bit triples (encoder.rs:22-43 writes only 0.0 / 1.0), so the stem
+    // 3 -> 128 convolution + lrelu of a pixel is one of 8 rows: each CTA computes them once, with the arithmetic of
+    // t16_stem (bit-identical to the general float-image path), as fp32 and as packed fp16 hi / lo A-operand words.
+    for (int e = t; e < 8 * 64; e += T16_THREADS) {
+        const int combo = e >> 6, ch = (e & 63) * 2;
+        const float v0 = (float)(combo & 1), v1 = (float)((combo >> 1) & 1), v2 = (float)(combo >> 2);
+        float2 sv = __ffma2_rn(make_float2(v0, v0), make_float2(P.wstem[0][ch], P.wstem[0][ch + 1]),
+                               make_float2(P.bstem[ch], P.bstem[ch + 1]));
+        sv = __ffma2_rn(make_float2(v1, v1), make_float2(P.wstem[1][ch], P.wstem[1][ch + 1]), sv);
+        sv = __ffma2_rn(make_float2(v2, v2), make_float2(P.wstem[2][ch], P.wstem[2][ch + 1]), sv);
+        const float a0 = t16_lrelu(sv.x), a1 = t16_lrelu(sv.y);
+        T32[combo * T16_TABSTRIDE + ch] = a0;
+        T32[combo * T16_TABSTRIDE + ch + 1] = a1;
+        uint32_t hi, lo;
+        split2_f16(a0, a1, hi, lo);
+        TW[combo * T16_TABSTRIDE + (ch >> 4) * 16 + ((ch & 15) >> 1)] = hi;  // group layout of t16_store_group: hi[8] then lo[8]
+        TW[combo * T16_TABSTRIDE + (ch >> 4) * 16 + 8 + ((ch & 15) >> 1)] = lo;
     }
     if (warp == 1) tmem_alloc<1>(tmem_slot, T16_TMEM_COLS);
     fence_before();
     __syncthreads();
+    cluster_sync_all();  // the peer's barriers exist before anything crosses the pair
     fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);  // this warp's lane quadrant
-    // Cluster barrier protocol for the single-buffered H tile: phase A ("my stencil reads are done, you may overwrite
-    // my mirror rows") is arrived after each stencil and waited before the next E1; phase B ("my E1 rows, local and
-    // mirrored, are written") is an arrive+wait between E1 and the stencil.  This arrive opens the first phase A.
-    cluster_arrive();
 
     uint32_t g = 0;          // running block counter: weight buffer = g & 1, its phase parity = (g >> 1) & 1
     uint32_t mma_uses = 0;   // completed uses of bar_mma
@@ -157,76 +268,69 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     };
     if (t == 0) issue_weights(0);
 
-    NNIn cur0{}, cur1{}, cur2{};
-    if (!images) {
-        cur0 = nn_in[min(pair * 3 + 0, rows - 1)];
-        cur1 = nn_in[min(pair * 3 + 1, rows - 1)];
-        cur2 = nn_in[min(pair * 3 + 2, rows - 1)];
-    }
+    // boards path: a thread needs only the request row of ITS position (prefetched one iteration ahead)
+    NNIn cur{};
+    if (!images) cur = nn_in[min(pair * 3 + j, rows - 1)];
     int pos_iter = 0;
     for (int tr = pair; tr < n_triples; tr += n_pairs, ++pos_iter) {
         const bool dbg_on = blockIdx.x == 0 && pos_iter == 1;
-        const int row = tr * 3 + j;                       // this thread's position (global row of the batch)
-        const bool real = R < 3 * kCells && row < rows;   // 13 padding lanes per pair; the last triple may be partial
+        const int row = tr * 3 + j;                  // this thread's position (global row of the batch)
+        const bool real = in_tile && row < rows;     // 13 padding lanes per pair; the last triple may be partial
         T16_STAMP(0);
-        // ---- input images of the triple (the reference's 243-float slot read as [81][3]) ----
-        if (t < 243) {
-            if (images) {
+        float x[64];
+        if (images) {
+            // ---- general float images (AgentModel::evaluate_pv takes any tensor): the reference's 243-float slot read as [81][3] ----
+            if (t < 243) {
                 IMG[t] = images[(size_t)min(tr * 3 + 0, rows - 1) * 243 + t];
                 IMG[243 + t] = images[(size_t)min(tr * 3 + 1, rows - 1) * 243 + t];
                 IMG[486 + t] = images[(size_t)min(tr * 3 + 2, rows - 1) * 243 + t];
-            } else {
-                IMG[t] = image_value(cur0.black, cur0.white, cur0.meta & 1u, (cur0.meta >> 1) & 1u, t);
-                IMG[243 + t] = image_value(cur1.black, cur1.white, cur1.meta & 1u, (cur1.meta >> 1) & 1u, t);
-                IMG[486 + t] = image_value(cur2.black, cur2.white, cur2.meta & 1u, (cur2.meta >> 1) & 1u, t);
             }
-        }
-        // prefetch the next triple's request rows: their global-load latency hides behind this whole iteration
-        if (!images && tr + n_pairs < n_triples) {
-            cur0 = nn_in[min((tr + n_pairs) * 3 + 0, rows - 1)];
-            cur1 = nn_in[min((tr + n_pairs) * 3 + 1, rows - 1)];
-            cur2 = nn_in[min((tr + n_pairs) * 3 + 2, rows - 1)];
-        }
-        __syncthreads();
-        // ---- stem 1x1 conv 3 -> 128 (network.rs:65-79): this thread's pixel, its 64 channels ----
-        float x[64];
-        {
+            __syncthreads();
             const int pc = real ? p : 0;  // padded rows recompute pixel 0 (harmless, never stored)
             const float *im = IMG + (real ? j : 0) * 243;
             const float v0 = im[3 * pc], v1 = im[3 * pc + 1], v2 = im[3 * pc + 2];
-#pragma unroll
-            for (int c = 0; c < 64; c += 4) {
-                const int ch = half * 64 + c;
-                const float4 b = *reinterpret_cast<const float4 *>(PAR + P16_BSTEM + ch);
-                const float4 w0 = *reinterpret_cast<const float4 *>(PAR + P16_WSTEM + ch);
-                const float4 w1 = *reinterpret_cast<const float4 *>(PAR + P16_WSTEM + 128 + ch);
-                const float4 w2 = *reinterpret_cast<const float4 *>(PAR + P16_WSTEM + 256 + ch);
-                float2 s01 = __ffma2_rn(make_float2(v0, v0), make_float2(w0.x, w0.y), make_float2(b.x, b.y));
-                float2 s23 = __ffma2_rn(make_float2(v0, v0), make_float2(w0.z, w0.w), make_float2(b.z, b.w));
-                s01 = __ffma2_rn(make_float2(v1, v1), make_float2(w1.x, w1.y), s01);
-                s23 = __ffma2_rn(make_float2(v1, v1), make_float2(w1.z, w1.w), s23);
-                s01 = __ffma2_rn(make_float2(v2, v2), make_float2(w2.x, w2.y), s01);
-                s23 = __ffma2_rn(make_float2(v2, v2), make_float2(w2.z, w2.w), s23);
-                x[c + 0] = t16_lrelu(s01.x);
-                x[c + 1] = t16_lrelu(s01.y);
-                x[c + 2] = t16_lrelu(s23.x);
-                x[c + 3] = t16_lrelu(s23.y);
-            }
+            T16_HALF(t16_stem<0>(P, v0, v1, v2, x), t16_stem<1>(P, v0, v1, v2, x));
 #pragma unroll
             for (int c = 0; c < 4; ++c) t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c * 16), x + c * 16);
+        } else {
+            // ---- packed boards: the stem of this pixel is a table row ----
+            const int pc = in_tile ? p : 0;
+            const uint32_t combo = t16_image_bit(cur, 3 * pc) | (t16_image_bit(cur, 3 * pc + 1) << 1) | (t16_image_bit(cur, 3 * pc + 2) << 2);
+            // prefetch the next triple's request row: its global-load latency hides behind this whole iteration
+            if (tr + n_pairs < n_triples) cur = nn_in[min((tr + n_pairs) * 3 + j, rows - 1)];
+            const float4 *tx = reinterpret_cast<const float4 *>(T32 + combo * T16_TABSTRIDE + half * 64);
+            const uint4 *tw = reinterpret_cast<const uint4 *>(TW + combo * T16_TABSTRIDE + half * 64);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float4 v = tx[c];
+                x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t w[16];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4 v = tw[c * 4 + k];
+                    w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+                }
+                tmem_st16(tlane + TC_X + (uint32_t)(half * 64 + c * 16), w);
+            }
         }
         tmem_wait_st();
         T16_STAMP(1);
 
         for (int r = 0; r < 3; ++r, ++g) {
-            const float *bp = PAR + P16_BLK0 + r * P16_BLK;
+            const Tower16Block &B = P.blk[r];
             const uint32_t wb = sbase + S16_W + (g & 1u) * W16_BYTES;
             // ================= conv0: 1x1 128 -> 32 (A = X in TMEM) =================
             fence_before();
             __syncthreads();
             if (lane == 0) {
                 fence_after();
-                if (warp == 3) issue_weights(g + 1);  // the other buffer's last reader (block g-1, or the write-out) has completed
+                if (warp == 3) {
+                    issue_weights(g + 1);  // the other buffer's last reader (block g-1, or the write-out) has completed
+                    mbar_expect_tx(bar_band, T16_BAND_BYTES);  // arm this block's band phase
+                }
                 if (warp < 3) {
                     // one accumulator chain per product (lo.hi, hi.lo, hi.hi), issued in parallel from three threads: the
                     // single-thread issue path costs ~60 clk per small MMA
@@ -247,74 +351,49 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             T16_STAMP(2 + r * 8 + 0);
             // epilogue 1: + b0, lrelu -> fp32 tile for the depthwise stencil (this thread: 16 channels of its pixel)
             {
-                float d[16], e[16], f[16];
+                float d[16], e[16], f[16], o[16];
                 tmem_ld16(tlane + TC_ACC + half * 16, d);
                 tmem_ld16(tlane + TC_ACC + 32 + half * 16, e);
                 tmem_ld16(tlane + TC_ACC + 64 + half * 16, f);
-                cluster_wait();  // phase A: the peer has finished the previous stencil, its mirror rows may be overwritten
                 tmem_wait_ld();
-                const float inv = bp[P16_INV + 0];
+                T16_HALF(t16_bias_lrelu16<0>(B.b0, B.inv[0], d, e, f, o), t16_bias_lrelu16<1>(B.b0, B.inv[0], d, e, f, o));
+                if (in_tile) {
+                    float *hrow = H0 + (slot * kCells + p) * T16_HSTRIDE + half * 16;
 #pragma unroll
-                for (int c = 0; c < 16; c += 4) {
-                    const float4 b = *reinterpret_cast<const float4 *>(bp + P16_B0 + half * 16 + c);
-                    float4 o;
-                    o.x = t16_lrelu(fmaf((d[c + 0] + e[c + 0]) + f[c + 0], inv, b.x));
-                    o.y = t16_lrelu(fmaf((d[c + 1] + e[c + 1]) + f[c + 1], inv, b.y));
-                    o.z = t16_lrelu(fmaf((d[c + 2] + e[c + 2]) + f[c + 2], inv, b.z));
-                    o.w = t16_lrelu(fmaf((d[c + 3] + e[c + 3]) + f[c + 3], inv, b.w));
-                    if (real) {
-                        *reinterpret_cast<float4 *>(H0 + (slot * kCells + p) * T16_HSTRIDE + half * 16 + c) = o;
-                        // only the band the peer's stencil can reach (pixels 37..46 from CTA 0, 47..56 from CTA 1) is mirrored
-                        if (j == 1 && (rank == 0 ? p >= 37 : p <= 56)) {  // the peer keeps this position in its slot 1 - peer_rank = rank
-                            const uint32_t ra = peer_h0 + (uint32_t)((((int)rank * kCells + p) * T16_HSTRIDE + half * 16 + c) * 4);
-                            asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-                        }
-                    }
+                    for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4 *>(hrow + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+                }
+                if (band) {  // the peer keeps this position in its slot 1 - peer_rank = rank
+                    mbar_wait(bar_free, (g & 1u) ^ 1u);  // the peer has finished the previous block's stencil
+                    const uint32_t ra = peer_h0 + (uint32_t)((((int)rank * kCells + p) * T16_HSTRIDE + half * 16) * 4);
+#pragma unroll
+                    for (int c = 0; c < 16; c += 4)
+                        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                                     ::"r"(ra + c * 4), "f"(o[c]), "f"(o[c + 1]), "f"(o[c + 2]), "f"(o[c + 3]), "r"(peer_band) : "memory");
                 }
             }
-            // phase B: both CTAs' rows (local and mirrored) must be visible before the stencil
-            cluster_arrive();
-            cluster_wait();
+            __syncthreads();                 // this CTA's rows are in the tile
+            mbar_wait(bar_band, g & 1u);     // ... and so is the band mirrored by the peer
             T16_STAMP(2 + r * 8 + 1);
-            // conv1 depthwise 3x3, SAME zero padding, no bias (lib.rs:204-216) -> A operand of the pointwise conv
+            // conv1 depthwise 3x3 -> A operand of the pointwise conv
             {
                 float a[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) a[c] = 0.0f;
                 if (real) {
-                    const int y = p / kSide, xx0 = p % kSide;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int yy = y + ky - 1;
-                        if (yy < 0 || yy >= kSide) continue;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const int xx = xx0 + kx - 1;
-                            if (xx < 0 || xx >= kSide) continue;
-                            const float *hp = H0 + (slot * kCells + yy * kSide + xx) * T16_HSTRIDE + half * 16;
-                            const float *wp = bp + P16_DW + (ky * 3 + kx) * 32 + half * 16;
-#pragma unroll
-                            for (int c = 0; c < 16; c += 4) {
-                                const float4 h = *reinterpret_cast<const float4 *>(hp + c);
-                                const float4 w = *reinterpret_cast<const float4 *>(wp + c);
-                                // packed fp32x2 FMA (sm_100): same results as two FFMAs, half the issue slots
-                                float2 lo2 = __ffma2_rn(make_float2(h.x, h.y), make_float2(w.x, w.y), make_float2(a[c + 0], a[c + 1]));
-                                float2 hi2 = __ffma2_rn(make_float2(h.z, h.w), make_float2(w.z, w.w), make_float2(a[c + 2], a[c + 3]));
-                                a[c + 0] = lo2.x; a[c + 1] = lo2.y; a[c + 2] = hi2.x; a[c + 3] = hi2.y;
-                            }
-                        }
-                    }
+                    const float *Hpos = H0 + slot * kCells * T16_HSTRIDE;
+                    const int y = p / kSide, xx0 = p - y * kSide;
+                    T16_HALF(t16_stencil<0>(B, Hpos, y, xx0, a), t16_stencil<1>(B, Hpos, y, xx0, a));
                 }
-                cluster_arrive();  // phase A of the next block: this CTA's stencil reads are done
                 t16_store_group(tlane + TC_H + (uint32_t)(half * 16), a);
             }
             tmem_wait_st();
             T16_STAMP(2 + r * 8 + 2);
             // ================= conv1 pointwise: 1x1 32 -> 32 (A = H in TMEM) =================
             fence_before();
-            __syncthreads();
+            __syncthreads();  // also: every thread's stencil reads of the tile are complete
             if (lane == 0) {
                 fence_after();
+                if (warp == 3) mbar_arrive_cluster(peer_free);  // the peer may overwrite this CTA's mirrored band
                 if (warp < 3) {
                     const uint32_t acol = tmem_base + TC_H + (warp == 0 ? 8u : 0u);
                     const uint32_t bimg = wb + W16_PW + (warp == 1 ? 64u : 0u);
@@ -330,21 +409,13 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             fence_after();
             T16_STAMP(2 + r * 8 + 3);
             {   // epilogue 2: + b1, lrelu -> A operand of conv2
-                float d[16], e[16], f[16];
+                float d[16], e[16], f[16], o[16];
                 tmem_ld16(tlane + TC_ACC + half * 16, d);
                 tmem_ld16(tlane + TC_ACC + 32 + half * 16, e);
                 tmem_ld16(tlane + TC_ACC + 64 + half * 16, f);
                 tmem_wait_ld();
-                const float inv = bp[P16_INV + 1];
-#pragma unroll
-                for (int c = 0; c < 16; c += 4) {
-                    const float4 b = *reinterpret_cast<const float4 *>(bp + P16_B1 + half * 16 + c);
-                    d[c + 0] = t16_lrelu(fmaf((d[c + 0] + e[c + 0]) + f[c + 0], inv, b.x));
-                    d[c + 1] = t16_lrelu(fmaf((d[c + 1] + e[c + 1]) + f[c + 1], inv, b.y));
-                    d[c + 2] = t16_lrelu(fmaf((d[c + 2] + e[c + 2]) + f[c + 2], inv, b.z));
-                    d[c + 3] = t16_lrelu(fmaf((d[c + 3] + e[c + 3]) + f[c + 3], inv, b.w));
-                }
-                t16_store_group(tlane + TC_H + (uint32_t)(half * 16), d);
+                T16_HALF(t16_bias_lrelu16<0>(B.b1, B.inv[1], d, e, f, o), t16_bias_lrelu16<1>(B.b1, B.inv[1], d, e, f, o));
+                t16_store_group(tlane + TC_H + (uint32_t)(half * 16), o);
             }
             tmem_wait_st();
             T16_STAMP(2 + r * 8 + 4);
@@ -370,32 +441,17 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             __syncwarp();
             fence_after();
             T16_STAMP(2 + r * 8 + 5);
-            {   // epilogue 3: x = lrelu(conv2 + b2 + x); the next block's A operand is written in place over D3
-                const float inv = bp[P16_INV + 2];
+            // epilogue 3: x = lrelu(conv2 + b2 + x); the next block's A operand is written in place over D3
 #pragma unroll
-                for (int c2 = 0; c2 < 4; c2 += 2) {
-                    float d[32];
-                    tmem_ld16(tlane + TC_D3 + half * 64 + c2 * 16, d);
-                    tmem_ld16(tlane + TC_D3 + half * 64 + c2 * 16 + 16, d + 16);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {  // padded rows carry harmless garbage; they are never stored
-                        const int c = c2 * 16 + i;
-                        const float4 b = *reinterpret_cast<const float4 *>(bp + P16_B2 + half * 64 + c);
-                        const float2 s01 = __ffma2_rn(make_float2(d[i + 0], d[i + 1]), make_float2(inv, inv), make_float2(b.x, b.y));
-                        const float2 s23 = __ffma2_rn(make_float2(d[i + 2], d[i + 3]), make_float2(inv, inv), make_float2(b.z, b.w));
-                        const float2 t01 = __fadd2_rn(s01, make_float2(x[c + 0], x[c + 1]));
-                        const float2 t23 = __fadd2_rn(s23, make_float2(x[c + 2], x[c + 3]));
-                        const float2 u01 = __fmul2_rn(t01, make_float2(0.2f, 0.2f)), u23 = __fmul2_rn(t23, make_float2(0.2f, 0.2f));
-                        x[c + 0] = fmaxf(t01.x, u01.x);
-                        x[c + 1] = fmaxf(t01.y, u01.y);
-                        x[c + 2] = fmaxf(t23.x, u23.x);
-                        x[c + 3] = fmaxf(t23.y, u23.y);
-                    }
-                    if (r < 2) {
-                        t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16), x + c2 * 16);
-                        t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16 + 16), x + c2 * 16 + 16);
-                    }
+            for (int c2 = 0; c2 < 4; c2 += 2) {
+                float d[32];
+                tmem_ld16(tlane + TC_D3 + half * 64 + c2 * 16, d);
+                tmem_ld16(tlane + TC_D3 + half * 64 + c2 * 16 + 16, d + 16);
+                tmem_wait_ld();
+                T16_HALF(t16_residual32<0>(B, c2 * 16, d, x), t16_residual32<1>(B, c2 * 16, d, x));
+                if (r < 2) {
+                    t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16), x + c2 * 16);
+                    t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16 + 16), x + c2 * 16 + 16);
                 }
             }
             tmem_wait_st();
@@ -411,11 +467,11 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
         T16_STAMP(31);
     }
     // (timestamps: 0 start, 1 stem done, then per block: conv0 done, E1+sync, dw stored, conv1 done, E2 stored, conv2 done, E3 stored)
-    cluster_wait();  // consume the last phase-A arrive: no distributed-shared-memory traffic is in flight past this point
     // drain the weight prefetch that was issued one block ahead, then release TMEM
     if (t == 0) mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
     fence_before();
     __syncthreads();
+    cluster_sync_all();  // no mirrored store or remote arrival is in flight once both CTAs are here
     if (warp == 1) {
         fence_after();
         tmem_dealloc<1>(tmem_base, T16_TMEM_COLS);
@@ -505,6 +561,11 @@ bool tower16_prepare_weights(omk_ctx *c) {
     k_tower16_absmax<<<9, 256, 0, c->stream>>>(a, w.tower16_absmax);
     k_tower16_pack<<<16, 256, 0, c->stream>>>(a, w.tower16_absmax, w.tower16_wimg, w.tower16_pimg);
     c->launches += 2;
+    // the fp32 parameter image is passed to k_tower16 by value (constant bank): keep a host copy
+    if (!c->tower16_params_host) c->tower16_params_host = malloc(sizeof(Tower16Params));
+    if (!c->tower16_params_host) return false;
+    if (cudaMemcpyAsync(c->tower16_params_host, w.tower16_pimg, sizeof(Tower16Params), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
     return true;
 }
 
@@ -563,11 +624,12 @@ bool launch_tower_f16(omk_ctx *c, const float *images_dev, int rows_bound) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const uint8_t *wimg = c->net.tower16_wimg;
-    const float *pimg = c->net.tower16_pimg;
+    if (!c->tower16_params_host) return false;
+    const Tower16Params &params = *reinterpret_cast<const Tower16Params *>(c->tower16_params_host);
     const NNIn *nn_in = c->ws.nn_in;
     const uint32_t *n_req = c->ws.n_req;
     __half *ah = c->ws.act0_h16, *al = c->ws.act0_l16;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower16, wimg, pimg, nn_in, images_dev, n_req, rows_bound, ah, al);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower16, wimg, params, nn_in, images_dev, n_req, rows_bound, ah, al);
     if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_tower16): %s\n", cudaGetErrorString(e));
     c->launches++;
     return e == cudaSuccess;
