@@ -48,6 +48,16 @@ def read_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the network kernels, from the committed
+    `ncu --set full` capture of this same workload (profiles/r01_ncu_traffic.json; tools/ncu_summary.py wrote it)."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        return {k: v["dram_bytes_per_launch"] for k, v in json.load(open(path)).items()}
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -272,26 +282,33 @@ def main():
         fc0_tflops = (int(stats.nn_evals) * FLOP_FC0) / (fc0_ms * 1e-3) / 1e12 if fc0_ms > 0 else 0.0
         tower_tflops = (int(stats.nn_evals) * FLOP_TOWER) / (tower_ms * 1e-3) / 1e12 if tower_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        fc0_tc = os.environ.get("OMK_FC0", "tc") != "simt"
-        roof_fc0 = {"bound": "tensor",
-                    "kernel": "k_fc0_tc (fc0 10368->512, tcgen05 kind::tf32, 3-pass hi/lo split, TMEM chunk promotion)" if fc0_tc
-                              else "k_gemm (fc0 10368->512, fp32 CUDA cores)",
+        fc0_mode = os.environ.get("OMK_FC0", "f16")
+        tower_mode = os.environ.get("OMK_TOWER", "f16")
+        passes = {"f16": 3, "simt": 0}
+        traffic = ncu_traffic()
+        fc0_names = {"f16": "k_fc16 (fc0 10368->512: tcgen05 kind::f16 cta_group::2, 3-pass fp16 hi/lo split, TMA-fed, TMEM chunk promotion)",
+                     "simt": "k_gemm (fc0 10368->512, fp32 CUDA cores)"}
+        tower_names = {"f16": "k_tower16 (stem + 3 bottleneck blocks: 1x1 convs on tcgen05 kind::f16 3-pass with the activations as TMEM A "
+                              "operand, depthwise 3x3 + epilogues on CUDA cores, two CTAs per SM)",
+                       "simt": "k_tower (fp32 CUDA cores in shared memory)"}
+        note = (f"{peaks['src']} bf16/fp16 dense sustained (MEASURED_PEAKS.json); the fp32-accurate path issues 3 fp16 MMAs per "
+                "product (hi.hi + hi.lo + lo.hi), so frac <= 1/3 by construction; tensor_pipe_tflops = 3 x achieved is what the "
+                "tensor pipe executes (DESIGN.md 3)")
+        roof_fc0 = {"bound": "tensor", "kernel": fc0_names.get(fc0_mode, fc0_mode),
                     "achieved": fc0_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fc0_tflops / peak,
-                    "tensor_pipe_tflops": 3 * fc0_tflops if fc0_tc else 0.0,
-                    "tf32_peak_estimate": peak / 2,
-                    "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json); TF32 runs at half the bf16 rate and "
-                                   "the fp32-accurate path issues 3 MMAs per product, so frac <= 1/6 by construction (DESIGN.md 3)",
+                    "tensor_pipe_tflops": passes.get(fc0_mode, 3) * fc0_tflops,
+                    "tensor_pipe_frac": passes.get(fc0_mode, 3) * fc0_tflops / peak,
+                    "peak_source": note,
                     "avg_launch_ms": fc0_ms / max(1, fc0_launches), "rows_per_launch": rows_per_launch,
-                    "share_of_step": fc0_ms / float(stats.gpu_ms) if stats.gpu_ms else None, "traffic": None}
-        tower_tc = os.environ.get("OMK_TOWER", "tc") != "simt"
-        roof_tower = {"bound": "tensor",
-                      "kernel": "k_tower_tc (stem + 3 bottleneck blocks; 1x1 convs on tcgen05 kind::tf32 3-pass with activations as TMEM A operand, "
-                                "depthwise 3x3 + activations on CUDA cores)" if tower_tc
-                                else "k_tower (stem + 3 bottleneck blocks, fp32 CUDA cores in shared memory)",
+                    "share_of_step": fc0_ms / float(stats.gpu_ms) if stats.gpu_ms else None,
+                    "traffic": traffic.get("k_fc16") if fc0_mode == "f16" else None}
+        roof_tower = {"bound": "tensor", "kernel": tower_names.get(tower_mode, tower_mode),
                       "achieved": tower_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tower_tflops / peak,
-                      "peak_source": f"{peaks['src']} bf16 dense sustained (MEASURED_PEAKS.json)",
+                      "tensor_pipe_tflops": passes.get(tower_mode, 3) * tower_tflops,
+                      "peak_source": note + "; this kernel is bound by its CUDA-core epilogues (issue slots), not by the tensor pipe",
                       "avg_launch_ms": tower_ms / max(1, tower_launches), "rows_per_launch": rows_per_launch,
-                      "share_of_step": tower_ms / float(stats.gpu_ms) if stats.gpu_ms else None, "traffic": None}
+                      "share_of_step": tower_ms / float(stats.gpu_ms) if stats.gpu_ms else None,
+                      "traffic": traffic.get("k_tower16") if tower_mode == "f16" else None}
         dominant, other = (roof_tower, roof_fc0) if tower_ms >= fc0_ms else (roof_fc0, roof_tower)
         line = {
             "metric": "mcts_simulations_per_sec", "value": sims / (ms * 1e-3), "unit": "simulations/s",

@@ -345,13 +345,13 @@ bool fc16_prepare_weights(omk_ctx *c) {
 }
 
 static bool refresh_maps16(omk_ctx *c, Fc16State *s) {
-    if (s->a_ptr == c->ws.act0_h16 && s->a_rows == c->ws.max_rows) return true;
-    if (!encode_map16(&s->map0_a_hi, c->ws.act0_h16, (uint64_t)c->ws.max_rows, F_BM, F_K0)) return false;
-    if (!encode_map16(&s->map0_a_lo, c->ws.act0_l16, (uint64_t)c->ws.max_rows, F_BM, F_K0)) return false;
-    if (!encode_map16(&s->map1_a_hi, c->ws.act1_h16, (uint64_t)c->ws.max_rows, F_BM, F_K1)) return false;
-    if (!encode_map16(&s->map1_a_lo, c->ws.act1_l16, (uint64_t)c->ws.max_rows, F_BM, F_K1)) return false;
+    if (s->a_ptr == c->ws.act0_h16 && s->a_rows == c->ws.act_rows) return true;
+    if (!encode_map16(&s->map0_a_hi, c->ws.act0_h16, (uint64_t)c->ws.act_rows, F_BM, F_K0)) return false;
+    if (!encode_map16(&s->map0_a_lo, c->ws.act0_l16, (uint64_t)c->ws.act_rows, F_BM, F_K0)) return false;
+    if (!encode_map16(&s->map1_a_hi, c->ws.act1_h16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
+    if (!encode_map16(&s->map1_a_lo, c->ws.act1_l16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
     s->a_ptr = c->ws.act0_h16;
-    s->a_rows = c->ws.max_rows;
+    s->a_rows = c->ws.act_rows;
     return true;
 }
 

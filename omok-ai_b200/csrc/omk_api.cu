@@ -45,42 +45,47 @@ static int32_t ensure_workspace(omk_ctx *c, int rows) {
     CK(cudaStreamSynchronize(c->stream));
     Workspace &w = c->ws;
     cudaFree(w.nn_in); cudaFree(w.req_tree); cudaFree(w.req_node); cudaFree(w.P); cudaFree(w.V);
-    cudaFree(w.act0); cudaFree(w.act1); cudaFree(w.act2); cudaFree(w.logits); cudaFree(w.act0_hi); cudaFree(w.act0_lo);
-    cudaFree(w.act1_hi); cudaFree(w.act1_lo);
-    cudaFree(w.act0_h16); cudaFree(w.act0_l16); cudaFree(w.act1_h16); cudaFree(w.act1_l16);
-    w.act0 = w.act0_hi = w.act0_lo = w.act1_hi = w.act1_lo = nullptr;
-    w.act0_h16 = w.act0_l16 = w.act1_h16 = w.act1_l16 = nullptr;
     w.max_rows = 0;
     CK(cudaMalloc(&w.nn_in, sizeof(NNIn) * (size_t)rows));
     CK(cudaMalloc(&w.req_tree, sizeof(uint32_t) * (size_t)rows));
     CK(cudaMalloc(&w.req_node, sizeof(uint32_t) * (size_t)rows));
     CK(cudaMalloc(&w.P, sizeof(float) * (size_t)rows * kRow));
     CK(cudaMalloc(&w.V, sizeof(float) * (size_t)rows));
-    CK(cudaMalloc(&w.act0, sizeof(float) * (size_t)rows * 10368));
-    CK(cudaMalloc(&w.act0_hi, sizeof(float) * (size_t)rows * 10368));
-    CK(cudaMalloc(&w.act0_lo, sizeof(float) * (size_t)rows * 10368));
-    CK(cudaMemsetAsync(w.act0_hi, 0, sizeof(float) * (size_t)rows * 10368, c->stream));
-    CK(cudaMemsetAsync(w.act0_lo, 0, sizeof(float) * (size_t)rows * 10368, c->stream));
-    CK(cudaMalloc(&w.act1, sizeof(float) * (size_t)rows * 512));
-    CK(cudaMalloc(&w.act1_hi, sizeof(float) * (size_t)rows * 512));
-    CK(cudaMalloc(&w.act1_lo, sizeof(float) * (size_t)rows * 512));
-    CK(cudaMemsetAsync(w.act1_hi, 0, sizeof(float) * (size_t)rows * 512, c->stream));
-    CK(cudaMemsetAsync(w.act1_lo, 0, sizeof(float) * (size_t)rows * 512, c->stream));
-    CK(cudaMalloc(&w.act0_h16, sizeof(__half) * (size_t)rows * 10368));
-    CK(cudaMalloc(&w.act0_l16, sizeof(__half) * (size_t)rows * 10368));
-    CK(cudaMemsetAsync(w.act0_h16, 0, sizeof(__half) * (size_t)rows * 10368, c->stream));
-    CK(cudaMemsetAsync(w.act0_l16, 0, sizeof(__half) * (size_t)rows * 10368, c->stream));
-    CK(cudaMalloc(&w.act1_h16, sizeof(__half) * (size_t)rows * 512));
-    CK(cudaMalloc(&w.act1_l16, sizeof(__half) * (size_t)rows * 512));
-    CK(cudaMemsetAsync(w.act1_h16, 0, sizeof(__half) * (size_t)rows * 512, c->stream));
-    CK(cudaMemsetAsync(w.act1_l16, 0, sizeof(__half) * (size_t)rows * 512, c->stream));
-    CK(cudaMalloc(&w.act2, sizeof(float) * (size_t)rows * 512));
-    CK(cudaMalloc(&w.logits, sizeof(float) * (size_t)rows * 128));
-    CK(cudaMemsetAsync(w.act0, 0, sizeof(float) * (size_t)rows * 10368, c->stream));
     CK(cudaMemsetAsync(w.nn_in, 0, sizeof(NNIn) * (size_t)rows, c->stream));
     w.max_rows = rows;
     return OMK_OK;
 }
+
+namespace omk {
+// Activation buffers of the network, sized on first use (the hash evaluator never needs them): fp16 hi/lo operands of the
+// tensor-core path always; the fp32 buffers of the CUDA-core A/B kernels only once such a mode has been selected.
+bool ensure_activations(omk_ctx *c, int rows) {
+    Workspace &w = c->ws;
+    rows = (rows + 255) / 256 * 256;
+    const bool want_fp32 = c->tower_mode == 0 || c->fc0_mode == 0;
+    if (rows <= w.act_rows && (!want_fp32 || w.act_fp32)) return true;
+    if (rows < w.act_rows) rows = w.act_rows;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+    void **bufs[] = {(void **)&w.act0_h16, (void **)&w.act0_l16, (void **)&w.act1_h16, (void **)&w.act1_l16, (void **)&w.act2,
+                     (void **)&w.logits, (void **)&w.act0, (void **)&w.act1};
+    for (void **b : bufs) {
+        cudaFree(*b);
+        *b = nullptr;
+    }
+    w.act_rows = 0;
+    w.act_fp32 = false;
+    const size_t r = (size_t)rows;
+    const size_t sizes[] = {sizeof(__half) * r * 10368, sizeof(__half) * r * 10368, sizeof(__half) * r * 512, sizeof(__half) * r * 512,
+                            sizeof(float) * r * 512, sizeof(float) * r * 128, sizeof(float) * r * 10368, sizeof(float) * r * 512};
+    for (int i = 0; i < (want_fp32 ? 8 : 6); ++i) {
+        if (cudaMalloc(bufs[i], sizes[i]) != cudaSuccess) return false;
+        if (cudaMemsetAsync(*bufs[i], 0, sizes[i], c->stream) != cudaSuccess) return false;  // padded tile rows read zeros, never NaNs
+    }
+    w.act_rows = rows;
+    w.act_fp32 = want_fp32;
+    return true;
+}
+}  // namespace omk
 
 static int32_t check_device_error(omk_ctx *c) {
     uint32_t e = 0;
@@ -168,10 +173,8 @@ extern "C" int32_t omk_ctx_create(int32_t device, int32_t capacity_envs, int32_t
     c->cap_trees = capacity_trees;
     c->cap_nodes = capacity_nodes;
     c->seed = seed;
-    auto parse_mode = [](const char *m) { return strcmp(m, "simt") == 0 ? 0 : (strcmp(m, "tf32") == 0 ? 1 : 2); };
+    auto parse_mode = [](const char *m) { return strcmp(m, "simt") == 0 ? 0 : 1; };
     if (const char *m = getenv("OMK_FC0")) c->fc0_mode = parse_mode(m);
-    if (const char *m = getenv("OMK_FC0_PAIR")) c->fc0_pair = atoi(m) != 0;
-    if (const char *m = getenv("OMK_TOWER_PAIR")) c->tower_pair = atoi(m) != 0;
     if (const char *m = getenv("OMK_TOWER")) c->tower_mode = parse_mode(m);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
@@ -216,11 +219,9 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
     void *ptrs[] = {c->envs, c->tree_hdrs, c->tree_nodes, c->remap, c->dev_error, c->dev_sims, w.nn_in, w.req_tree,
                     w.req_node, w.P, w.V, w.act0, w.act1, w.act2, w.logits, w.n_req, w.slot_base, w.slot_count, w.ids,
                     w.actions, w.modes, w.temps, w.status, w.policy_out, w.streams, c->net.heads_w, c->net.heads_b,
-                    c->sp_ply, c->sp_buf, w.act0_hi, w.act0_lo, c->net.fc0_wt_hi, c->net.fc0_wt_lo, c->net.fc1_wt_hi, c->net.fc1_wt_lo, w.act1_hi, w.act1_lo, c->net.tower_wimg,
-                    c->net.tower_pimg, w.act0_h16, w.act0_l16, w.act1_h16, w.act1_l16, c->net.fc0_wt_h16, c->net.fc0_wt_l16,
+                    c->sp_ply, c->sp_buf, w.act0_h16, w.act0_l16, w.act1_h16, w.act1_l16, c->net.fc0_wt_h16, c->net.fc0_wt_l16,
                     c->net.fc1_wt_h16, c->net.fc1_wt_l16, c->net.fc_inv_scale, c->net.fc_absmax, c->net.tower16_wimg,
                     c->net.tower16_pimg, c->net.tower16_absmax};
-    fc0_tc_free(c);
     fc16_free(c);
     free(c->tower16_params_host);
     for (void *p : ptrs) cudaFree(p);
@@ -251,8 +252,6 @@ extern "C" int32_t omk_net_load_params(omk_ctx *c, const float *const *tensors, 
     for (int i = 0; i < kNetTensors; ++i)
         CK(cudaMemcpyAsync(c->net.t[i], tensors[i], sizeof(float) * (size_t)kLens[i], cudaMemcpyHostToDevice, c->stream));
     net_pack_heads(c);
-    if (!fc0_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core fc0 weight preparation failed");
-    if (!tower_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core tower weight preparation failed");
     if (!fc16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split fc weight preparation failed");
     if (!tower16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split tower weight preparation failed");
     CK(cudaStreamSynchronize(c->stream));
@@ -273,8 +272,6 @@ extern "C" int32_t omk_net_init_random(omk_ctx *c, uint64_t seed) {
     CK(cudaSetDevice(c->device));
     launch_net_init_random(c, seed);
     net_pack_heads(c);
-    if (!fc0_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core fc0 weight preparation failed");
-    if (!tower_tc_prepare_weights(c)) return fail(OMK_ERR_CUDA, "tensor-core tower weight preparation failed");
     if (!fc16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split fc weight preparation failed");
     if (!tower16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split tower weight preparation failed");
     CK(cudaStreamSynchronize(c->stream));
@@ -333,20 +330,19 @@ extern "C" int32_t omk_net_eval_images(omk_ctx *c, const float *images, int32_t 
 
 // ------------------------------------------------------------------ diagnostics
 extern "C" int32_t omk_debug_set_fc0_mode(omk_ctx *c, int32_t mode) {
-    if (mode < 0 || mode > 2) return fail(OMK_ERR_INVALID, "fc0 mode must be 0 (fp32 CUDA cores), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xFP16)");
+    if (mode != 0 && mode != 1) return fail(OMK_ERR_INVALID, "fc0 mode must be 1 (tcgen05 3xFP16) or 0 (fp32 CUDA cores, A/B check)");
     c->fc0_mode = mode;
     return OMK_OK;
 }
 extern "C" int32_t omk_debug_set_tower_mode(omk_ctx *c, int32_t mode) {
-    if (mode < 0 || mode > 2) return fail(OMK_ERR_INVALID, "tower mode must be 0 (fp32 CUDA cores), 1 (tcgen05 3xTF32) or 2 (tcgen05 3xFP16)");
+    if (mode != 0 && mode != 1) return fail(OMK_ERR_INVALID, "tower mode must be 1 (tcgen05 3xFP16) or 0 (fp32 CUDA cores, A/B check)");
     c->tower_mode = mode;
     return OMK_OK;
 }
 extern "C" int32_t omk_debug_tower_timing(omk_ctx *c, int64_t *out64) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    if (c->tower_mode == 2) tower16_read_timing(reinterpret_cast<long long *>(out64));
-    else tower_tc_read_timing(reinterpret_cast<long long *>(out64));
+    tower16_read_timing(reinterpret_cast<long long *>(out64));
     return OMK_OK;
 }
 extern "C" int32_t omk_debug_get_buffer(omk_ctx *c, int32_t which, float *out, int64_t count) {
@@ -361,8 +357,7 @@ extern "C" int32_t omk_debug_get_buffer(omk_ctx *c, int32_t which, float *out, i
         cudaFree(tmp);
         return OMK_OK;
     }
-    const float *src = which == 0 ? c->ws.act0 : which == 1 ? c->ws.act1 : which == 2 ? c->ws.act2 : which == 3 ? c->ws.logits
-                     : which == 4 ? c->ws.act0_hi : which == 5 ? c->ws.act0_lo : which == 6 ? c->ws.act1_hi : which == 7 ? c->ws.act1_lo : nullptr;
+    const float *src = which == 0 ? c->ws.act0 : which == 1 ? c->ws.act1 : which == 2 ? c->ws.act2 : which == 3 ? c->ws.logits : nullptr;
     if (!src || !out || count < 0) return fail(OMK_ERR_INVALID, "bad buffer id");
     CK(cudaMemcpyAsync(out, src, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

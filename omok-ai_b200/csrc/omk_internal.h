@@ -19,11 +19,6 @@ struct NetWeights {
     float *t[kNetTensors] = {};  // device copies in checkpoint order
     float *heads_w = nullptr;    // [512][128]: cols 0..80 policy, col 81 value, rest 0
     float *heads_b = nullptr;    // [128]
-    float *fc0_wt_hi = nullptr;  // [512][10368] K-major TF32-exact high part of fc0_w (tensor-core path)
-    float *fc0_wt_lo = nullptr;  // [512][10368] residual low part
-    float *fc1_wt_hi = nullptr, *fc1_wt_lo = nullptr;  // [512][512] same for fc1
-    uint8_t *tower_wimg = nullptr;  // 3 x 72 KB pre-swizzled B-operand images of the tower weights (tower_tc.cu)
-    float *tower_pimg = nullptr;    // fp32 stem / bias / depthwise parameters
     // fp16-split tensor-core path (fc_f16.cu, tower_f16.cu): weights scaled by a power of two, then split hi/lo
     __half *fc0_wt_h16 = nullptr, *fc0_wt_l16 = nullptr;  // [512][10368] K-major
     __half *fc1_wt_h16 = nullptr, *fc1_wt_l16 = nullptr;  // [512][512]
@@ -35,22 +30,21 @@ struct NetWeights {
     bool loaded = false;
 };
 
-struct Workspace {  // evaluator request/response buffers, sized for max_rows
+struct Workspace {  // evaluator request/response buffers [max_rows]; activation buffers [act_rows], allocated on first use
     int max_rows = 0;
+    int act_rows = 0;
+    bool act_fp32 = false;        // the fp32 buffers of the CUDA-core A/B kernels exist (act0, act1)
     NNIn *nn_in = nullptr;        // [max_rows]
     uint32_t *req_tree = nullptr; // [max_rows]
     uint32_t *req_node = nullptr; // [max_rows]
     float *P = nullptr;           // [max_rows][96]
     float *V = nullptr;           // [max_rows]
-    float *act0 = nullptr;        // [max_rows][10368] tower output == fc0 input (fp32 CUDA-core path)
-    float *act0_hi = nullptr;     // [max_rows][10368] TF32-exact high part (tensor-core path)
-    float *act0_lo = nullptr;     // [max_rows][10368] residual low part
-    float *act1 = nullptr;        // [max_rows][512]
-    float *act1_hi = nullptr, *act1_lo = nullptr;  // [max_rows][512] hi/lo split of fc0's output (tensor-core fc1)
-    __half *act0_h16 = nullptr, *act0_l16 = nullptr;  // [max_rows][10368] fp16 hi/lo split of the tower output (fp16-split path)
-    __half *act1_h16 = nullptr, *act1_l16 = nullptr;  // [max_rows][512] fp16 hi/lo split of fc0's output
-    float *act2 = nullptr;        // [max_rows][512]
-    float *logits = nullptr;      // [max_rows][128]
+    __half *act0_h16 = nullptr, *act0_l16 = nullptr;  // [act_rows][10368] fp16 hi/lo split of the tower output == fc0's A operand
+    __half *act1_h16 = nullptr, *act1_l16 = nullptr;  // [act_rows][512] fp16 hi/lo split of fc0's output == fc1's A operand
+    float *act2 = nullptr;        // [act_rows][512] fc1 output
+    float *logits = nullptr;      // [act_rows][128]
+    float *act0 = nullptr;        // [act_rows][10368] fp32 tower output (CUDA-core A/B kernels only)
+    float *act1 = nullptr;        // [act_rows][512]   fp32 fc0 output   (CUDA-core A/B kernels only)
     uint32_t *n_req = nullptr;    // device counter
     uint32_t *slot_base = nullptr, *slot_count = nullptr;  // [capacity_trees]
     int32_t *ids = nullptr;       // [capacity_trees] device copy of the call's id list
@@ -90,14 +84,11 @@ struct omk_ctx {
 
     omk::NetWeights net;
     omk::Workspace ws;
-    int fc0_mode = 2;               // 0: fp32 CUDA-core k_gemm, 1: tcgen05 3xTF32 k_fc_tc, 2: tcgen05 3xFP16 k_fc16 (default)
+    int fc0_mode = 1;               // fc0 + fc1: 1 = tcgen05 3xFP16 k_fc16 (the product path), 0 = fp32 CUDA-core k_gemm (A/B check only)
     void *fc16_state = nullptr;     // tensor maps of the fp16-split path (fc_f16.cu)
     int tower16_pairs = 0;          // resident CTA pairs of k_tower16 (0 = not queried yet)
     void *tower16_params_host = nullptr;  // host copy of the tower's fp32 parameter image (kernel argument of k_tower16)
-    void *fc0_tc_state = nullptr;   // tensor maps of the tensor-core path (fc0_tc.cu)
-    int fc0_pair = 1;               // 1: fc0 runs the cta_group::2 (CTA pair, 256x256 tile) kernel; 0: one CTA per 128x256 tile
-    int tower_pair = 1;             // 1: k_tower_tc3 (CTA pair, three positions per iteration); 0: k_tower_tc (one position per CTA)
-    int tower_mode = 2;             // 0: fp32 CUDA-core k_tower, 1: tcgen05 3xTF32 k_tower_tc, 2: tcgen05 3xFP16 k_tower16 (default)
+    int tower_mode = 1;             // tower: 1 = tcgen05 3xFP16 k_tower16 (the product path), 0 = fp32 CUDA-core k_tower (A/B check only)
 
     // self-play driver state
     omk_selfplay_config sp_cfg{};
@@ -154,17 +145,8 @@ void net_forward(omk_ctx *c, const float *images_dev /* or nullptr: use ws.nn_in
 void net_pack_heads(omk_ctx *c);
 void launch_net_init_random(omk_ctx *c, uint64_t seed);
 
-// fc0_tc.cu
-bool fc0_tc_prepare_weights(omk_ctx *c);
-bool launch_fc0_tc(omk_ctx *c, int rows_bound, bool split_out);
-bool launch_fc1_tc(omk_ctx *c, int rows_bound);
-void fc0_tc_free(omk_ctx *c);
-
-// tower_tc.cu
-bool tower_tc_prepare_weights(omk_ctx *c);
-void launch_tower_tc(omk_ctx *c, const float *images_dev, int rows_bound, bool split_out);
-void tower_tc_read_timing(long long *out64);
-
+// omk_api.cu: size the activation buffers for `rows` evaluator rows (fp32 A/B buffers only when a CUDA-core mode is on)
+bool ensure_activations(omk_ctx *c, int rows);
 
 // fc_f16.cu
 bool fc16_prepare_weights(omk_ctx *c);

@@ -376,7 +376,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
 // kApplyNewGame: agent.rs:20-25 (raw, unmasked); kApplyEnsure: agent.rs:159-182.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_apply(TreeArgs a, int mode) {
-    const int slot = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    // Requests of a tree are handled in chunks of 16, in four warp-wide phases, so that the dependent chains of the 16
+    // requests overlap instead of running back to back: (B) gather + mask the 16 network rows into shared memory,
+    // (C) lane i runs request i's SEQUENTIAL index-order f32 sum (the reference's `iter().sum()`, :241) -- 16 chains side
+    // by side instead of 16 x 81 dependent warp shuffles --, (D) scale + store the policies, (E) lane 0 applies the
+    // backups in request order (the f32 adds along shared ancestors are order-dependent).
+    constexpr int kChunk = 16;
+    __shared__ float s_p[kWarpsPerBlock][kChunk][kCells];       // odd row stride: the per-lane chains are conflict-free
+    __shared__ uint32_t s_meta[kWarpsPerBlock][kChunk][4];      // node id, header word 9 (parent | action), word 10, -V bits
+    const int wib = threadIdx.x >> 5;
+    const int slot = blockIdx.x * kWarpsPerBlock + wib;
     const int lane = threadIdx.x & 31;
     if (slot >= a.n) return;
     const int tree = tree_of(a, slot);
@@ -387,64 +396,100 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_apply(TreeArgs a, int m
     if (cnt == 0) return;
     uint32_t root_n = th->root_n;
     float root_w = th->root_w;
-    NodeHdr root_h{};
-    if (mode == kApplyEnsure) root_h = load_hdr(tn);
+    uint32_t root_occ[3] = {0u, 0u, 0u};
+    if (mode == kApplyEnsure) {
+        const NodeHdr root_h = load_hdr(tn);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) root_occ[k] = root_h.black[k] | root_h.white[k];
+    }
+    float(*sp)[kCells] = s_p[wib];
+    uint32_t(*meta)[4] = s_meta[wib];
 
-    for (int i = 0; i < cnt; ++i) {
-        const uint32_t row = base + (uint32_t)i;
-        const uint32_t id = a.req_node[row];
-        uint8_t *nd = node_ptr(tn, id);
-        NodeHdr h = load_hdr(nd);
-        const float *Prow = a.P + (size_t)row * kRow;
-        float p[3];
+    for (int c0 = 0; c0 < cnt; c0 += kChunk) {
+        const int m = min(kChunk, cnt - c0);
+        const uint32_t row0 = base + (uint32_t)c0;
+        // ---- (A) lane i fetches request i's node id and value ----
+        uint32_t my_id = 0;
+        float my_v = 0.0f;
+        if (lane < m) {
+            my_id = a.req_node[row0 + lane];
+            if (mode == kApplySearch) my_v = -a.V[row0 + lane];  // :229 value from the opponent's perspective
+        }
+        // ---- (B) gather + mask (:232-239) ----
+#pragma unroll 4
+        for (int i = 0; i < m; ++i) {
+            const uint32_t id = __shfl_sync(kFull, my_id, i);
+            const NodeHdr h = load_hdr(node_ptr(tn, id));
+            const float *Prow = a.P + (size_t)(row0 + i) * kRow;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int c = lane + 32 * j;
-            p[j] = 0.0f;
-            if (c < kCells) {
-                p[j] = Prow[c];
-                if (mode == kApplySearch) {  // :232-239 mask by the node's own board
-                    const uint32_t occ = sel3(h.black[0] | h.white[0], h.black[1] | h.white[1], h.black[2] | h.white[2], c >> 5);
-                    if ((occ >> (c & 31)) & 1u) p[j] = 0.0f;
-                } else if (mode == kApplyEnsure) {  // agent.rs:165-171: the action, then the ROOT's occupancy
-                    const uint32_t occ = sel3(root_h.black[0] | root_h.white[0], root_h.black[1] | root_h.white[1],
-                                              root_h.black[2] | root_h.white[2], c >> 5);
-                    if (c == (int)h.action || ((occ >> (c & 31)) & 1u)) p[j] = 0.0f;
+            for (int j = 0; j < 3; ++j) {
+                const int c = lane + 32 * j;
+                if (c < kCells) {
+                    float v = Prow[c];
+                    if (mode == kApplySearch) {  // mask by the node's own board
+                        const uint32_t occ = sel3(h.black[0] | h.white[0], h.black[1] | h.white[1], h.black[2] | h.white[2], c >> 5);
+                        if ((occ >> (c & 31)) & 1u) v = 0.0f;
+                    } else if (mode == kApplyEnsure) {  // agent.rs:165-171: the action, then the ROOT's occupancy
+                        const uint32_t occ = sel3(root_occ[0], root_occ[1], root_occ[2], c >> 5);
+                        if (c == (int)h.action || ((occ >> (c & 31)) & 1u)) v = 0.0f;
+                    }
+                    sp[i][c] = v;
+                }
+            }
+            if (lane == i) {
+                meta[i][0] = id;
+                meta[i][1] = h.parent | (h.action << 16);
+                meta[i][2] = h.legal | (h.turn << 8) | (1u << 16);  // header word 10 with has_policy set
+                meta[i][3] = __float_as_uint(my_v);
+            }
+        }
+        __syncwarp();
+        // ---- (C) sequential sums, one request per lane (:241-249) ----
+        float inv = 0.0f;
+        bool scale = false;
+        if (mode != kApplyNewGame && lane < m) {
+            float sum = 0.0f;
+#pragma unroll 9
+            for (int c = 0; c < kCells; ++c) sum = __fadd_rn(sum, sp[lane][c]);
+            scale = kF32Eps <= sum;
+            if (scale) inv = __fdiv_rn(1.0f, sum);
+        }
+        // ---- (D) scale + store the policies (:243-252) ----
+#pragma unroll 4
+        for (int i = 0; i < m; ++i) {
+            const float inv_i = __shfl_sync(kFull, inv, i);
+            const bool scale_i = __shfl_sync(kFull, (int)scale, i) != 0;
+            const uint32_t id = __shfl_sync(kFull, my_id, i);
+            float *pol = node_policy(node_ptr(tn, id));
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int c = lane + 32 * j;
+                if (c < kCells) {
+                    const float v = sp[i][c];
+                    pol[c] = scale_i ? __fmul_rn(v, inv_i) : v;
                 }
             }
         }
-        if (mode != kApplyNewGame) {
-            const float s = seq_sum81(p);
-            if (kF32Eps <= s) {
-                const float inv = __fdiv_rn(1.0f, s);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) p[j] = __fmul_rn(p[j], inv);
-            }
-        }
-        float *pol = node_policy(nd);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int c = lane + 32 * j;
-            if (c < kCells) pol[c] = p[j];
-        }
+        // ---- (E) has_policy flag + backups, in request order (:264, node.rs:83-99) ----
         if (lane == 0) {
-            h.has_policy = 1;
-            reinterpret_cast<uint32_t *>(nd)[10] = h.legal | (h.turn << 8) | (1u << 16);
-            if (mode == kApplySearch) {
-                // :229 value from the opponent's perspective; :264 + node.rs:83-99 backup from the node itself
-                float v = -a.V[row];
-                uint32_t cur_parent = h.parent, cur_action = h.action;
-                while (cur_parent != kNoNode) {
-                    uint8_t *pn = node_ptr(tn, cur_parent);
-                    node_edge_n(pn)[cur_action] += 1u;
-                    node_edge_w(pn)[cur_action] = __fadd_rn(node_edge_w(pn)[cur_action], v);
-                    v = -v;
-                    const uint32_t w9 = reinterpret_cast<const uint32_t *>(pn)[9];
-                    cur_parent = w9 & 0xFFFFu;
-                    cur_action = (w9 >> 16) & 0xFFu;
+            for (int i = 0; i < m; ++i) {
+                uint8_t *nd = node_ptr(tn, meta[i][0]);
+                reinterpret_cast<uint32_t *>(nd)[10] = meta[i][2];
+                if (mode == kApplySearch) {
+                    float v = __uint_as_float(meta[i][3]);
+                    uint32_t cur_parent = meta[i][1] & 0xFFFFu, cur_action = (meta[i][1] >> 16) & 0xFFu;
+                    while (cur_parent != kNoNode) {
+                        uint8_t *pn = node_ptr(tn, cur_parent);
+                        node_edge_n(pn)[cur_action] += 1u;
+                        node_edge_w(pn)[cur_action] = __fadd_rn(node_edge_w(pn)[cur_action], v);
+                        v = -v;
+                        const uint32_t w9 = reinterpret_cast<const uint32_t *>(pn)[9];
+                        cur_parent = w9 & 0xFFFFu;
+                        cur_action = (w9 >> 16) & 0xFFu;
+                    }
+                    root_n += 1u;
+                    root_w = __fadd_rn(root_w, v);
                 }
-                root_n += 1u;
-                root_w = __fadd_rn(root_w, v);
             }
         }
         __syncwarp();

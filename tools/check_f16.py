@@ -41,7 +41,7 @@ def report(name, a, ref):
 run(0, 0)
 x0 = ctx.debug_get_buffer(0, n * 10368).reshape(n, 81, 128).astype(np.float64)
 a1_0 = ctx.debug_get_buffer(1, n * 512).reshape(n, 512).astype(np.float64)
-run(2, 0)
+run(1, 0)
 x2 = ctx.debug_get_buffer(0, n * 10368).reshape(n, 81, 128).astype(np.float64)
 d = report("tower f16 vs simt (act0)", x2, x0)
 bad = np.argwhere(d > 1e-4 * np.abs(x0).max())
@@ -51,7 +51,7 @@ if len(bad):
     print("  bad by pixel:", np.bincount(bad[:, 1], minlength=81).tolist())
     print("  bad by channel/16:", np.bincount(bad[:, 2] // 16, minlength=8).tolist())
 # 2. fc0 alone: CUDA-core tower -> split -> fp16-split fc0/fc1
-run(0, 2)
+run(0, 1)
 a1_2 = ctx.debug_get_buffer(9, n * 512).reshape(n, 512).astype(np.float64)
 d = report("fc0 f16 vs simt (act1)", a1_2, a1_0)
 bad = np.argwhere(d > 1e-4 * np.abs(a1_0).max())
@@ -61,13 +61,13 @@ m = min(n, 96)
 import torch  # noqa: E402
 
 rp, rv, _ = net_oracle.forward_boards(params, boards[:m], turns[:m], dtype=torch.float64)
-for tower, fc in ((0, 0), (1, 1), (2, 0), (0, 2), (2, 2)):
+for tower, fc in ((0, 0), (1, 0), (0, 1), (1, 1)):
     p, v = run(tower, fc)
     big = rp > 1e-12
     print(f"tower {tower} fc {fc}: max rel P vs fp64 {np.max(np.abs(p[:m][big] - rp[big]) / rp[big]):.3g}  "
           f"max rel V {np.max(np.abs(v[:m] - rv) / np.maximum(np.abs(rv), 1e-3)):.3g}", flush=True)
 # phase timing of one iteration (clock64 stamps inside k_tower16)
-run(2, 2)
+run(1, 1)
 ts = ctx.debug_tower_timing()
 names = ["start", "stem"] + [f"b{r}:{nm}" for r in range(3) for nm in ("conv0", "E1+sync", "dw+st", "conv1", "E2+st", "conv2", "E3+st", "-")]
 prev = ts[0]

@@ -17,6 +17,7 @@ ap.add_argument("--warm", type=int, default=2)
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--evaluator", default="net")
 ap.add_argument("--env", action="store_true")
+ap.add_argument("--tree-sweep", action="store_true", help="tree-kernel bandwidth vs pool size (hash evaluator, no network)")
 args = ap.parse_args()
 
 if args.env:
@@ -43,6 +44,27 @@ if args.env:
         out.append({"boards": n, "ms_per_step": ms, "board_steps_per_s": n / ms * 1e3, "algorithmic_GBs": n * 78 / ms / 1e6})
         ctx.close()
     print(json.dumps({"env_step_sweep": out}))
+    sys.exit(0)
+
+if args.tree_sweep:
+    # K2 roofline sweep: the tree kernels are warp-per-tree, so bandwidth grows with the number of concurrent trees until
+    # HBM saturates.  Hash evaluator (no network), 160 simulations per move in rounds of 16, two plies timed.
+    # Algorithmic bytes per simulation: 12*S + 16*(L+2) + 1720 - 972 (packed boards, no 972-byte image), S ~ 73, L ~ 1.
+    B_SIM = 12 * 73 + 16 * 3 + 1720 - 972
+    out = []
+    for games in (1024, 4096, 16384, 32768):
+        ctx = omk.Context(device=0, capacity_envs=4, capacity_trees=2 * games, capacity_nodes=768, seed=1)
+        ctx.selfplay_begin(games, 160, 16, 0.25, 0.03, 1.0, 30, omk.EVAL_HASH)
+        ctx.selfplay_run(2, profile=0, want_transitions=False)
+        stats, *_ = ctx.selfplay_run(2, profile=2, want_transitions=False)
+        kinds = stats.by_kind()
+        tree_ms = kinds["select_expand"][0] + kinds["apply"][0]
+        sims = int(stats.simulations)
+        out.append({"games": games, "trees": 2 * games, "sims": sims, "select_expand_ms": round(kinds["select_expand"][0], 3),
+                    "apply_ms": round(kinds["apply"][0], 3), "tree_sims_per_s": sims / tree_ms * 1e3,
+                    "algorithmic_GBs": sims * B_SIM / tree_ms / 1e6, "bytes_per_sim": B_SIM})
+        ctx.close()
+    print(json.dumps({"tree_sweep": out}))
     sys.exit(0)
 
 ev = omk.EVAL_NET if args.evaluator == "net" else omk.EVAL_HASH
