@@ -34,28 +34,33 @@ constexpr int F_BM = 128, F_BN = 256, F_BK = 64;  // BK fp16 elements = one 128-
 constexpr int F_N = 512;
 constexpr int F_K0 = 10368, F_K1 = 512;
 constexpr int F_A_BYTES = F_BM * F_BK * 2;        // 16 KB
-constexpr int F_THREADS = 320;
-constexpr uint32_t F_TMEM_COLS = 512;             // two 256-column accumulator buffers
 constexpr int F_CHUNK0 = 9;                       // fc0: 162 k-blocks = 18 x 9
 constexpr int F_CHUNK1 = 8;                       // fc1: 8 k-blocks = 1 x 8
 
-template <bool PAIR>
+template <bool PAIR, int BN>
 struct FcCfg {
     static constexpr int kStages = PAIR ? 3 : 2;
-    static constexpr int kBRows = PAIR ? 128 : 256;               // B rows loaded by one CTA
+    static constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows loaded by one CTA
     static constexpr int kBBytes = kBRows * F_BK * 2;             // 16 / 32 KB
     static constexpr int kStageBytes = 2 * F_A_BYTES + 2 * kBBytes;  // 64 / 96 KB
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
-    static constexpr uint32_t kIdesc = idesc_f16(PAIR ? 256 : 128, F_BN);
+    static constexpr uint32_t kIdesc = idesc_f16(PAIR ? 256 : 128, BN);
+    static constexpr int kDrainWarps = 4 * (BN / 128);            // one warp per lane quadrant and 128-column slab
+    static constexpr int kThreads = 64 + 32 * kDrainWarps;
+    static constexpr uint32_t kTmemCols = 2 * BN;                 // two accumulator buffers
 };
 
-template <int K, int CHUNK, bool PAIR>
-__global__ void __launch_bounds__(F_THREADS, 1)
+// BN = 256: fc0 / fc1 tiles.  BN = 128 with HEADS: the policy/value heads (512 -> 81 | 1, padded to 128 columns): a drain
+// thread owns a whole row of logits, so tanh (value, network.rs:188-202) and softmax (policy, :227-247) finish in registers.
+template <int K, int CHUNK, bool PAIR, int BN = 256, bool HEADS = false>
+__global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
     k_fc16(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
            const float *__restrict__ bias, const float *__restrict__ inv_scale_p, float *__restrict__ C,
-           __half *__restrict__ C_hi, __half *__restrict__ C_lo, const uint32_t *n_req, int max_rows) {
-    using Cfg = FcCfg<PAIR>;
+           __half *__restrict__ C_hi, __half *__restrict__ C_lo, const uint32_t *n_req, int max_rows,
+           float *__restrict__ P_out = nullptr, float *__restrict__ V_out = nullptr) {
+    using Cfg = FcCfg<PAIR, BN>;
+    static_assert(!HEADS || (BN == 128 && !PAIR), "the heads epilogue needs a whole logit row per thread");
     constexpr int CG = PAIR ? 2 : 1;
     constexpr int NKB = K / F_BK;
     constexpr int NCHUNK = NKB / CHUNK;
@@ -70,11 +75,11 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         rank = cluster_rank();
         const int pair = blockIdx.x >> 2;
         m0 = pair * 256 + (int)rank * F_BM;
-        n0 = (int)((blockIdx.x >> 1) & 1u) * F_BN;
+        n0 = (int)((blockIdx.x >> 1) & 1u) * BN;
         if (pair * 256 >= rows) return;  // uniform for the whole cluster
     } else {
         m0 = blockIdx.y * F_BM;
-        n0 = blockIdx.x * F_BN;
+        n0 = blockIdx.x * BN;
         if (m0 >= rows) return;  // uniform for the whole CTA, before any barrier or TMEM use
     }
     const bool leader = rank == 0;
@@ -96,11 +101,11 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tmem_full0 + 8 * b, 1);
-            mbar_init(tmem_empty0 + 8 * b, PAIR ? 16 : 8);  // one arrival per drain warp (of both CTAs)
+            mbar_init(tmem_empty0 + 8 * b, (PAIR ? 2 : 1) * Cfg::kDrainWarps);  // one arrival per drain warp (of both CTAs)
         }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<CG>(tmem_slot, F_TMEM_COLS);
+    if (warp == 1) tmem_alloc<CG>(tmem_slot, Cfg::kTmemCols);
     fence_before();
     __syncthreads();
     if constexpr (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before anything crosses the pair
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
                 const uint32_t use = (uint32_t)(ch >> 1);
                 mbar_wait(tmem_empty0 + 8 * buf, (use & 1u) ^ 1u);  // drained (passes at once for the first use)
                 fence_after();
-                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * F_BN);
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
                 for (int kc = 0; kc < CHUNK; ++kc) {
                     const int kb = ch * CHUNK + kc;
                     const int s = kb % Cfg::kStages;
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 #pragma unroll
             for (int c = 0; c < 128; c += 32) {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * F_BN + half * 128 + c), v);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 128 + c), v);
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[c + j] += v[j];
@@ -189,7 +194,30 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         const size_t coff = (size_t)row * F_N + n0 + half * 128;
         const float *brow = bias + n0 + half * 128;
         const float inv_scale = *inv_scale_p;  // undo the power-of-two weight scaling (exact)
-        if (row < rows) {  // rows past the batch are never stored (the tile may extend past the workspace)
+        if constexpr (HEADS) {
+            if (row < rows) {
+                // logits: columns 0..80 policy, 81 value (k_pack_heads); same softmax / tanh arithmetic as k_heads
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < kCells; ++j) {
+                    acc[j] = fmaf(acc[j], inv_scale, brow[j]);
+                    mx = fmaxf(mx, acc[j]);
+                }
+                float sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < kCells; ++j) {
+                    acc[j] = expf(acc[j] - mx);
+                    sum += acc[j];
+                }
+                const float inv = 1.0f / sum;
+                float *prow = P_out + (size_t)row * kRow;
+#pragma unroll
+                for (int j = 0; j < 80; j += 4)
+                    *reinterpret_cast<float4 *>(prow + j) = make_float4(acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
+                prow[80] = acc[80] * inv;
+                V_out[row] = tanhf(fmaf(acc[kCells], inv_scale, brow[kCells]));
+            }
+        } else if (row < rows) {  // rows past the batch are never stored (the tile may extend past the workspace)
 #pragma unroll
             for (int j = 0; j < 128; j += 8) {
                 float o[8];
@@ -224,7 +252,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
     if constexpr (PAIR) cluster_sync_all();  // the peer's shared memory and TMEM stay alive until every MMA and drain has finished
     if (warp == 1) {
         fence_after();
-        tmem_dealloc<CG>(tmem_base, F_TMEM_COLS);
+        tmem_dealloc<CG>(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -238,15 +266,15 @@ __global__ void k_absmax_bits(const float *__restrict__ w, long long n, uint32_t
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
-// W[K][512] -> K-major transposed fp16 hi / lo parts Wt[512][K] of W * 2^s; writes 2^-s to *inv_scale
+// W[K][N] -> K-major transposed fp16 hi / lo parts Wt[N][K] of W * 2^s; writes 2^-s to *inv_scale
 __global__ void k_fc16_split_weights(const float *__restrict__ W, const uint32_t *absmax_bits, __half *__restrict__ hi,
-                                     __half *__restrict__ lo, float *inv_scale, int K) {
+                                     __half *__restrict__ lo, float *inv_scale, int K, int N) {
     __shared__ float tile[32][33];
     const float scale = f16_split_scale(*absmax_bits);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *inv_scale = 1.0f / scale;
     const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    for (int r = ty; r < 32; r += 8) tile[r][tx] = W[(size_t)(k0 + r) * F_N + n0 + tx];
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = W[(size_t)(k0 + r) * N + n0 + tx];
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const float x = tile[tx][r] * scale;  // W[k0+tx][n0+r]
@@ -301,6 +329,7 @@ static bool encode_map16(CUtensorMap *map, __half *ptr, uint64_t rows, uint32_t 
 struct Fc16State {
     CUtensorMap map0_a_hi, map0_a_lo, map0_b_hi, map0_b_lo;  // fc0 (B boxes of 128 rows: the pair kernel loads half tiles)
     CUtensorMap map1_a_hi, map1_a_lo, map1_b_hi, map1_b_lo;  // fc1 (B boxes of 256 rows)
+    CUtensorMap map2_a_hi, map2_a_lo, map2_b_hi, map2_b_lo;  // heads (B = all 128 padded output rows)
     __half *a_ptr = nullptr;
     int a_rows = 0;
     bool weights_ready = false;
@@ -325,21 +354,28 @@ bool fc16_prepare_weights(omk_ctx *c) {
         if (cudaMalloc(&w.fc0_wt_l16, sizeof(__half) * (size_t)F_K0 * F_N) != cudaSuccess) return false;
         if (cudaMalloc(&w.fc1_wt_h16, sizeof(__half) * (size_t)F_K1 * F_N) != cudaSuccess) return false;
         if (cudaMalloc(&w.fc1_wt_l16, sizeof(__half) * (size_t)F_K1 * F_N) != cudaSuccess) return false;
-        if (cudaMalloc(&w.fc_inv_scale, sizeof(float) * 2) != cudaSuccess) return false;
-        if (cudaMalloc(&w.fc_absmax, sizeof(uint32_t) * 2) != cudaSuccess) return false;
+        if (cudaMalloc(&w.heads_wt_h16, sizeof(__half) * (size_t)F_K1 * 128) != cudaSuccess) return false;
+        if (cudaMalloc(&w.heads_wt_l16, sizeof(__half) * (size_t)F_K1 * 128) != cudaSuccess) return false;
+        if (cudaMalloc(&w.fc_inv_scale, sizeof(float) * 3) != cudaSuccess) return false;
+        if (cudaMalloc(&w.fc_absmax, sizeof(uint32_t) * 3) != cudaSuccess) return false;
     }
-    cudaMemsetAsync(w.fc_absmax, 0, sizeof(uint32_t) * 2, c->stream);
+    cudaMemsetAsync(w.fc_absmax, 0, sizeof(uint32_t) * 3, c->stream);
     k_absmax_bits<<<592, 256, 0, c->stream>>>(w.t[23], (long long)F_K0 * F_N, w.fc_absmax);
     k_absmax_bits<<<148, 256, 0, c->stream>>>(w.t[25], (long long)F_K1 * F_N, w.fc_absmax + 1);
+    k_absmax_bits<<<64, 256, 0, c->stream>>>(w.heads_w, (long long)F_K1 * 128, w.fc_absmax + 2);  // packed by net_pack_heads
     k_fc16_split_weights<<<dim3(F_K0 / 32, F_N / 32), 256, 0, c->stream>>>(w.t[23], w.fc_absmax, w.fc0_wt_h16, w.fc0_wt_l16,
-                                                                           w.fc_inv_scale, F_K0);
+                                                                           w.fc_inv_scale, F_K0, F_N);
     k_fc16_split_weights<<<dim3(F_K1 / 32, F_N / 32), 256, 0, c->stream>>>(w.t[25], w.fc_absmax + 1, w.fc1_wt_h16, w.fc1_wt_l16,
-                                                                           w.fc_inv_scale + 1, F_K1);
-    c->launches += 4;
+                                                                           w.fc_inv_scale + 1, F_K1, F_N);
+    k_fc16_split_weights<<<dim3(F_K1 / 32, 128 / 32), 256, 0, c->stream>>>(w.heads_w, w.fc_absmax + 2, w.heads_wt_h16, w.heads_wt_l16,
+                                                                         w.fc_inv_scale + 2, F_K1, 128);
+    c->launches += 6;
     if (!encode_map16(&s->map0_b_hi, w.fc0_wt_h16, F_N, 128, F_K0)) return false;
     if (!encode_map16(&s->map0_b_lo, w.fc0_wt_l16, F_N, 128, F_K0)) return false;
     if (!encode_map16(&s->map1_b_hi, w.fc1_wt_h16, F_N, F_BN, F_K1)) return false;
     if (!encode_map16(&s->map1_b_lo, w.fc1_wt_l16, F_N, F_BN, F_K1)) return false;
+    if (!encode_map16(&s->map2_b_hi, w.heads_wt_h16, 128, 128, F_K1)) return false;
+    if (!encode_map16(&s->map2_b_lo, w.heads_wt_l16, 128, 128, F_K1)) return false;
     s->weights_ready = true;
     return true;
 }
@@ -350,6 +386,8 @@ static bool refresh_maps16(omk_ctx *c, Fc16State *s) {
     if (!encode_map16(&s->map0_a_lo, c->ws.act0_l16, (uint64_t)c->ws.act_rows, F_BM, F_K0)) return false;
     if (!encode_map16(&s->map1_a_hi, c->ws.act1_h16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
     if (!encode_map16(&s->map1_a_lo, c->ws.act1_l16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
+    if (!encode_map16(&s->map2_a_hi, c->ws.act2_h16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
+    if (!encode_map16(&s->map2_a_lo, c->ws.act2_l16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
     s->a_ptr = c->ws.act0_h16;
     s->a_rows = c->ws.act_rows;
     return true;
@@ -367,12 +405,12 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     Fc16State *s = state16_of(c);
     if (!s->weights_ready || !refresh_maps16(c, s)) return false;
     auto kern = k_fc16<F_K0, F_CHUNK0, true>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<true>::kSmemBytes);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<true, 256>::kSmemBytes);
     const int pairs = (rows_bound + 255) / 256;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * (F_N / F_BN) * pairs, 1);
-    cfg.blockDim = dim3(F_THREADS);
-    cfg.dynamicSmemBytes = FcCfg<true>::kSmemBytes;
+    cfg.blockDim = dim3(FcCfg<true, 256>::kThreads);
+    cfg.dynamicSmemBytes = FcCfg<true, 256>::kSmemBytes;
     cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -386,25 +424,42 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     float *c_f32 = nullptr;
     __half *c_hi = c->ws.act1_h16, *c_lo = c->ws.act1_l16;
     const uint32_t *nreq_p = c->ws.n_req;
+    float *no_p = nullptr, *no_v = nullptr;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, s->map0_a_hi, s->map0_a_lo, s->map0_b_hi, s->map0_b_lo, bias_p, inv_p, c_f32,
-                                             c_hi, c_lo, nreq_p, rows_bound);
+                                             c_hi, c_lo, nreq_p, rows_bound, no_p, no_v);
     if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_fc16 pair): %s\n", cudaGetErrorString(e));
     c->launches++;
     return e == cudaSuccess && check_launch("fc0 (fp16 split)");
 }
 
-// fc1: act1_h16/l16 -> act2 (fp32, read by the heads GEMM)
+// fc1: act1_h16/l16 -> act2_h16/l16 (the A operand of the heads)
 bool launch_fc1_f16(omk_ctx *c, int rows_bound) {
     Fc16State *s = state16_of(c);
     if (!s->weights_ready || !refresh_maps16(c, s)) return false;
+    using Cfg = FcCfg<false, 256>;
     auto kern = k_fc16<F_K1, F_CHUNK1, false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<false>::kSmemBytes);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     const int mt = (rows_bound + F_BM - 1) / F_BM;
-    kern<<<dim3(F_N / F_BN, mt), F_THREADS, FcCfg<false>::kSmemBytes, c->stream>>>(
-        s->map1_a_hi, s->map1_a_lo, s->map1_b_hi, s->map1_b_lo, c->net.t[26], c->net.fc_inv_scale + 1, c->ws.act2, nullptr, nullptr,
-        c->ws.n_req, rows_bound);
+    kern<<<dim3(F_N / F_BN, mt), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+        s->map1_a_hi, s->map1_a_lo, s->map1_b_hi, s->map1_b_lo, c->net.t[26], c->net.fc_inv_scale + 1, nullptr, c->ws.act2_h16,
+        c->ws.act2_l16, c->ws.n_req, rows_bound, nullptr, nullptr);
     c->launches++;
     return check_launch("fc1 (fp16 split)");
+}
+
+// heads: act2_h16/l16 -> P (softmax of the 81 policy logits) and V (tanh of the value logit)
+bool launch_heads_f16(omk_ctx *c, int rows_bound) {
+    Fc16State *s = state16_of(c);
+    if (!s->weights_ready || !refresh_maps16(c, s)) return false;
+    using Cfg = FcCfg<false, 128>;
+    auto kern = k_fc16<F_K1, F_CHUNK1, false, 128, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    const int mt = (rows_bound + F_BM - 1) / F_BM;
+    kern<<<dim3(1, mt), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+        s->map2_a_hi, s->map2_a_lo, s->map2_b_hi, s->map2_b_lo, c->net.heads_b, c->net.fc_inv_scale + 2, nullptr, nullptr, nullptr,
+        c->ws.n_req, rows_bound, c->ws.P, c->ws.V);
+    c->launches++;
+    return check_launch("heads (fp16 split)");
 }
 
 }  // namespace omk

@@ -460,11 +460,16 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     }
     prof_end(c, sp);
     sp = prof_begin(c, OMK_K_HEADS, 2);
-    k_gemm<<<dim3(1, mt), 256, 0, c->stream>>>(c->ws.act2, c->net.heads_w, c->net.heads_b, c->ws.logits, c->ws.n_req, max_rows,
-                                               128, kFc, 0);
-    k_heads<<<(max_rows + 7) / 8, 256, 0, c->stream>>>(c->ws.logits, c->ws.n_req, max_rows, c->ws.P, c->ws.V);
+    if (c->fc0_mode == 1) {  // heads GEMM + tanh / softmax in one tensor-core kernel
+        launch_heads_f16(c, max_rows);
+    } else {
+        k_gemm<<<dim3(1, mt), 256, 0, c->stream>>>(c->ws.act2, c->net.heads_w, c->net.heads_b, c->ws.logits, c->ws.n_req, max_rows,
+                                                   128, kFc, 0);
+        k_heads<<<(max_rows + 7) / 8, 256, 0, c->stream>>>(c->ws.logits, c->ws.n_req, max_rows, c->ws.P, c->ws.V);
+        c->launches++;
+    }
     prof_end(c, sp);
-    c->launches += 5;
+    c->launches += 3;  // tower, fc0, fc1 (launch_heads_f16 / the CUDA-core heads counted above)
 }
 
 }  // namespace omk

@@ -66,8 +66,8 @@ bool ensure_activations(omk_ctx *c, int rows) {
     if (rows <= w.act_rows && (!want_fp32 || w.act_fp32)) return true;
     if (rows < w.act_rows) rows = w.act_rows;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
-    void **bufs[] = {(void **)&w.act0_h16, (void **)&w.act0_l16, (void **)&w.act1_h16, (void **)&w.act1_l16, (void **)&w.act2,
-                     (void **)&w.logits, (void **)&w.act0, (void **)&w.act1};
+    void **bufs[] = {(void **)&w.act0_h16, (void **)&w.act0_l16, (void **)&w.act1_h16, (void **)&w.act1_l16, (void **)&w.act2_h16,
+                     (void **)&w.act2_l16, (void **)&w.act2, (void **)&w.logits, (void **)&w.act0, (void **)&w.act1};
     for (void **b : bufs) {
         cudaFree(*b);
         *b = nullptr;
@@ -76,8 +76,9 @@ bool ensure_activations(omk_ctx *c, int rows) {
     w.act_fp32 = false;
     const size_t r = (size_t)rows;
     const size_t sizes[] = {sizeof(__half) * r * 10368, sizeof(__half) * r * 10368, sizeof(__half) * r * 512, sizeof(__half) * r * 512,
+                            sizeof(__half) * r * 512, sizeof(__half) * r * 512,
                             sizeof(float) * r * 512, sizeof(float) * r * 128, sizeof(float) * r * 10368, sizeof(float) * r * 512};
-    for (int i = 0; i < (want_fp32 ? 8 : 6); ++i) {
+    for (int i = 0; i < (want_fp32 ? 10 : 8); ++i) {
         if (cudaMalloc(bufs[i], sizes[i]) != cudaSuccess) return false;
         if (cudaMemsetAsync(*bufs[i], 0, sizes[i], c->stream) != cudaSuccess) return false;  // padded tile rows read zeros, never NaNs
     }
@@ -219,7 +220,7 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
     void *ptrs[] = {c->envs, c->tree_hdrs, c->tree_nodes, c->remap, c->dev_error, c->dev_sims, w.nn_in, w.req_tree,
                     w.req_node, w.P, w.V, w.act0, w.act1, w.act2, w.logits, w.n_req, w.slot_base, w.slot_count, w.ids,
                     w.actions, w.modes, w.temps, w.status, w.policy_out, w.streams, c->net.heads_w, c->net.heads_b,
-                    c->sp_ply, c->sp_buf, w.act0_h16, w.act0_l16, w.act1_h16, w.act1_l16, c->net.fc0_wt_h16, c->net.fc0_wt_l16,
+                    c->sp_ply, c->sp_buf, w.act0_h16, w.act0_l16, w.act1_h16, w.act1_l16, w.act2_h16, w.act2_l16, c->net.heads_wt_h16, c->net.heads_wt_l16, c->net.fc0_wt_h16, c->net.fc0_wt_l16,
                     c->net.fc1_wt_h16, c->net.fc1_wt_l16, c->net.fc_inv_scale, c->net.fc_absmax, c->net.tower16_wimg,
                     c->net.tower16_pimg, c->net.tower16_absmax};
     fc16_free(c);

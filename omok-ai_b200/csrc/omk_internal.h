@@ -22,8 +22,9 @@ struct NetWeights {
     // fp16-split tensor-core path (fc_f16.cu, tower_f16.cu): weights scaled by a power of two, then split hi/lo
     __half *fc0_wt_h16 = nullptr, *fc0_wt_l16 = nullptr;  // [512][10368] K-major
     __half *fc1_wt_h16 = nullptr, *fc1_wt_l16 = nullptr;  // [512][512]
-    float *fc_inv_scale = nullptr;     // [2] 2^-s of fc0, fc1
-    uint32_t *fc_absmax = nullptr;     // [2] max |w| bits
+    __half *heads_wt_h16 = nullptr, *heads_wt_l16 = nullptr;  // [128][512]: rows 0..80 policy, 81 value, rest 0
+    float *fc_inv_scale = nullptr;     // [3] 2^-s of fc0, fc1, heads
+    uint32_t *fc_absmax = nullptr;     // [3] max |w| bits
     uint8_t *tower16_wimg = nullptr;   // 3 x 36 KB pre-swizzled B-operand images
     float *tower16_pimg = nullptr;     // fp32 stem / bias / depthwise parameters + inverse scales
     uint32_t *tower16_absmax = nullptr;  // [9]
@@ -41,7 +42,8 @@ struct Workspace {  // evaluator request/response buffers [max_rows]; activation
     float *V = nullptr;           // [max_rows]
     __half *act0_h16 = nullptr, *act0_l16 = nullptr;  // [act_rows][10368] fp16 hi/lo split of the tower output == fc0's A operand
     __half *act1_h16 = nullptr, *act1_l16 = nullptr;  // [act_rows][512] fp16 hi/lo split of fc0's output == fc1's A operand
-    float *act2 = nullptr;        // [act_rows][512] fc1 output
+    __half *act2_h16 = nullptr, *act2_l16 = nullptr;  // [act_rows][512] fp16 hi/lo split of fc1's output == the heads' A operand
+    float *act2 = nullptr;        // [act_rows][512] fc1 output (fp32: CUDA-core heads, debugging)
     float *logits = nullptr;      // [act_rows][128]
     float *act0 = nullptr;        // [act_rows][10368] fp32 tower output (CUDA-core A/B kernels only)
     float *act1 = nullptr;        // [act_rows][512]   fp32 fc0 output   (CUDA-core A/B kernels only)
@@ -152,6 +154,7 @@ bool ensure_activations(omk_ctx *c, int rows);
 bool fc16_prepare_weights(omk_ctx *c);
 bool launch_fc0_f16(omk_ctx *c, int rows_bound);
 bool launch_fc1_f16(omk_ctx *c, int rows_bound);
+bool launch_heads_f16(omk_ctx *c, int rows_bound);
 void fc16_free(omk_ctx *c);
 void launch_f32_to_split16(omk_ctx *c, const float *x, __half *hi, __half *lo, long long n);
 void launch_split16_to_f32(omk_ctx *c, const __half *hi, const __half *lo, float *x, long long n);
