@@ -46,6 +46,8 @@ enum {
     OMK_ERR_CUDA = -2,      /* CUDA runtime failure (message has the detail) */
     OMK_ERR_CAPACITY = -3,  /* a tree ran out of node slots; raise capacity_nodes */
     OMK_ERR_STATE = -4,     /* call order (e.g. search before net weights are loaded) */
+    OMK_ERR_NUMERIC = -5,   /* the network produced a non-finite output (an activation beyond the fp16 range of the
+                               tensor-core operand split, or non-finite weights): results of this call are invalid */
 };
 
 /* evaluator driving the search */

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
            const float *__restrict__ bias, const float *__restrict__ inv_scale_p, float *__restrict__ C,
            __half *__restrict__ C_hi, __half *__restrict__ C_lo, const uint32_t *n_req, int max_rows,
-           float *__restrict__ P_out = nullptr, float *__restrict__ V_out = nullptr) {
+           float *__restrict__ P_out = nullptr, float *__restrict__ V_out = nullptr, uint32_t *dev_error = nullptr) {
     using Cfg = FcCfg<PAIR, BN>;
     static_assert(!HEADS || (BN == 128 && !PAIR), "the heads epilogue needs a whole logit row per thread");
     constexpr int CG = PAIR ? 2 : 1;
@@ -210,12 +210,15 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
                     sum += acc[j];
                 }
                 const float inv = 1.0f / sum;
+                const float vlogit = fmaf(acc[kCells], inv_scale, brow[kCells]);
+                // loud failure instead of silent garbage: an fp16 operand overflow upstream shows up here as NaN / Inf
+                if (!(sum >= 1.0f && sum < INFINITY) || !(fabsf(vlogit) < INFINITY)) atomicOr(dev_error, 2u);
                 float *prow = P_out + (size_t)row * kRow;
 #pragma unroll
                 for (int j = 0; j < 80; j += 4)
                     *reinterpret_cast<float4 *>(prow + j) = make_float4(acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
                 prow[80] = acc[80] * inv;
-                V_out[row] = tanhf(fmaf(acc[kCells], inv_scale, brow[kCells]));
+                V_out[row] = tanhf(vlogit);
             }
         } else if (row < rows) {  // rows past the batch are never stored (the tile may extend past the workspace)
 #pragma unroll
@@ -425,8 +428,9 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     __half *c_hi = c->ws.act1_h16, *c_lo = c->ws.act1_l16;
     const uint32_t *nreq_p = c->ws.n_req;
     float *no_p = nullptr, *no_v = nullptr;
+    uint32_t *no_err = nullptr;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, s->map0_a_hi, s->map0_a_lo, s->map0_b_hi, s->map0_b_lo, bias_p, inv_p, c_f32,
-                                             c_hi, c_lo, nreq_p, rows_bound, no_p, no_v);
+                                             c_hi, c_lo, nreq_p, rows_bound, no_p, no_v, no_err);
     if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_fc16 pair): %s\n", cudaGetErrorString(e));
     c->launches++;
     return e == cudaSuccess && check_launch("fc0 (fp16 split)");
@@ -442,7 +446,7 @@ bool launch_fc1_f16(omk_ctx *c, int rows_bound) {
     const int mt = (rows_bound + F_BM - 1) / F_BM;
     kern<<<dim3(F_N / F_BN, mt), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
         s->map1_a_hi, s->map1_a_lo, s->map1_b_hi, s->map1_b_lo, c->net.t[26], c->net.fc_inv_scale + 1, nullptr, c->ws.act2_h16,
-        c->ws.act2_l16, c->ws.n_req, rows_bound, nullptr, nullptr);
+        c->ws.act2_l16, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr);
     c->launches++;
     return check_launch("fc1 (fp16 split)");
 }
@@ -457,7 +461,7 @@ bool launch_heads_f16(omk_ctx *c, int rows_bound) {
     const int mt = (rows_bound + F_BM - 1) / F_BM;
     kern<<<dim3(1, mt), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
         s->map2_a_hi, s->map2_a_lo, s->map2_b_hi, s->map2_b_lo, c->net.heads_b, c->net.fc_inv_scale + 2, nullptr, nullptr, nullptr,
-        c->ws.n_req, rows_bound, c->ws.P, c->ws.V);
+        c->ws.n_req, rows_bound, c->ws.P, c->ws.V, c->dev_error);
     c->launches++;
     return check_launch("heads (fp16 split)");
 }

@@ -93,11 +93,14 @@ static int32_t check_device_error(omk_ctx *c) {
     CK(cudaMemcpyAsync(&e, c->dev_error, sizeof e, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
-    if (e & 1u) {
+    if (e) {
         uint32_t z = 0;
         cudaMemcpyAsync(c->dev_error, &z, sizeof z, cudaMemcpyHostToDevice, c->stream);
-        return fail(OMK_ERR_CAPACITY, "a tree ran out of node slots (capacity_nodes=" + std::to_string(c->cap_nodes) + ")");
     }
+    if (e & 1u) return fail(OMK_ERR_CAPACITY, "a tree ran out of node slots (capacity_nodes=" + std::to_string(c->cap_nodes) + ")");
+    if (e & 2u)
+        return fail(OMK_ERR_NUMERIC, "the network produced a non-finite policy or value (activation beyond the fp16 operand range "
+                                     "of the tensor-core path, |x| >= 65504, or non-finite weights)");
     return OMK_OK;
 }
 
@@ -289,7 +292,7 @@ static int32_t net_eval_common(omk_ctx *c, int n, const float *images_dev, float
     if (out_v) CK(cudaMemcpyAsync(out_v, c->ws.V, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
-    return OMK_OK;
+    return check_device_error(c);  // OMK_ERR_NUMERIC when the network produced a non-finite output
 }
 
 extern "C" int32_t omk_net_eval(omk_ctx *c, const uint8_t *boards, const uint8_t *turns, int32_t n, int32_t mode,

@@ -215,6 +215,26 @@ def test_f16_tower_is_independent_of_the_grid(omk, n):
         assert res[0][0].tobytes() == r[0].tobytes() and res[0][1].tobytes() == r[1].tobytes()
 
 
+def test_operand_overflow_is_a_loud_error(omk):
+    """The tensor-core path splits activations into fp16 halves: |x| >= 65504 cannot be represented.  Such a network must
+    fail with OMK_ERR_NUMERIC, never return garbage priors; and the context must keep working afterwards."""
+    from oracle import net_oracle
+
+    params = net_oracle.random_params(0)
+    boards, turns = random_positions(5, 77)
+    c = omk.Context(device=0, capacity_envs=1, capacity_trees=1, capacity_nodes=16, seed=0)
+    bad = [p.copy() for p in params]
+    bad[0] = bad[0] * np.float32(1e5)  # stem weights x 1e5: the residual stream leaves the fp16 range
+    c.net_load_params(bad)
+    with pytest.raises(omk.OmkError) as ei:
+        c.net_eval(boards, turns)
+    assert ei.value.code == -5
+    c.net_load_params(params)
+    p, v = c.net_eval(boards, turns)
+    assert np.isfinite(p).all() and np.allclose(p.sum(1), 1, atol=1e-4)
+    c.close()
+
+
 def test_tensor_core_kernels_are_in_the_library(omk):
     """SASS evidence: tcgen05.mma -> UTC*MMA, TMA -> UTMALDG / UBLKCP, tcgen05.ld/st -> LDTM / STTM."""
     import subprocess
