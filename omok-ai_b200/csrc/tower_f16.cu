@@ -118,7 +118,8 @@ __device__ __forceinline__ void t16_store_out(uint32_t *stage, int lane, uint32_
 }
 
 // ---- per-phase CUDA-core work, templated on the channel half so that every parameter offset is a compile-time
-//      constant-bank address (the half is warp-uniform but the compiler cannot prove it) ----
+//      constant-bank address (the half is warp-uniform but the compiler cannot prove it).  Measured: indexing by a run-time
+//      half instead shrinks the kernel from 4.9k to 3.9k SASS instructions but runs 9 % slower. ----
 // stem 1x1 conv 3 -> 128 (network.rs:65-79): this thread's pixel, its 64 channels
 template <int HALF>
 __device__ __forceinline__ void t16_stem(const Tower16Params &P, float v0, float v1, float v2, float *x) {
