@@ -329,12 +329,17 @@ static bool encode_map16(CUtensorMap *map, __half *ptr, uint64_t rows, uint32_t 
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct Fc16State {
-    CUtensorMap map0_a_hi, map0_a_lo, map0_b_hi, map0_b_lo;  // fc0 (B boxes of 128 rows: the pair kernel loads half tiles)
-    CUtensorMap map1_a_hi, map1_a_lo, map1_b_hi, map1_b_lo;  // fc1 (B boxes of 256 rows)
-    CUtensorMap map2_a_hi, map2_a_lo, map2_b_hi, map2_b_lo;  // heads (B = all 128 padded output rows)
-    __half *a_ptr = nullptr;
+struct ActMaps {  // tensor maps over one workspace's activation buffers (each search lane has its own workspace)
+    CUtensorMap map0_a_hi, map0_a_lo, map1_a_hi, map1_a_lo, map2_a_hi, map2_a_lo;
+    const __half *key[6] = {};  // the six buffers the maps were encoded for (a reallocation may reuse only some addresses)
     int a_rows = 0;
+};
+struct Fc16State {
+    CUtensorMap map0_b_hi, map0_b_lo;  // fc0 (B boxes of 128 rows: the pair kernel loads half tiles)
+    CUtensorMap map1_b_hi, map1_b_lo;  // fc1 (B boxes of 256 rows)
+    CUtensorMap map2_b_hi, map2_b_lo;  // heads (B = all 128 padded output rows)
+    ActMaps acts[2];
+    int next_victim = 0;
     bool weights_ready = false;
 };
 
@@ -383,17 +388,26 @@ bool fc16_prepare_weights(omk_ctx *c) {
     return true;
 }
 
-static bool refresh_maps16(omk_ctx *c, Fc16State *s) {
-    if (s->a_ptr == c->ws.act0_h16 && s->a_rows == c->ws.act_rows) return true;
-    if (!encode_map16(&s->map0_a_hi, c->ws.act0_h16, (uint64_t)c->ws.act_rows, F_BM, F_K0)) return false;
-    if (!encode_map16(&s->map0_a_lo, c->ws.act0_l16, (uint64_t)c->ws.act_rows, F_BM, F_K0)) return false;
-    if (!encode_map16(&s->map1_a_hi, c->ws.act1_h16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
-    if (!encode_map16(&s->map1_a_lo, c->ws.act1_l16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
-    if (!encode_map16(&s->map2_a_hi, c->ws.act2_h16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
-    if (!encode_map16(&s->map2_a_lo, c->ws.act2_l16, (uint64_t)c->ws.act_rows, F_BM, F_K1)) return false;
-    s->a_ptr = c->ws.act0_h16;
-    s->a_rows = c->ws.act_rows;
-    return true;
+static const ActMaps *refresh_maps16(omk_ctx *c, Fc16State *s) {
+    const Workspace &w = c->ws;
+    const __half *key[6] = {w.act0_h16, w.act0_l16, w.act1_h16, w.act1_l16, w.act2_h16, w.act2_l16};
+    for (ActMaps &m : s->acts) {
+        bool same = m.key[0] != nullptr && m.a_rows == w.act_rows;
+        for (int i = 0; i < 6; ++i) same = same && m.key[i] == key[i];
+        if (same) return &m;
+    }
+    ActMaps &m = s->acts[s->next_victim];
+    s->next_victim ^= 1;
+    m.key[0] = nullptr;
+    if (!encode_map16(&m.map0_a_hi, w.act0_h16, (uint64_t)w.act_rows, F_BM, F_K0)) return nullptr;
+    if (!encode_map16(&m.map0_a_lo, w.act0_l16, (uint64_t)w.act_rows, F_BM, F_K0)) return nullptr;
+    if (!encode_map16(&m.map1_a_hi, w.act1_h16, (uint64_t)w.act_rows, F_BM, F_K1)) return nullptr;
+    if (!encode_map16(&m.map1_a_lo, w.act1_l16, (uint64_t)w.act_rows, F_BM, F_K1)) return nullptr;
+    if (!encode_map16(&m.map2_a_hi, w.act2_h16, (uint64_t)w.act_rows, F_BM, F_K1)) return nullptr;
+    if (!encode_map16(&m.map2_a_lo, w.act2_l16, (uint64_t)w.act_rows, F_BM, F_K1)) return nullptr;
+    for (int i = 0; i < 6; ++i) m.key[i] = key[i];
+    m.a_rows = w.act_rows;
+    return &m;
 }
 
 static bool check_launch(const char *what) {
@@ -406,7 +420,8 @@ static bool check_launch(const char *what) {
 // fc0: act0_h16/l16 -> act1_h16/l16 (the A operand of fc1)
 bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     Fc16State *s = state16_of(c);
-    if (!s->weights_ready || !refresh_maps16(c, s)) return false;
+    const ActMaps *am = s->weights_ready ? refresh_maps16(c, s) : nullptr;
+    if (!am) return false;
     auto kern = k_fc16<F_K0, F_CHUNK0, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<true, 256>::kSmemBytes);
     const int pairs = (rows_bound + 255) / 256;
@@ -429,7 +444,7 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     const uint32_t *nreq_p = c->ws.n_req;
     float *no_p = nullptr, *no_v = nullptr;
     uint32_t *no_err = nullptr;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, s->map0_a_hi, s->map0_a_lo, s->map0_b_hi, s->map0_b_lo, bias_p, inv_p, c_f32,
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, am->map0_a_hi, am->map0_a_lo, s->map0_b_hi, s->map0_b_lo, bias_p, inv_p, c_f32,
                                              c_hi, c_lo, nreq_p, rows_bound, no_p, no_v, no_err);
     if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_fc16 pair): %s\n", cudaGetErrorString(e));
     c->launches++;
@@ -439,13 +454,14 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
 // fc1: act1_h16/l16 -> act2_h16/l16 (the A operand of the heads)
 bool launch_fc1_f16(omk_ctx *c, int rows_bound) {
     Fc16State *s = state16_of(c);
-    if (!s->weights_ready || !refresh_maps16(c, s)) return false;
+    const ActMaps *am = s->weights_ready ? refresh_maps16(c, s) : nullptr;
+    if (!am) return false;
     using Cfg = FcCfg<false, 256>;
     auto kern = k_fc16<F_K1, F_CHUNK1, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     const int mt = (rows_bound + F_BM - 1) / F_BM;
     kern<<<dim3(F_N / F_BN, mt), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
-        s->map1_a_hi, s->map1_a_lo, s->map1_b_hi, s->map1_b_lo, c->net.t[26], c->net.fc_inv_scale + 1, nullptr, c->ws.act2_h16,
+        am->map1_a_hi, am->map1_a_lo, s->map1_b_hi, s->map1_b_lo, c->net.t[26], c->net.fc_inv_scale + 1, nullptr, c->ws.act2_h16,
         c->ws.act2_l16, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr);
     c->launches++;
     return check_launch("fc1 (fp16 split)");
@@ -454,13 +470,14 @@ bool launch_fc1_f16(omk_ctx *c, int rows_bound) {
 // heads: act2_h16/l16 -> P (softmax of the 81 policy logits) and V (tanh of the value logit)
 bool launch_heads_f16(omk_ctx *c, int rows_bound) {
     Fc16State *s = state16_of(c);
-    if (!s->weights_ready || !refresh_maps16(c, s)) return false;
+    const ActMaps *am = s->weights_ready ? refresh_maps16(c, s) : nullptr;
+    if (!am) return false;
     using Cfg = FcCfg<false, 128>;
     auto kern = k_fc16<F_K1, F_CHUNK1, false, 128, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     const int mt = (rows_bound + F_BM - 1) / F_BM;
     kern<<<dim3(1, mt), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
-        s->map2_a_hi, s->map2_a_lo, s->map2_b_hi, s->map2_b_lo, c->net.heads_b, c->net.fc_inv_scale + 2, nullptr, nullptr, nullptr,
+        am->map2_a_hi, am->map2_a_lo, s->map2_b_hi, s->map2_b_lo, c->net.heads_b, c->net.fc_inv_scale + 2, nullptr, nullptr, nullptr,
         c->ws.n_req, rows_bound, c->ws.P, c->ws.V, c->dev_error);
     c->launches++;
     return check_launch("heads (fp16 split)");

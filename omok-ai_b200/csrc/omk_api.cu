@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <utility>
+
 #include "omk_internal.h"
 
 using namespace omk;
@@ -87,6 +89,56 @@ bool ensure_activations(omk_ctx *c, int rows) {
     return true;
 }
 }  // namespace omk
+
+// ------------------------------------------------------------------ search lanes
+// RAII: lane 1 = swap the context's stream and evaluator workspace with the second lane's for the launches in scope.
+struct LaneScope {
+    omk_ctx *c;
+    bool swapped;
+    LaneScope(omk_ctx *ctx, int lane, int id_base) : c(ctx), swapped(lane == 1) {
+        if (swapped) {
+            std::swap(c->stream, c->lane1_stream);
+            std::swap(c->ws, c->lane1_ws);
+        }
+        c->id_base = id_base;
+    }
+    ~LaneScope() {
+        if (swapped) {
+            std::swap(c->stream, c->lane1_stream);
+            std::swap(c->ws, c->lane1_ws);
+        }
+        c->id_base = 0;
+    }
+};
+// how many lanes a search over n trees uses; creates lane 1 on first use
+static int lanes_for(omk_ctx *c, int n) {
+    if (c->lane_min_trees <= 0 || n < c->lane_min_trees || n < 2) return 1;
+    if (!c->lane1_stream) {
+        Workspace &w = c->lane1_ws;
+        const size_t ct = (size_t)(c->cap_trees > 0 ? c->cap_trees : 1);
+        if (cudaStreamCreateWithFlags(&c->lane1_stream, cudaStreamNonBlocking) != cudaSuccess) return 1;
+        bool ok = cudaEventCreateWithFlags(&c->lane_fork, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&c->lane_join, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaMalloc(&w.n_req, sizeof(uint32_t) * 4) == cudaSuccess &&
+                  cudaMalloc(&w.slot_base, sizeof(uint32_t) * ct) == cudaSuccess &&
+                  cudaMalloc(&w.slot_count, sizeof(uint32_t) * ct) == cudaSuccess &&
+                  cudaMemsetAsync(w.n_req, 0, sizeof(uint32_t) * 4, c->lane1_stream) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            c->lane_min_trees = 0;  // no second lane on this context
+            return 1;
+        }
+    }
+    return 2;
+}
+static void lanes_fork(omk_ctx *c) {  // lane 1 starts after everything already queued on the main stream
+    cudaEventRecord(c->lane_fork, c->stream);
+    cudaStreamWaitEvent(c->lane1_stream, c->lane_fork, 0);
+}
+static void lanes_join(omk_ctx *c) {  // the main stream continues after lane 1 has drained
+    cudaEventRecord(c->lane_join, c->lane1_stream);
+    cudaStreamWaitEvent(c->stream, c->lane_join, 0);
+}
 
 static int32_t check_device_error(omk_ctx *c) {
     uint32_t e = 0;
@@ -180,6 +232,7 @@ extern "C" int32_t omk_ctx_create(int32_t device, int32_t capacity_envs, int32_t
     auto parse_mode = [](const char *m) { return strcmp(m, "simt") == 0 ? 0 : 1; };
     if (const char *m = getenv("OMK_FC0")) c->fc0_mode = parse_mode(m);
     if (const char *m = getenv("OMK_TOWER")) c->tower_mode = parse_mode(m);
+    if (const char *m = getenv("OMK_LANE_MIN_TREES")) c->lane_min_trees = atoi(m);
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -228,6 +281,16 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
                     c->net.tower16_pimg, c->net.tower16_absmax};
     fc16_free(c);
     free(c->tower16_params_host);
+    if (c->lane1_stream) {
+        cudaStreamSynchronize(c->lane1_stream);
+        Workspace &l = c->lane1_ws;
+        void *lp[] = {l.nn_in, l.req_tree, l.req_node, l.P, l.V, l.act0_h16, l.act0_l16, l.act1_h16, l.act1_l16, l.act2_h16, l.act2_l16,
+                      l.act2, l.logits, l.act0, l.act1, l.n_req, l.slot_base, l.slot_count};
+        for (void *q : lp) cudaFree(q);
+        cudaEventDestroy(c->lane_fork);
+        cudaEventDestroy(c->lane_join);
+        cudaStreamDestroy(c->lane1_stream);
+    }
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < kNetTensors; ++i) cudaFree(c->net.t[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -518,17 +581,29 @@ extern "C" int32_t omk_pool_search(omk_ctx *c, const int32_t *ids, int32_t n, in
     rc = stage_ids(c, ids, n, &d_ids, c->cap_trees);
     if (rc) return rc;
     if (n == 0 || count == 0) return OMK_OK;
-    const int rows = n * batch_size;
-    rc = ensure_workspace(c, rows);
-    if (rc) return rc;
     const int rounds = (count + batch_size - 1) / batch_size;  // parallel_mcts_executor.rs:39-42,207
-    for (int r = 0; r < rounds; ++r) {
-        if (r == 0) launch_root_noise(c, d_ids, n, epsilon, alpha);
-        launch_reset_requests(c);
-        launch_select_expand(c, d_ids, n, batch_size);
-        run_evaluator(c, evaluator, rows);
-        launch_apply(c, d_ids, n, kApplySearch);
+    // large searches run as two lanes (halves of the id list) on two streams: per-tree results do not depend on the split
+    const int lanes = lanes_for(c, n);
+    const int lane_n[2] = {lanes == 2 ? (n + 1) / 2 : n, lanes == 2 ? n / 2 : 0};
+    const int lane_first[2] = {0, lane_n[0]};
+    for (int l = 0; l < lanes; ++l) {
+        LaneScope scope(c, l, 0);
+        rc = ensure_workspace(c, lane_n[l] * batch_size);
+        if (rc) return rc;
     }
+    if (lanes == 2) lanes_fork(c);
+    for (int r = 0; r < rounds; ++r) {
+        for (int l = 0; l < lanes; ++l) {
+            LaneScope scope(c, l, lane_first[l]);
+            const int32_t *ids_l = d_ids ? d_ids + lane_first[l] : nullptr;
+            if (r == 0) launch_root_noise(c, ids_l, lane_n[l], epsilon, alpha);
+            launch_reset_requests(c);
+            launch_select_expand(c, ids_l, lane_n[l], batch_size);
+            run_evaluator(c, evaluator, lane_n[l] * batch_size);
+            launch_apply(c, ids_l, lane_n[l], kApplySearch);
+        }
+    }
+    if (lanes == 2) lanes_join(c);
     return check_device_error(c);
 }
 
@@ -748,7 +823,6 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
     if (plies < 0) return fail(OMK_ERR_INVALID, "plies < 0");
     const omk_selfplay_config &cfg = c->sp_cfg;
     const int n = cfg.n_games;
-    const int rows = n * cfg.batch_size;
     const int rounds = (cfg.count + cfg.batch_size - 1) / cfg.batch_size;
 
     const SpLayout L = sp_layout(c, n);
@@ -781,41 +855,70 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
     auto span_end = [&](bool sp) { prof_end(c, sp); };
 
     size_t d2h = 0;
+    // Two search lanes (halves of the games) when the pool is large enough: two independent kernel chains on two streams.
+    const int lanes = lanes_for(c, n);
+    const int lane_n[2] = {lanes == 2 ? (n + 1) / 2 : n, lanes == 2 ? n / 2 : 0};
+    const int lane_g0[2] = {0, lane_n[0]};
+    float *policy_out = c->ws.policy_out;
+    for (int l = 0; l < lanes; ++l) {
+        LaneScope scope(c, l, 0);
+        int32_t rc_ws = ensure_workspace(c, lane_n[l] * cfg.batch_size);
+        if (rc_ws) return rc_ws;
+    }
     CK(cudaEventRecord(c->ev0, c->stream));
+    if (lanes == 2) lanes_fork(c);
     for (int ply = 0; ply < plies; ++ply) {
-        bool sp = span_begin(OMK_K_MOVE);
-        launch_sp_prepare(c, n, mover, other, modes, temps);
-        launch_root_noise(c, mover, n, cfg.epsilon, cfg.alpha);
-        span_end(sp);
-        for (int r = 0; r < rounds; ++r) {
-            sp = span_begin(OMK_K_SELECT);
-            launch_reset_requests(c);
-            launch_select_expand(c, mover, n, cfg.batch_size);
-            span_end(sp);
-            run_evaluator(c, cfg.evaluator, rows);
-            sp = span_begin(OMK_K_APPLY);
-            launch_apply(c, mover, n, kApplySearch);
+        for (int l = 0; l < lanes; ++l) {
+            LaneScope scope(c, l, 0);
+            const int g0 = lane_g0[l], nl = lane_n[l];
+            bool sp = span_begin(OMK_K_MOVE);
+            launch_sp_prepare(c, g0, nl, mover, other, modes, temps);
+            launch_root_noise(c, mover + g0, nl, cfg.epsilon, cfg.alpha);
             span_end(sp);
         }
-        sp = span_begin(OMK_K_MOVE);
-        launch_sample(c, mover, n, modes, temps, actions, c->ws.policy_out, nullptr);
-        launch_sp_record(c, n, mover, actions, c->ws.policy_out, d_boards + (size_t)ply * n * kCells,
-                         d_policy + (size_t)ply * n * kCells, d_actions + (size_t)ply * n);
-        launch_play(c, mover, actions, n, status);
-        launch_reset_requests(c);
-        launch_ensure_prepare(c, other, actions, n);
-        span_end(sp);
-        run_evaluator(c, cfg.evaluator, n);
-        sp = span_begin(OMK_K_MOVE);
-        launch_apply(c, other, n, kApplyEnsure);
-        launch_play(c, other, actions, n, status2);
-        CK(cudaMemcpyAsync(d_status + (size_t)ply * n, status, (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
-        // finished games restart with fresh trees for both colours (cached root policy) and ply 0
-        launch_new_games(c, mover, n, nullptr, status, root_policy);
-        launch_new_games(c, other, n, nullptr, status, root_policy);
-        launch_sp_advance(c, n, status, counters);
-        span_end(sp);
+        for (int r = 0; r < rounds; ++r) {
+            for (int l = 0; l < lanes; ++l) {
+                LaneScope scope(c, l, 0);
+                const int g0 = lane_g0[l], nl = lane_n[l];
+                bool sp = span_begin(OMK_K_SELECT);
+                launch_reset_requests(c);
+                launch_select_expand(c, mover + g0, nl, cfg.batch_size);
+                span_end(sp);
+                run_evaluator(c, cfg.evaluator, nl * cfg.batch_size);
+                sp = span_begin(OMK_K_APPLY);
+                launch_apply(c, mover + g0, nl, kApplySearch);
+                span_end(sp);
+            }
+        }
+        for (int l = 0; l < lanes; ++l) {
+            LaneScope scope(c, l, 0);
+            const int g0 = lane_g0[l], nl = lane_n[l];
+            const size_t row = (size_t)ply * n + g0;
+            bool sp = span_begin(OMK_K_MOVE);
+            launch_sample(c, mover + g0, nl, modes + g0, temps + g0, actions + g0, policy_out + (size_t)g0 * kCells, nullptr);
+            launch_sp_record(c, nl, mover + g0, actions + g0, policy_out + (size_t)g0 * kCells, d_boards + row * kCells,
+                             d_policy + row * kCells, d_actions + row);
+            launch_play(c, mover + g0, actions + g0, nl, status + g0);
+            launch_reset_requests(c);
+            launch_ensure_prepare(c, other + g0, actions + g0, nl);
+            span_end(sp);
+            run_evaluator(c, cfg.evaluator, nl);
+            sp = span_begin(OMK_K_MOVE);
+            launch_apply(c, other + g0, nl, kApplyEnsure);
+            launch_play(c, other + g0, actions + g0, nl, status2 + g0);
+            CK(cudaMemcpyAsync(d_status + row, status + g0, (size_t)nl, cudaMemcpyDeviceToDevice, c->stream));
+            // finished games restart with fresh trees for both colours (cached root policy) and ply 0
+            launch_new_games(c, mover + g0, nl, nullptr, status + g0, root_policy);
+            launch_new_games(c, other + g0, nl, nullptr, status + g0, root_policy);
+            launch_sp_advance(c, g0, nl, status, counters);
+            span_end(sp);
+        }
     }
+    if (lanes == 2) {
+        LaneScope scope(c, 1, 0);
+        launch_reset_requests(c);
+    }
+    if (lanes == 2) lanes_join(c);
     launch_reset_requests(c);  // folds the last round's request count into the evaluator total
     CK(cudaEventRecord(c->ev1, c->stream));
     if (tot) {

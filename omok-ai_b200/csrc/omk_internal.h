@@ -76,6 +76,15 @@ struct omk_ctx {
     uint64_t seed = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    // Second search lane: large searches split their trees into two halves that run as two independent chains of
+    // kernels on two streams with two evaluator workspaces.  Trees never interact, so the split changes no result; the
+    // latency-bound tree kernels of one half then overlap the (tensor-bound, register-light) fc0 of the other half.
+    // `stream` / `ws` above are the lane in use: LaneScope (omk_api.cu) swaps them with these for lane 1.
+    cudaStream_t lane1_stream = nullptr;
+    omk::Workspace lane1_ws;
+    cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
+    int lane_min_trees = 512;       // searches over fewer trees stay on one lane (env OMK_LANE_MIN_TREES; 0 disables lanes)
+    int id_base = 0;                // first tree id of the lane in use when the id list is the identity
 
     omk::EnvRec *envs = nullptr;
     omk::TreeHdr *tree_hdrs = nullptr;
@@ -133,10 +142,10 @@ void launch_root_children(omk_ctx *c, int tree, int32_t *actions_dev, unsigned l
                           float *p_dev, int32_t *len_dev, float *policy_dev, uint32_t *misc_dev);
 void launch_eval_hash(omk_ctx *c, int rows_bound);
 void launch_reset_requests(omk_ctx *c);
-void launch_sp_prepare(omk_ctx *c, int n, int32_t *mover, int32_t *other, uint8_t *modes, float *temps);
+void launch_sp_prepare(omk_ctx *c, int g0, int n, int32_t *mover, int32_t *other, uint8_t *modes, float *temps);
 void launch_sp_record(omk_ctx *c, int n, const int32_t *mover, const int32_t *actions, const float *policy_in,
                       uint8_t *boards_out, float *policy_out, int32_t *actions_out);
-void launch_sp_advance(omk_ctx *c, int n, const int8_t *status, unsigned long long *counters);
+void launch_sp_advance(omk_ctx *c, int g0, int n, const int8_t *status, unsigned long long *counters);
 
 // omk_api.cu: open / close a profiling span of kernel family `kind` (no-op below min_level)
 bool prof_begin(omk_ctx *c, int kind, int min_level);

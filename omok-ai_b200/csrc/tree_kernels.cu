@@ -24,6 +24,7 @@ struct TreeArgs {
     uint8_t *nodes;
     int cap_nodes;
     const int32_t *ids;
+    int id_base;  // identity id lists (ids == nullptr) start here: a search lane owns a contiguous slice of the pool
     int n;
     uint64_t seed;
     uint32_t *dev_error;
@@ -37,7 +38,7 @@ struct TreeArgs {
     int max_rows;
 };
 
-__device__ __forceinline__ int tree_of(const TreeArgs &a, int slot) { return a.ids ? a.ids[slot] : slot; }
+__device__ __forceinline__ int tree_of(const TreeArgs &a, int slot) { return a.ids ? a.ids[slot] : slot + a.id_base; }
 __device__ __forceinline__ uint8_t *tree_nodes_of(const TreeArgs &a, int tree) {
     return a.nodes + (size_t)tree * (size_t)a.cap_nodes * kNodeBytes;
 }
@@ -873,15 +874,15 @@ __global__ void k_eval_hash(const NNIn *in, const uint32_t *n_req, float *P, flo
 
 // zero the request counter, folding the previous count into the evaluated-positions total
 __global__ void k_reset_requests(uint32_t *n_req, unsigned long long *dev_sims) {
-    dev_sims[1] += *n_req;
+    atomicAdd(&dev_sims[1], (unsigned long long)*n_req);  // two search lanes fold their counters concurrently
     *n_req = 0;
 }
 
 // ---- self-play driver glue (src/trainer.rs:86-204 restated on the device) ----
-__global__ void k_sp_prepare(int n, const int32_t *ply, int threshold, float temperature, int32_t *mover, int32_t *other,
+__global__ void k_sp_prepare(int g0, int n, const int32_t *ply, int threshold, float temperature, int32_t *mover, int32_t *other,
                              uint8_t *modes, float *temps) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n) return;
+    const int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;  // games [g0, g0 + n): one search lane's slice
+    if (g >= g0 + n) return;
     const int p = ply[g];
     mover[g] = 2 * g + (p & 1);       // black agent = tree 2g, white agent = tree 2g+1 (trainer.rs:86-94)
     other[g] = 2 * g + 1 - (p & 1);
@@ -902,9 +903,9 @@ __global__ void k_sp_record(TreeArgs a, const int32_t *actions, const float *pol
     if (threadIdx.x == 0) actions_out[g] = actions[g];
 }
 
-__global__ void k_sp_advance(int n, int32_t *ply, const int8_t *status, unsigned long long *counters) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n) return;
+__global__ void k_sp_advance(int g0, int n, int32_t *ply, const int8_t *status, unsigned long long *counters) {
+    const int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g0 + n) return;
     const int st = status[g];
     if (st == kDraw || st == kBlackWin || st == kWhiteWin) {
         ply[g] = 0;
@@ -923,6 +924,7 @@ static TreeArgs make_args(omk_ctx *c, const int32_t *ids_dev, int n) {
     a.nodes = c->tree_nodes;
     a.cap_nodes = c->cap_nodes;
     a.ids = ids_dev;
+    a.id_base = ids_dev ? 0 : c->id_base;
     a.n = n;
     a.seed = c->seed;
     a.dev_error = c->dev_error;
@@ -951,8 +953,8 @@ void launch_new_games(omk_ctx *c, const int32_t *ids_dev, int n, const uint32_t 
                                                                        only_if_terminal, root_policy);
     c->launches++;
 }
-void launch_sp_prepare(omk_ctx *c, int n, int32_t *mover, int32_t *other, uint8_t *modes, float *temps) {
-    k_sp_prepare<<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->sp_ply, c->sp_cfg.temperature_threshold,
+void launch_sp_prepare(omk_ctx *c, int g0, int n, int32_t *mover, int32_t *other, uint8_t *modes, float *temps) {
+    k_sp_prepare<<<(n + 127) / 128, 128, 0, c->stream>>>(g0, n, c->sp_ply, c->sp_cfg.temperature_threshold,
                                                           c->sp_cfg.temperature, mover, other, modes, temps);
     c->launches++;
 }
@@ -961,8 +963,8 @@ void launch_sp_record(omk_ctx *c, int n, const int32_t *mover, const int32_t *ac
     k_sp_record<<<n, 96, 0, c->stream>>>(make_args(c, mover, n), actions, policy_in, boards_out, policy_out, actions_out);
     c->launches++;
 }
-void launch_sp_advance(omk_ctx *c, int n, const int8_t *status, unsigned long long *counters) {
-    k_sp_advance<<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->sp_ply, status, counters);
+void launch_sp_advance(omk_ctx *c, int g0, int n, const int8_t *status, unsigned long long *counters) {
+    k_sp_advance<<<(n + 127) / 128, 128, 0, c->stream>>>(g0, n, c->sp_ply, status, counters);
     c->launches++;
 }
 void launch_root_noise(omk_ctx *c, const int32_t *ids_dev, int n, float epsilon, float alpha) {

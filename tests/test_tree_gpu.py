@@ -127,3 +127,43 @@ def test_reference_shaped_api(ctx, omk, orc):
     assert a.play_action(act) == omk.GameStatus.InProgress
     assert a.play_action(act) is None
     assert a.env["turn"] == omk.Turn.White
+
+
+@pytest.mark.parametrize("ids_kind", ["identity", "explicit"])
+def test_two_lane_search_matches_oracle_bit_exact(omk, orc, ids_kind):
+    """Large searches split their trees over two lanes (two streams, two evaluator workspaces, omk_api.cu LaneScope).
+    Forced here for a small pool (OMK_LANE_MIN_TREES=2): every tree must still match the oracle bit for bit, with the
+    identity id list (lane 1 starts at an id offset) and with an explicit, shuffled id list; and the self-play driver
+    must produce the same transitions with and without lanes."""
+    import os
+
+    T = 11  # odd: the lanes get 6 and 5 trees
+    ev = orc.NativeHashEvaluator()
+    os.environ["OMK_LANE_MIN_TREES"] = "2"
+    try:
+        c = omk.Context(device=0, capacity_envs=4, capacity_trees=32, capacity_nodes=2048, seed=77)
+    finally:
+        del os.environ["OMK_LANE_MIN_TREES"]
+    ids = None if ids_kind == "identity" else np.array([20, 3, 9, 14, 1, 30, 7, 8, 25, 2, 11], dtype=np.int32)
+    trees = list(range(T)) if ids is None else [int(i) for i in ids]
+    agents = [orc.Agent(ev, c.seed, t) for t in trees]  # stream == tree id
+    c.pool_new_games(ids=ids, n=T, evaluator=omk.EVAL_HASH)
+    for rnd in range(2):
+        orc.execute(agents, 96, 16, 0.25, 0.03, ev)
+        c.pool_search(ids=ids, n=T, count=96, batch_size=16, epsilon=0.25, alpha=0.03, evaluator=omk.EVAL_HASH)
+        for t, a in zip(trees, agents):
+            assert_tree_equal(c, t, a, f"round {rnd} tree {t}")
+    c.close()
+    if ids_kind == "identity":
+        out = []
+        for lanes in ("2", "0"):
+            os.environ["OMK_LANE_MIN_TREES"] = lanes
+            try:
+                c = omk.Context(device=0, capacity_envs=4, capacity_trees=2 * 9, capacity_nodes=2048, seed=5)
+            finally:
+                del os.environ["OMK_LANE_MIN_TREES"]
+            c.selfplay_begin(9, 64, 16, 0.25, 0.03, 1.0, 4, omk.EVAL_HASH)
+            stats, boards, policy, status, actions = c.selfplay_run(14, profile=0, want_transitions=True)
+            out.append((boards.tobytes(), policy.tobytes(), status.tobytes(), actions.tobytes(), int(stats.simulations), int(stats.nn_evals)))
+            c.close()
+        assert out[0] == out[1]
