@@ -178,8 +178,9 @@ def workload_config(n_gpus):
                         f"rounds of {BATCH}, eps {EPS}, alpha {ALPHA}, random-init residual policy/value net; "
                         "trainer-shaped self-play (2 trees per game, ensure_action_exists + re-root each ply)",
             "games_per_gpu": GAMES_PER_GPU, "trees_per_gpu": 2 * GAMES_PER_GPU, "sims_per_move": COUNT,
-            "nn_batch_per_tree": BATCH, "capacity_nodes": CAP_NODES, "parallelism": f"games sharded x{n_gpus}, no collective",
-            "l2": "no flush: each round streams a 680 MB fc0 input (>> 126 MB L2) and ~2.9 GB of tree records are resident"}
+            "nn_batch_per_tree": BATCH, "capacity_nodes": CAP_NODES,
+            "parallelism": f"games sharded x{n_gpus}, no collective; per GPU two search lanes (streams) of 512 games each",
+            "l2": "no flush: each network launch streams a 333 MB fc0 input (>> 126 MB L2) and ~2.9 GB of tree records are resident"}
 
 
 def main():
@@ -233,13 +234,20 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    stats, *_ = ctx.selfplay_run(steps, profile=1, want_transitions=False)
+    stats, *_ = ctx.selfplay_run(steps, profile=0, want_transitions=False)
     barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     ms = float(stats.gpu_ms)
     sims, positions, nn_evals = int(stats.simulations), int(stats.positions), int(stats.nn_evals)
-    fc0_ms, fc0_launches = stats.by_kind()["fc0"]
+    # Kernel durations for the rooflines: the timed region above runs two search lanes on two streams, where a CUDA-event
+    # span around one kernel also contains its wait for the other lane's kernels.  The SAME workload is therefore stepped
+    # on with the second lane disabled (one stream, whole 16k-row batches) and event spans around the network kernels.
+    ctx.debug_set_lane_min_trees(0)
+    ctx.selfplay_run(1, profile=0, want_transitions=False)
+    kstats, *_ = ctx.selfplay_run(max(2, steps // 2), profile=1, want_transitions=False)
+    ctx.debug_set_lane_min_trees(512)
+    fc0_ms, fc0_launches = kstats.by_kind()["fc0"]
 
     # ---- e2e arm: granular C-ABI calls with host buffers, as the Rust alpha-zero shim would issue them ----
     e2e_steps = steps
@@ -275,12 +283,12 @@ def main():
 
     if rank == 0:
         peaks = read_peaks()
-        kinds = stats.by_kind()
+        kinds = kstats.by_kind()
         tower_ms, tower_launches = kinds["tower"]
-        rows_per_launch = (int(stats.nn_evals) / max(1, fc0_launches))
+        rows_per_launch = (int(kstats.nn_evals) / max(1, fc0_launches))
         # launches also cover the (small) ensure_action batches; algorithmic flops = rows actually evaluated
-        fc0_tflops = (int(stats.nn_evals) * FLOP_FC0) / (fc0_ms * 1e-3) / 1e12 if fc0_ms > 0 else 0.0
-        tower_tflops = (int(stats.nn_evals) * FLOP_TOWER) / (tower_ms * 1e-3) / 1e12 if tower_ms > 0 else 0.0
+        fc0_tflops = (int(kstats.nn_evals) * FLOP_FC0) / (fc0_ms * 1e-3) / 1e12 if fc0_ms > 0 else 0.0
+        tower_tflops = (int(kstats.nn_evals) * FLOP_TOWER) / (tower_ms * 1e-3) / 1e12 if tower_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
         fc0_mode = os.environ.get("OMK_FC0", "f16")
         tower_mode = os.environ.get("OMK_TOWER", "f16")
@@ -300,14 +308,16 @@ def main():
                     "tensor_pipe_frac": passes.get(fc0_mode, 3) * fc0_tflops / peak,
                     "peak_source": note,
                     "avg_launch_ms": fc0_ms / max(1, fc0_launches), "rows_per_launch": rows_per_launch,
-                    "share_of_step": fc0_ms / float(stats.gpu_ms) if stats.gpu_ms else None,
+                    "share_of_step": fc0_ms / float(kstats.gpu_ms) if kstats.gpu_ms else None,
+                    "measured": "second pass of the same workload, one search lane (see bench.py)",
                     "traffic": traffic.get("k_fc16") if fc0_mode == "f16" else None}
         roof_tower = {"bound": "tensor", "kernel": tower_names.get(tower_mode, tower_mode),
                       "achieved": tower_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tower_tflops / peak,
                       "tensor_pipe_tflops": passes.get(tower_mode, 3) * tower_tflops,
                       "peak_source": note + "; this kernel is bound by its CUDA-core epilogues (issue slots), not by the tensor pipe",
                       "avg_launch_ms": tower_ms / max(1, tower_launches), "rows_per_launch": rows_per_launch,
-                      "share_of_step": tower_ms / float(stats.gpu_ms) if stats.gpu_ms else None,
+                      "share_of_step": tower_ms / float(kstats.gpu_ms) if kstats.gpu_ms else None,
+                      "measured": "second pass of the same workload, one search lane (see bench.py)",
                       "traffic": traffic.get("k_tower16") if tower_mode == "f16" else None}
         dominant, other = (roof_tower, roof_fc0) if tower_ms >= fc0_ms else (roof_fc0, roof_tower)
         line = {

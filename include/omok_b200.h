@@ -99,15 +99,20 @@ OMK_API int32_t omk_net_eval(omk_ctx *ctx, const uint8_t *boards, const uint8_t 
 OMK_API int32_t omk_net_eval_images(omk_ctx *ctx, const float *images, int32_t n, float *out_p, float *out_v);
 
 /* ---------------------------------------------------------------- diagnostics (tests / A-B runs)
- * fc0 kernel choice: 0 = fp32 CUDA-core GEMM, 1 = tcgen05 kind::tf32 with 3-pass error compensation (default;
- * env OMK_FC0=simt|tc at context creation).  omk_debug_get_buffer copies an intermediate activation buffer
- * (0 fc0 input, 1 fc0 output [CUDA-core path], 2 fc1 output, 3 head logits, 4/5 fc0 input hi/lo parts, 6/7 fc0 output hi/lo parts) to the host.        */
+ * Kernel choice for fc0 + fc1 + heads, and for the tower: 1 = the tcgen05 kernels (3-pass fp16 hi/lo split; the product
+ * path and the default), 0 = the fp32 CUDA-core kernels kept in the library as an A/B check of each layer (env
+ * OMK_FC0=simt / OMK_TOWER=simt at context creation).  omk_debug_get_buffer copies an intermediate activation buffer to
+ * the host: 8 = tower output and 9 = fc0 output of the tensor-core path (hi + lo), 0 = tower output, 1 = fc0 output,
+ * 3 = head logits of the CUDA-core path.                                                                           */
 OMK_API int32_t omk_debug_set_fc0_mode(omk_ctx *ctx, int32_t mode);
-/* tower kernel choice, same convention (env OMK_TOWER=simt|tc) */
 OMK_API int32_t omk_debug_set_tower_mode(omk_ctx *ctx, int32_t mode);
-/* clock64 phase timestamps of one position inside k_tower_tc (64 values; tools/check_tower_tc.py --timing) */
+/* clock64 phase timestamps of one iteration inside k_tower16 (64 values; tools/check_f16.py) */
 OMK_API int32_t omk_debug_tower_timing(omk_ctx *ctx, int64_t *out64);
 OMK_API int32_t omk_debug_get_buffer(omk_ctx *ctx, int32_t which, float *out, int64_t count);
+/* Searches over at least `min_trees` trees run as two lanes (two streams, halves of the trees; per-tree results are
+ * unaffected).  0 disables the second lane, e.g. to time kernels without cross-stream queueing (env OMK_LANE_MIN_TREES;
+ * default 512).                                                                                                     */
+OMK_API int32_t omk_debug_set_lane_min_trees(omk_ctx *ctx, int32_t min_trees);
 
 /* ---------------------------------------------------------------- environment
  * Replaces environment::Environment (environment/src/lib.rs:62-193), batched.   */

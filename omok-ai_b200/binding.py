@@ -105,6 +105,7 @@ def load_library():
     L.omk_net_eval_images.argtypes = [vp, vp, i32, vp, vp]
     L.omk_debug_set_fc0_mode.argtypes = [vp, i32]
     L.omk_debug_set_tower_mode.argtypes = [vp, i32]
+    L.omk_debug_set_lane_min_trees.argtypes = [vp, i32]
     L.omk_debug_get_buffer.argtypes = [vp, i32, vp, i64]
     L.omk_debug_tower_timing.argtypes = [vp, vp]
     L.omk_env_reset.argtypes = [vp, vp, i32]
@@ -220,6 +221,9 @@ class Context:
 
     def debug_set_tower_mode(self, mode: int):
         self._check(self.L.omk_debug_set_tower_mode(self.h, mode))
+
+    def debug_set_lane_min_trees(self, min_trees: int):
+        self._check(self.L.omk_debug_set_lane_min_trees(self.h, min_trees))
 
     def debug_tower_timing(self):
         out = np.zeros(64, dtype=np.int64)

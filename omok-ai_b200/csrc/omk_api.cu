@@ -406,6 +406,11 @@ extern "C" int32_t omk_debug_set_tower_mode(omk_ctx *c, int32_t mode) {
     c->tower_mode = mode;
     return OMK_OK;
 }
+extern "C" int32_t omk_debug_set_lane_min_trees(omk_ctx *c, int32_t min_trees) {
+    if (min_trees < 0) return fail(OMK_ERR_INVALID, "min_trees < 0");
+    c->lane_min_trees = min_trees;
+    return OMK_OK;
+}
 extern "C" int32_t omk_debug_tower_timing(omk_ctx *c, int64_t *out64) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));

@@ -16,6 +16,7 @@ ap.add_argument("--plies", type=int, default=2)
 ap.add_argument("--warm", type=int, default=2)
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--evaluator", default="net")
+ap.add_argument("--lanes", type=int, default=0, help="1: keep the two search lanes (kernel spans then include cross-stream queueing)")
 ap.add_argument("--env", action="store_true")
 ap.add_argument("--tree-sweep", action="store_true", help="tree-kernel bandwidth vs pool size (hash evaluator, no network)")
 args = ap.parse_args()
@@ -54,6 +55,7 @@ if args.tree_sweep:
     out = []
     for games in (1024, 4096, 16384, 32768):
         ctx = omk.Context(device=0, capacity_envs=4, capacity_trees=2 * games, capacity_nodes=768, seed=1)
+        ctx.debug_set_lane_min_trees(0)  # one stream: the spans then time the kernels alone
         ctx.selfplay_begin(games, 160, 16, 0.25, 0.03, 1.0, 30, omk.EVAL_HASH)
         ctx.selfplay_run(2, profile=0, want_transitions=False)
         stats, *_ = ctx.selfplay_run(2, profile=2, want_transitions=False)
@@ -69,6 +71,8 @@ if args.tree_sweep:
 
 ev = omk.EVAL_NET if args.evaluator == "net" else omk.EVAL_HASH
 ctx = omk.Context(device=0, capacity_envs=4, capacity_trees=2 * args.games, capacity_nodes=4096, seed=1)
+if not args.lanes:
+    ctx.debug_set_lane_min_trees(0)
 if ev == omk.EVAL_NET:
     ctx.net_init_random(0)
 ctx.selfplay_begin(args.games, 800, args.batch, 0.25, 0.03, 1.0, 30, ev)
