@@ -8,8 +8,8 @@
 // their low parts stay in fp16's normal range) and each k-step issues three tcgen05.mma kind::f16 into one
 // TMEM accumulator:    lo.hi + hi.lo + hi.hi     (the dropped lo.lo term is ~2^-22 relative).
 // Measured on the CPU (tools/emulate_split.py): priors within 9e-5 of fp64, the same as plain fp32; one-pass
-// TF32 misses the 1e-3 bar by 50x and a bf16 split by 1.2x.  Against the 3 x TF32 kernels this replaces
-// (fc0_tc.cu) every MMA carries twice the K, operand bytes halve, and the MMA count halves.
+// TF32 misses the 1e-3 bar by 50x and a bf16 split by 1.2x.  Against the 3 x TF32 kernels this replaced (git history:
+// fc0_tc.cu) every MMA carries twice the K, operand bytes halve, and the MMA count halves.
 //
 // The tensor-core accumulator truncates (measured on the TF32 path: 86 % of outputs biased toward zero), so K is
 // accumulated in TMEM only over chunks of CHUNK k-blocks; each chunk is drained into fp32 registers with

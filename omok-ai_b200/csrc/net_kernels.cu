@@ -1,4 +1,4 @@
-// net_kernels.cu -- K3: the residual policy/value network forward (fp32 path).
+// net_kernels.cu -- K3: network forward orchestration (net_forward) and the fp32 CUDA-core A/B kernels.
 //
 // Replaces AgentModel::{evaluate_p, evaluate_pv} (alpha-zero/src/agent_model.rs:105-134) for the
 // graph built by Network::new (alpha-zero/src/network.rs:51-262) from the layer builders of
@@ -7,9 +7,10 @@
 //
 // Precision: the reference's random-init recipe (2/sqrt(fan_in)) produces logits with a
 // standard deviation of ~22, so the north-star tolerance (1e-3 relative on priors/values) needs
-// fp32-class products: one-pass TF32 misses it by 50x and bf16 by 350x (DESIGN.md "Network
-// precision").  This file is the fp32 CUDA-core path; tcgen05 kind::tf32 with 3-pass error
-// compensation is the tensor-core successor for fc0.
+// fp32-class products: one-pass TF32 misses it by 50x and bf16 by 350x ("Precision").
+// The product path is the tcgen05 kernels of tower_f16.cu / fc_f16.cu (3-pass fp16 hi/lo split); the kernels
+// in this file are the first version's fp32 CUDA-core path, kept only as an in-library A/B check of each layer
+// (omk_debug_set_tower_mode / _fc0_mode = 0).  net_forward() at the bottom sequences either set.
 //
 // Kernels
 //   k_tower : one CTA walks positions; stem 1x1 (3->128), 3x bottleneck {1x1 128->32, depthwise
