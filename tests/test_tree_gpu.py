@@ -167,3 +167,48 @@ def test_two_lane_search_matches_oracle_bit_exact(omk, orc, ids_kind):
             out.append((boards.tobytes(), policy.tobytes(), status.tobytes(), actions.tobytes(), int(stats.simulations), int(stats.nn_evals)))
             c.close()
         assert out[0] == out[1]
+
+
+def test_config3_full_size_pool_properties(omk, orc):
+    """BASELINE config 3 at full size -- 1024 concurrent trees x 800 simulations per move (rounds of 16, eps 0.25,
+    alpha 0.03) -- with the exact hash evaluator, checked through properties that do not need the oracle to replay a
+    million simulations: (1) the simulation counter, (2) root.n == sum of child visits + the root's own evaluation-free
+    start, (3) compute_policy == n_child * recip(sum n) and sums to one, (4) the two-lane and the one-lane runs of the same
+    pool agree bit for bit on every tree, (5) eight trees picked at random match the oracle bit for bit."""
+    import os
+
+    T, count, batch = 1024, 800, 16
+    runs = []
+    for lanes in ("512", "0"):
+        os.environ["OMK_LANE_MIN_TREES"] = lanes
+        try:
+            c = omk.Context(device=0, capacity_envs=4, capacity_trees=T, capacity_nodes=2048, seed=31)
+        finally:
+            del os.environ["OMK_LANE_MIN_TREES"]
+        c.pool_new_games(n=T, evaluator=omk.EVAL_HASH)
+        c.selfplay_begin(1, 16, 16, 0.0, 1.0, 1.0, 30, omk.EVAL_HASH)  # only to read the simulation counter through stats
+        c.pool_new_games(n=T, evaluator=omk.EVAL_HASH)
+        c.pool_search(n=T, count=count, batch_size=batch, epsilon=0.25, alpha=0.03, evaluator=omk.EVAL_HASH)
+        pol, valid = c.pool_policy(n=T)
+        acts, _ = c.pool_sample(n=T)
+        per_tree = []
+        for t in range(T):
+            a, n, w, p = c.pool_root_children(t)
+            rn = c.pool_root_stats(t)[0]
+            per_tree.append((a.tobytes(), n.tobytes(), w.tobytes(), p.tobytes(), rn, c.pool_tree_info(t)))
+            if lanes == "512":
+                assert int(n.sum()) == rn == count, f"tree {t}: every simulation backs up through the root exactly once"
+                assert valid[t] and abs(float(pol[t].sum()) - 1.0) < 1e-5
+                # agent.rs:56-76: pi = n * recip(sum) in f32
+                assert np.array_equal(pol[t][a], n.astype(np.float32) * (np.float32(1.0) / np.float32(n.sum())))
+                assert int(acts[t]) == int(a[n == n.max()].max())  # Best: last maximum over the 81 cells (agent.rs:98-105)
+        runs.append((per_tree, pol.tobytes(), acts.tobytes()))
+        if lanes == "0":
+            ev = orc.NativeHashEvaluator()
+            rng = np.random.default_rng(0)
+            for t in rng.choice(T, size=8, replace=False):
+                agent = orc.Agent(ev, c.seed, int(t))
+                orc.execute([agent], count, batch, 0.25, 0.03, ev)
+                assert_tree_equal(c, int(t), agent, f"full-size tree {t}")
+        c.close()
+    assert runs[0] == runs[1], "two search lanes must not change any tree"
