@@ -138,7 +138,8 @@ __device__ __forceinline__ void t16_stem(const Tower16Params &P, float v0, float
 // Scalar on purpose: the packed fp32x2 forms measured 7 % slower here (operands not in aligned register pairs), while in
 // the stem / stencil / residual / split code, where pairs are natural, scalar forms measured 1-5 % slower.  A single
 // accumulator chain per conv (no partial sums to add) was also slower: conv1 +0.7 %, conv0 +14 % -- a dependent
-// tcgen05.mma costs ~175 clk, so short parallel chains matter even with a second CTA to hide behind.
+// tcgen05.mma costs ~175 clk, so short parallel chains matter even with a second CTA to hide behind.  Four chains of six
+// for conv0 (a fourth accumulator in the idle H columns) lost 8 %: one more TMEM load and add per element in E1.
 template <int HALF>
 __device__ __forceinline__ void t16_bias_lrelu16(const float *bias32, float inv, const float *d, const float *e, const float *f,
                                                  float *o) {
