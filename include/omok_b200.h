@@ -106,7 +106,7 @@ OMK_API int32_t omk_net_eval_images(omk_ctx *ctx, const float *images, int32_t n
  * 3 = head logits of the CUDA-core path.                                                                           */
 OMK_API int32_t omk_debug_set_fc0_mode(omk_ctx *ctx, int32_t mode);
 OMK_API int32_t omk_debug_set_tower_mode(omk_ctx *ctx, int32_t mode);
-/* clock64 phase timestamps of one iteration inside k_tower16 (64 values; tools/check_f16.py) */
+/* clock64 phase timestamps of one iteration inside k_tower16 (64 values; tests/tools/check_f16.py) */
 OMK_API int32_t omk_debug_tower_timing(omk_ctx *ctx, int64_t *out64);
 OMK_API int32_t omk_debug_get_buffer(omk_ctx *ctx, int32_t which, float *out, int64_t count);
 /* Searches over at least `min_trees` trees run as two lanes (two streams, halves of the trees; per-tree results are

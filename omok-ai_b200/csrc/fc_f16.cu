@@ -7,7 +7,7 @@
 // hi = fp16(x) and lo = fp16(x - hi) (22 significant bits; weights are pre-scaled by a power of two so that
 // their low parts stay in fp16's normal range) and each k-step issues three tcgen05.mma kind::f16 into one
 // TMEM accumulator:    lo.hi + hi.lo + hi.hi     (the dropped lo.lo term is ~2^-22 relative).
-// Measured on the CPU (tools/emulate_split.py): priors within 9e-5 of fp64, the same as plain fp32; one-pass
+// Measured on the CPU (tests/tools/emulate_split.py): priors within 9e-5 of fp64, the same as plain fp32; one-pass
 // TF32 misses the 1e-3 bar by 50x and a bf16 split by 1.2x.  Against the 3 x TF32 kernels this replaced (git history:
 // fc0_tc.cu) every MMA carries twice the K, operand bytes halve, and the MMA count halves.
 //

@@ -4,7 +4,7 @@ an fp64 forward when every matmul is computed as hi.hi + hi.lo + lo.hi with oper
 halves?  ("Precision".)  Uses oracle/net_oracle.py for weights and the fp64 reference; no GPU needed."""
 import sys, numpy as np, torch
 import os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import net_oracle as no
 import torch.nn.functional as F
 torch.set_num_threads(8)
