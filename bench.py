@@ -245,7 +245,7 @@ def main():
     # on with the second lane disabled (one stream, whole 16k-row batches) and event spans around the network kernels.
     ctx.debug_set_lane_min_trees(0)
     ctx.selfplay_run(1, profile=0, want_transitions=False)
-    kstats, *_ = ctx.selfplay_run(max(2, steps // 2), profile=1, want_transitions=False)
+    kstats, *_ = ctx.selfplay_run(max(2, steps // 2), profile=2, want_transitions=False)
     ctx.debug_set_lane_min_trees(512)
     fc0_ms, fc0_launches = kstats.by_kind()["fc0"]
 
@@ -319,6 +319,45 @@ def main():
                       "share_of_step": tower_ms / float(kstats.gpu_ms) if kstats.gpu_ms else None,
                       "measured": "second pass of the same workload, one search lane (see bench.py)",
                       "traffic": traffic.get("k_tower16") if tower_mode == "f16" else None}
+        # K2 tree kernels of this workload (one-lane pass) and K1 environment step (measured here, 16 Mi boards = 512 MB of
+        # records, far beyond L2) against the HBM roofline: SURVEY 8d byte models, 1672 B per simulation, 78 B per board-step
+        sel_ms, _ = kinds["select_expand"]
+        app_ms, _ = kinds["apply"]
+        tree_gbs = int(kstats.simulations) * 1672 / ((sel_ms + app_ms) * 1e-3) / 1e9 if sel_ms + app_ms > 0 else 0.0
+        roof_tree = {"bound": "hbm", "kernel": "k_select_expand + k_apply (warp per tree; 1024 searching trees per launch)",
+                     "achieved": tree_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tree_gbs / peaks["hbm_gbs"],
+                     "note": "algorithmic 1672 B/simulation; at this pool size the kernels are bound by the latency of one serial "
+                             "chain per tree (ncu: 42 % fixed-latency waits), at 65 536 trees by issue slots (78 %) with 5 % DRAM "
+                             "traffic because a round's re-reads of the root rows are L1 hits (DESIGN.md 3, profiles/r01_tree_pool_sweep.json); "
+                             "hidden behind the other search lane's fc0 in the timed region",
+                     "traffic": None}
+        roof_env = None
+        try:
+            n_env = 1 << 24
+            ectx = omk.Context(device=local_rank, capacity_envs=n_env, capacity_trees=1, capacity_nodes=16, seed=0)
+            ectx.env_reset(n=n_env)
+            acts = [torch.randint(0, 81, (n_env,), dtype=torch.uint8, device="cuda") for _ in range(8)]
+            st = torch.empty(n_env, dtype=torch.int8, device="cuda")
+            legal = torch.empty((n_env, 3), dtype=torch.int32, device="cuda")
+            es = torch.cuda.ExternalStream(ectx.stream)
+            with torch.cuda.stream(es):
+                for a in acts[:3]:
+                    ectx.env_step_device(a.data_ptr(), n_env, st.data_ptr(), legal.data_ptr())
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(es)
+                for a in acts[3:]:
+                    ectx.env_step_device(a.data_ptr(), n_env, st.data_ptr(), legal.data_ptr())
+                ev1.record(es)
+            ectx.synchronize()
+            env_ms = ev0.elapsed_time(ev1) / 5
+            env_gbs = n_env * 78 / (env_ms * 1e-3) / 1e9
+            roof_env = {"bound": "hbm", "kernel": "k_env_step (lane per board, 32-byte packed records; BASELINE configs[1] shape scaled to 16 Mi boards)",
+                        "achieved": env_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": env_gbs / peaks["hbm_gbs"],
+                        "avg_launch_ms": env_ms, "board_steps_per_s": n_env / (env_ms * 1e-3), "traffic": None}
+            ectx.close()
+            del acts, st, legal
+        except Exception as exc:  # the headline line must still print
+            roof_env = {"error": str(exc)}
         dominant, other = (roof_tower, roof_fc0) if tower_ms >= fc0_ms else (roof_fc0, roof_tower)
         line = {
             "metric": "mcts_simulations_per_sec", "value": sims / (ms * 1e-3), "unit": "simulations/s",
@@ -333,6 +372,8 @@ def main():
             "gpu_launches": launches,
             "roofline": dominant,
             "roofline_second": other,
+            "roofline_tree": roof_tree,
+            "roofline_env": roof_env,
         }
         if not args.no_cpu_baseline and world == 1:
             r = cpu_selfplay_sample(1, 0)
