@@ -52,7 +52,10 @@ struct FcCfg {
 
 // BN = 256: fc0 / fc1 tiles.  BN = 128 with HEADS: the policy/value heads (512 -> 81 | 1, padded to 128 columns): a drain
 // thread owns a whole row of logits, so tanh (value, network.rs:188-202) and softmax (policy, :227-247) finish in registers.
-template <int K, int CHUNK, bool PAIR, int BN = 256, bool HEADS = false>
+// SPLITK (small batches): blockIdx.z selects ONE chunk of CHUNK k-blocks; the CTA writes that chunk's raw fp32 partial sums
+// to C[z][128 rows][512] and k_fc0_reduce adds the chunks in order -- the same partial sums in the same order as the
+// unsplit kernel, so a row's result stays bit-identical whatever the batch size (recorded-mode parity).
+template <int K, int CHUNK, bool PAIR, int BN = 256, bool HEADS = false, bool SPLITK = false>
 __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
     k_fc16(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -62,9 +65,11 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
     using Cfg = FcCfg<PAIR, BN>;
     static_assert(!HEADS || (BN == 128 && !PAIR), "the heads epilogue needs a whole logit row per thread");
     constexpr int CG = PAIR ? 2 : 1;
-    constexpr int NKB = K / F_BK;
+    static_assert(K % F_BK == 0 && (K / F_BK) % CHUNK == 0, "chunking must tile K");
+    static_assert(!SPLITK || (!PAIR && !HEADS), "split-K is the one-CTA fc0 variant");
+    constexpr int NKB = SPLITK ? CHUNK : K / F_BK;      // k-blocks this CTA walks
     constexpr int NCHUNK = NKB / CHUNK;
-    static_assert(K % F_BK == 0 && NKB % CHUNK == 0, "chunking must tile K");
+    const int kb_base = SPLITK ? (int)blockIdx.z * CHUNK : 0;
     extern __shared__ uint8_t smem_raw[];
     const int rows = (int)min(*n_req, (uint32_t)max_rows);
     uint32_t rank = 0;
@@ -123,17 +128,17 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
                 if constexpr (PAIR) {  // both CTAs load; the transaction bytes of both land on the leader's barrier
                     const uint32_t lbar = mapa(full0 + 8 * s, 0);
                     if (leader) mbar_expect_tx(full0 + 8 * s, 2 * Cfg::kStageBytes);
-                    tma_load_2d_2sm(st, &map_a_hi, lbar, kb * F_BK, m0);
-                    tma_load_2d_2sm(st + F_A_BYTES, &map_a_lo, lbar, kb * F_BK, m0);
-                    tma_load_2d_2sm(st + 2 * F_A_BYTES, &map_b_hi, lbar, kb * F_BK, n0 + (int)rank * 128);
-                    tma_load_2d_2sm(st + 2 * F_A_BYTES + Cfg::kBBytes, &map_b_lo, lbar, kb * F_BK, n0 + (int)rank * 128);
+                    tma_load_2d_2sm(st, &map_a_hi, lbar, (kb_base + kb) * F_BK, m0);
+                    tma_load_2d_2sm(st + F_A_BYTES, &map_a_lo, lbar, (kb_base + kb) * F_BK, m0);
+                    tma_load_2d_2sm(st + 2 * F_A_BYTES, &map_b_hi, lbar, (kb_base + kb) * F_BK, n0 + (int)rank * 128);
+                    tma_load_2d_2sm(st + 2 * F_A_BYTES + Cfg::kBBytes, &map_b_lo, lbar, (kb_base + kb) * F_BK, n0 + (int)rank * 128);
                 } else {
                     const uint32_t bar = full0 + 8 * s;
                     mbar_expect_tx(bar, Cfg::kStageBytes);
-                    tma_load_2d(st, &map_a_hi, bar, kb * F_BK, m0);
-                    tma_load_2d(st + F_A_BYTES, &map_a_lo, bar, kb * F_BK, m0);
-                    tma_load_2d(st + 2 * F_A_BYTES, &map_b_hi, bar, kb * F_BK, n0);
-                    tma_load_2d(st + 2 * F_A_BYTES + Cfg::kBBytes, &map_b_lo, bar, kb * F_BK, n0);
+                    tma_load_2d(st, &map_a_hi, bar, (kb_base + kb) * F_BK, m0);
+                    tma_load_2d(st + F_A_BYTES, &map_a_lo, bar, (kb_base + kb) * F_BK, m0);
+                    tma_load_2d(st + 2 * F_A_BYTES, &map_b_hi, bar, (kb_base + kb) * F_BK, n0);
+                    tma_load_2d(st + 2 * F_A_BYTES + Cfg::kBBytes, &map_b_lo, bar, (kb_base + kb) * F_BK, n0);
                 }
             }
         }
@@ -194,7 +199,13 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
         const size_t coff = (size_t)row * F_N + n0 + half * 128;
         const float *brow = bias + n0 + half * 128;
         const float inv_scale = *inv_scale_p;  // undo the power-of-two weight scaling (exact)
-        if constexpr (HEADS) {
+        if constexpr (SPLITK) {
+            if (row < rows) {  // raw partial sums of this chunk: C[z][row in tile][512]
+                float *dst = C + ((size_t)blockIdx.z * F_BM + (size_t)(row - m0)) * F_N + n0 + half * 128;
+#pragma unroll
+                for (int j = 0; j < 128; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            }
+        } else if constexpr (HEADS) {
             if (row < rows) {
                 // logits: columns 0..80 policy, 81 value (k_pack_heads); same softmax / tanh arithmetic as k_heads
                 float mx = -INFINITY;
@@ -257,6 +268,40 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
         fence_after();
         tmem_dealloc<CG>(tmem_base, Cfg::kTmemCols);
     }
+}
+
+// split-K tail of fc0 for small batches: chunks added in order (bit-identical to the register accumulation of k_fc16),
+// then the same epilogue: * 2^-s + bias, lrelu, fp16 hi/lo split
+__global__ void k_fc0_reduce(const float *__restrict__ partial, int nchunks, const float *__restrict__ bias,
+                             const float *__restrict__ inv_scale_p, __half *__restrict__ C_hi, __half *__restrict__ C_lo,
+                             const uint32_t *n_req, int max_rows) {
+    const int rows = (int)min(*n_req, (uint32_t)max_rows);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (row, group of 8 columns)
+    const int row = idx >> 6, j = (idx & 63) * 8;
+    if (row >= rows) return;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int z = 0; z < nchunks; ++z) {
+        const float *p = partial + ((size_t)z * F_BM + row) * F_N + j;
+        const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    const float inv_scale = *inv_scale_p;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        o[i] = fmaf(acc[i], inv_scale, bias[j + i]);
+        o[i] = fmaxf(o[i], 0.2f * o[i]);
+    }
+    uint4 h, l;
+    split2_f16(o[0], o[1], h.x, l.x);
+    split2_f16(o[2], o[3], h.y, l.y);
+    split2_f16(o[4], o[5], h.z, l.z);
+    split2_f16(o[6], o[7], h.w, l.w);
+    *reinterpret_cast<uint4 *>(C_hi + (size_t)row * F_N + j) = h;
+    *reinterpret_cast<uint4 *>(C_lo + (size_t)row * F_N + j) = l;
 }
 
 // max |w| of a tensor as fp32 bits (non-negative floats order like their bit patterns)
@@ -341,6 +386,8 @@ struct Fc16State {
     ActMaps acts[2];
     int next_victim = 0;
     bool weights_ready = false;
+    CUtensorMap map0s_b_hi, map0s_b_lo;  // fc0 weights with 256-row boxes (one-CTA split-K kernel for small batches)
+    float *splitk_partial = nullptr;     // [18 chunks][128 rows][512] fp32
 };
 
 static Fc16State *state16_of(omk_ctx *c) {
@@ -349,6 +396,7 @@ static Fc16State *state16_of(omk_ctx *c) {
 }
 
 void fc16_free(omk_ctx *c) {
+    if (c->fc16_state) cudaFree(reinterpret_cast<Fc16State *>(c->fc16_state)->splitk_partial);
     delete reinterpret_cast<Fc16State *>(c->fc16_state);
     c->fc16_state = nullptr;
 }
@@ -380,6 +428,8 @@ bool fc16_prepare_weights(omk_ctx *c) {
     c->launches += 6;
     if (!encode_map16(&s->map0_b_hi, w.fc0_wt_h16, F_N, 128, F_K0)) return false;
     if (!encode_map16(&s->map0_b_lo, w.fc0_wt_l16, F_N, 128, F_K0)) return false;
+    if (!encode_map16(&s->map0s_b_hi, w.fc0_wt_h16, F_N, F_BN, F_K0)) return false;
+    if (!encode_map16(&s->map0s_b_lo, w.fc0_wt_l16, F_N, F_BN, F_K0)) return false;
     if (!encode_map16(&s->map1_b_hi, w.fc1_wt_h16, F_N, F_BN, F_K1)) return false;
     if (!encode_map16(&s->map1_b_lo, w.fc1_wt_l16, F_N, F_BN, F_K1)) return false;
     if (!encode_map16(&s->map2_b_hi, w.heads_wt_h16, 128, 128, F_K1)) return false;
@@ -422,6 +472,22 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     Fc16State *s = state16_of(c);
     const ActMaps *am = s->weights_ready ? refresh_maps16(c, s) : nullptr;
     if (!am) return false;
+    if (rows_bound <= F_BM) {
+        // Small batch (a single game's rounds of 8, Agent::new, ...): one 128-row tile would stream all of K through one
+        // CTA pair (0.18 ms); instead 2 x 18 CTAs take one chunk each and k_fc0_reduce adds the chunks in order.
+        constexpr int kChunks = F_K0 / F_BK / F_CHUNK0;
+        if (!s->splitk_partial && cudaMalloc(&s->splitk_partial, sizeof(float) * (size_t)kChunks * F_BM * F_N) != cudaSuccess) return false;
+        using Cfg = FcCfg<false, 256>;
+        auto sk = k_fc16<F_K0, F_CHUNK0, false, 256, false, true>;
+        cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        sk<<<dim3(F_N / F_BN, 1, kChunks), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+            am->map0_a_hi, am->map0_a_lo, s->map0s_b_hi, s->map0s_b_lo, c->net.t[24], c->net.fc_inv_scale, s->splitk_partial, nullptr,
+            nullptr, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr);
+        k_fc0_reduce<<<(rows_bound * 64 + 255) / 256, 256, 0, c->stream>>>(s->splitk_partial, kChunks, c->net.t[24], c->net.fc_inv_scale,
+                                                                            c->ws.act1_h16, c->ws.act1_l16, c->ws.n_req, rows_bound);
+        c->launches += 2;
+        return check_launch("fc0 (fp16 split, split-K)");
+    }
     auto kern = k_fc16<F_K0, F_CHUNK0, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<true, 256>::kSmemBytes);
     const int pairs = (rows_bound + 255) / 256;
