@@ -8,6 +8,8 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -167,6 +169,85 @@ class AgentModel {
 
   private:
     omk::Context *ctx_;
+};
+
+// alpha_zero::ModelIO::{save, load} (model_io.rs:59-120): `SavedData { variable_names: Vec<String>, parameters:
+// Vec<Vec<f32>> }` in bincode 1.3.3's default encoding (little-endian, u64 length prefixes).  As in the reference,
+// `load` matches parameters to variables by position and ignores the names; optimizer slots are not stored.
+class ModelIO {
+  public:
+    static constexpr int kTensors = 31;
+    static const int64_t *lens() {
+        static const int64_t L[kTensors] = {384, 128, 4096, 32, 288, 1024, 32, 4096, 128, 4096, 32, 288, 1024, 32, 4096, 128,
+                                           4096, 32, 288, 1024, 32, 4096, 128, 10368LL * 512, 512, 512 * 512, 512, 512, 1, 512 * 81, 81};
+        return L;
+    }
+    static std::vector<std::string> variable_names() {  // TensorFlow op names of the reference's builders (see model_io.py)
+        std::vector<std::string> n = {"conv_w", "conv_b"};
+        for (int i = 0; i < 3; ++i) {
+            const std::string r = "residual_" + std::to_string(i);
+            for (const char *s : {"_conv0_w", "_conv0_b", "_conv1_w", "_conv1_w_1", "_conv1_b", "_conv2_w", "_conv2_b"}) n.push_back(r + s);
+        }
+        for (const char *s : {"fc0_w", "fc0_b", "fc1_w", "fc1_b", "v_fc0_w", "v_fc0_b", "p_fc0_w", "p_fc0_b"}) n.push_back(s);
+        return n;
+    }
+    // read the network's variables from the context and write the checkpoint
+    static void save(omk::Context &ctx, const std::string &path) {
+        std::vector<std::vector<float>> params(kTensors);
+        float *ptrs[kTensors];
+        for (int i = 0; i < kTensors; ++i) {
+            params[i].resize((size_t)lens()[i]);
+            ptrs[i] = params[i].data();
+        }
+        omk::check(omk_net_get_params(ctx.raw(), ptrs, lens()));
+        FILE *f = std::fopen(path.c_str(), "wb");
+        if (!f) throw omk::Error(OMK_ERR_INVALID, "ModelIO::save: cannot open file");
+        auto u64 = [&](uint64_t v) { std::fwrite(&v, 8, 1, f); };  // little-endian hosts only (x86-64 / aarch64)
+        const auto names = variable_names();
+        u64(names.size());
+        for (const auto &n : names) {
+            u64(n.size());
+            std::fwrite(n.data(), 1, n.size(), f);
+        }
+        u64(kTensors);
+        for (const auto &p : params) {
+            u64(p.size());
+            std::fwrite(p.data(), 4, p.size(), f);
+        }
+        std::fclose(f);
+    }
+    // read a checkpoint and install it as the context's network
+    static void load(omk::Context &ctx, const std::string &path) {
+        FILE *f = std::fopen(path.c_str(), "rb");
+        if (!f) throw omk::Error(OMK_ERR_INVALID, "ModelIO::load: cannot open file");
+        auto fail = [&](const char *m) {
+            std::fclose(f);
+            throw omk::Error(OMK_ERR_INVALID, m);
+        };
+        auto u64 = [&]() {
+            uint64_t v = 0;
+            if (std::fread(&v, 8, 1, f) != 1) fail("ModelIO::load: unexpected end of file");
+            return v;
+        };
+        const uint64_t n_names = u64();
+        for (uint64_t i = 0; i < n_names; ++i) {
+            const uint64_t len = u64();
+            if (len > 4096 || std::fseek(f, (long)len, SEEK_CUR) != 0) fail("ModelIO::load: bad variable name");
+        }
+        const uint64_t n_params = u64();
+        if (n_params < (uint64_t)kTensors) fail("ModelIO::load: fewer parameters than network variables");
+        std::vector<std::vector<float>> params(kTensors);
+        const float *ptrs[kTensors];
+        for (int i = 0; i < kTensors; ++i) {
+            const uint64_t len = u64();
+            if (len != (uint64_t)lens()[i]) fail("ModelIO::load: parameter length does not fit its variable");
+            params[i].resize((size_t)len);
+            if (std::fread(params[i].data(), 4, (size_t)len, f) != len) fail("ModelIO::load: unexpected end of file");
+            ptrs[i] = params[i].data();
+        }
+        std::fclose(f);
+        omk::check(omk_net_load_params(ctx.raw(), ptrs, lens()));
+    }
 };
 
 // alpha_zero::Agent (agent.rs:10-232): environment + search tree on one tree slot

@@ -81,6 +81,22 @@ int main(int argc, char **argv) {
         auto in = alpha_zero::encode_nn_input(ctx, alpha_zero::EnvTurnMode::Player, {});
         REQUIRE(in.empty());
     }
+    {  // ModelIO round trip: save -> random re-init -> load restores the network's outputs bit for bit
+        alpha_zero::AgentModel model(ctx, 3);
+        std::vector<float> img(243, 0.0f);
+        img[0] = img[21] = 1.0f;
+        for (int i = 162; i < 243; ++i) img[i] = 1.0f;
+        const auto before = model.evaluate_pv(img);
+        const char *path = argc > 2 ? argv[2] : "/tmp/omok_b200_cpp_ckpt";
+        alpha_zero::ModelIO::save(ctx, path);
+        alpha_zero::AgentModel other(ctx, 4);
+        const auto changed = other.evaluate_pv(img);
+        REQUIRE(changed.first != before.first);
+        alpha_zero::ModelIO::load(ctx, path);
+        const auto after = model.evaluate_pv(img);
+        REQUIRE(after.first == before.first && after.second == before.second);
+        REQUIRE(alpha_zero::ModelIO::variable_names().size() == 31);
+    }
     std::printf("cpp host mirror ok\n");
     return 0;
 }

@@ -26,5 +26,14 @@ def test_cpp_mirror_compiles_and_links(omk):
 @pytest.mark.gpu
 def test_cpp_mirror_runs_reference_tests(omk):
     build(omk)
-    out = subprocess.run([EXE, "--run"], capture_output=True, text=True, timeout=120)
+    import importlib
+    import tempfile
+
+    ckpt = os.path.join(tempfile.mkdtemp(), "alpha-zero")
+    out = subprocess.run([EXE, "--run", ckpt], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "cpp host mirror ok" in out.stdout, out.stdout + out.stderr
+    # the checkpoint the C++ mirror wrote is the same bincode image the Python mirror reads and writes
+    model_io = importlib.import_module("omok-ai_b200.model_io")
+    names, params = model_io.load(ckpt)
+    assert names == model_io.VARIABLE_NAMES and len(params) == 31
+    assert model_io.dumps(params) == open(ckpt, "rb").read()
