@@ -179,6 +179,8 @@ __host__ __device__ inline float f16_split_scale(uint32_t absmax_bits) {
 }
 
 // ---- fp16 hi/lo split: x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits ----
+// (Measured alternatives: scalar subtraction instead of the packed FMA +1 %; hi by masking the 13 low mantissa bits on the
+// integer pipe -0.5 % time but one bit less accuracy -- not taken.)
 // two values -> one packed hi word and one packed lo word (element 0 in the low half: the k-order the MMA expects)
 __device__ __forceinline__ void split2_f16(float a, float b, uint32_t &hi, uint32_t &lo) {
     const __half2 h = __floats2half2_rn(a, b);
