@@ -358,6 +358,15 @@ def main():
             del acts, st, legal
         except Exception as exc:  # the headline line must still print
             roof_env = {"error": str(exc)}
+        # the whole network (tower + fc0 + fc1 + heads) against the tensor pipe: algorithmic flops and the 3-pass MMA rate
+        net_ms = sum(kinds[k][0] for k in ("tower", "fc0", "fc1", "heads"))
+        net_tflops = int(kstats.nn_evals) * FLOP_POSITION / (net_ms * 1e-3) / 1e12 if net_ms > 0 else 0.0
+        roof_net = {"bound": "tensor", "kernel": "whole network forward: k_tower16 + k_fc16 (fc0, fc1, heads)",
+                    "achieved": net_tflops, "peak": peak, "unit": "TFLOP/s", "frac": net_tflops / peak,
+                    "tensor_pipe_tflops": 3 * net_tflops, "tensor_pipe_frac": 3 * net_tflops / peak,
+                    "evals_per_s": int(kstats.nn_evals) / (net_ms * 1e-3) if net_ms > 0 else 0.0,
+                    "note": "15 906 240 flop per position; every product is three fp16 MMAs (hi.hi + hi.lo + lo.hi), so "
+                            "tensor_pipe_* is what the tensor cores execute; one-lane pass"}
         dominant, other = (roof_tower, roof_fc0) if tower_ms >= fc0_ms else (roof_fc0, roof_tower)
         line = {
             "metric": "mcts_simulations_per_sec", "value": sims / (ms * 1e-3), "unit": "simulations/s",
@@ -372,6 +381,7 @@ def main():
             "gpu_launches": launches,
             "roofline": dominant,
             "roofline_second": other,
+            "roofline_network": roof_net,
             "roofline_tree": roof_tree,
             "roofline_env": roof_env,
         }
