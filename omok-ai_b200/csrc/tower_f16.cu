@@ -71,7 +71,12 @@ static_assert(W16_BYTES == 8 * 32 * T16_HSTRIDE * 4, "the idle weight buffer dou
 static_assert(S16_BAR % 8 == 0, "mbarriers are 8-byte aligned");
 
 __device__ long long g_t16_dbg[64];  // phase timestamps of CTA 0's second iteration (omk_debug_tower_timing)
-#define T16_STAMP(i) do { if (dbg_on && t == 0) g_t16_dbg[(i)] = clock64(); } while (0)
+// Phase timestamps exist only in the STAMPS instantiation (env OMK_TOWER_STAMPS=1, tests/tools/check_f16.py): even
+// predicated off, the 25 clock reads + stores cost 4 % of the kernel.
+#define T16_STAMP(i) do { if constexpr (STAMPS) { if (dbg_on && t == 0) g_t16_dbg[(i)] = clock64(); } } while (0)
+// Wait for one of the CTA's mbarriers.  ONE warp polls it, the others block on the CTA barrier (no issue slots): with all
+// eight warps polling, try_wait + branch pairs were 10 % of the kernel's issued instructions.
+#define T16_WAIT(bar, parity) do { if (warp == 7) mbar_wait((bar), (parity)); __syncthreads(); } while (0)
 __device__ __forceinline__ float t16_lrelu(float v) { return fmaxf(v, 0.2f * v); }  // alpha < 1: max(v, alpha v)
 
 // split 16 fp32 values (one 16-channel group) into 8 packed hi words + 8 packed lo words and store them as A-operand columns
@@ -196,6 +201,7 @@ __device__ __forceinline__ uint32_t t16_image_bit(const NNIn &in, int f) {
 }
 #define T16_HALF(call_0, call_1) do { if (half == 0) { call_0; } else { call_1; } } while (0)
 
+template <bool STAMPS>
 __global__ void __launch_bounds__(T16_THREADS, 2)
     k_tower16(const uint8_t *__restrict__ wimg, const __grid_constant__ Tower16Params P, const NNIn *__restrict__ nn_in,
               const float *__restrict__ images, const uint32_t *n_req, int max_rows, __half *__restrict__ act_hi,
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     if (!images) cur = nn_in[min(pair * 3 + j, rows - 1)];
     int pos_iter = 0;
     for (int tr = pair; tr < n_triples; tr += n_pairs, ++pos_iter) {
-        const bool dbg_on = blockIdx.x == 0 && pos_iter == 1;
+        [[maybe_unused]] const bool dbg_on = blockIdx.x == 0 && pos_iter == 1;
         const int row = tr * 3 + j;                  // this thread's position (global row of the batch)
         const bool real = in_tile && row < rows;     // 13 padding lanes per pair; the last triple may be partial
         T16_STAMP(0);
@@ -350,9 +356,8 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                 }
                 umma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, mma_uses & 1u);
+            T16_WAIT(bar_mma, mma_uses & 1u);
             ++mma_uses;
-            __syncwarp();
             fence_after();
             T16_STAMP(2 + r * 8 + 0);
             // epilogue 1: + b0, lrelu -> fp32 tile for the depthwise stencil (this thread: 16 channels of its pixel)
@@ -377,8 +382,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                                      ::"r"(ra + c * 4), "f"(o[c]), "f"(o[c + 1]), "f"(o[c + 2]), "f"(o[c + 3]), "r"(peer_band) : "memory");
                 }
             }
-            __syncthreads();                 // this CTA's rows are in the tile
-            mbar_wait(bar_band, g & 1u);     // ... and so is the band mirrored by the peer
+            T16_WAIT(bar_band, g & 1u);      // the band mirrored by the peer has arrived, and (CTA barrier) this CTA's rows are in the tile
             T16_STAMP(2 + r * 8 + 1);
             // conv1 depthwise 3x3 -> A operand of the pointwise conv
             {
@@ -409,9 +413,8 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                 }
                 umma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, mma_uses & 1u);
+            T16_WAIT(bar_mma, mma_uses & 1u);
             ++mma_uses;
-            __syncwarp();
             fence_after();
             T16_STAMP(2 + r * 8 + 3);
             {   // epilogue 2: + b1, lrelu -> A operand of conv2
@@ -442,9 +445,8 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                 }
                 umma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, mma_uses & 1u);
+            T16_WAIT(bar_mma, mma_uses & 1u);
             ++mma_uses;
-            __syncwarp();
             fence_after();
             T16_STAMP(2 + r * 8 + 5);
             // epilogue 3: x = lrelu(conv2 + b2 + x); the next block's A operand is written in place over D3
@@ -596,12 +598,12 @@ static int tower16_max_pairs(omk_ctx *c) {
     // n_sms pairs instead of n_sms / 2), so the grid is sized from the SM count; surplus CTAs would simply queue.
     int n = c->n_sms;
     int api = 0;
-    if (cudaOccupancyMaxActiveClusters(&api, k_tower16, &cfg) != cudaSuccess) cudaGetLastError();
+    if (cudaOccupancyMaxActiveClusters(&api, k_tower16<false>, &cfg) != cudaSuccess) cudaGetLastError();
     if (getenv("OMK_DEBUG")) {
         int per_sm = -1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tower16, T16_THREADS, T16_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tower16<false>, T16_THREADS, T16_SMEM_BYTES);
         cudaFuncAttributes fa{};
-        cudaFuncGetAttributes(&fa, k_tower16);
+        cudaFuncGetAttributes(&fa, k_tower16<false>);
         fprintf(stderr, "omok_b200: k_tower16 CTA pairs: %d (%d SMs); occupancy API: %d clusters, %d blocks/SM; regs %d, static smem %zu, max dyn smem %d, carveout %d\n",
                 n, c->n_sms, api, per_sm, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
     }
@@ -611,9 +613,11 @@ static int tower16_max_pairs(omk_ctx *c) {
 }
 
 bool launch_tower_f16(omk_ctx *c, const float *images_dev, int rows_bound) {
-    cudaFuncSetAttribute(k_tower16, cudaFuncAttributeMaxDynamicSharedMemorySize, T16_SMEM_BYTES);
+    static const bool stamps = getenv("OMK_TOWER_STAMPS") && atoi(getenv("OMK_TOWER_STAMPS")) != 0;
+    auto kern = stamps ? k_tower16<true> : k_tower16<false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T16_SMEM_BYTES);
     // two 107 KB CTAs per SM need the full shared-memory carve-out; the default heuristic sizes it for one block
-    cudaFuncSetAttribute(k_tower16, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     const int triples = (rows_bound + 2) / 3;
     const int max_pairs = tower16_max_pairs(c);
     const int pairs = triples < max_pairs ? triples : max_pairs;
@@ -635,7 +639,7 @@ bool launch_tower_f16(omk_ctx *c, const float *images_dev, int rows_bound) {
     const NNIn *nn_in = c->ws.nn_in;
     const uint32_t *n_req = c->ws.n_req;
     __half *ah = c->ws.act0_h16, *al = c->ws.act0_l16;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower16, wimg, params, nn_in, images_dev, n_req, rows_bound, ah, al);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, wimg, params, nn_in, images_dev, n_req, rows_bound, ah, al);
     if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_tower16): %s\n", cudaGetErrorString(e));
     c->launches++;
     return e == cudaSuccess;

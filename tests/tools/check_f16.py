@@ -8,6 +8,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+os.environ.setdefault("OMK_TOWER_STAMPS", "1")  # the instrumented instantiation of k_tower16 (phase timestamps)
 omk = importlib.import_module("omok-ai_b200")
 from oracle import net_oracle  # noqa: E402
 
