@@ -41,7 +41,7 @@ for rep in reports:
         rows_out.append(rec)
         rd = float(r[col["dram__bytes_read.sum"]]) * UNIT_BYTES[units[col["dram__bytes_read.sum"]]]
         wr = float(r[col["dram__bytes_write.sum"]]) * UNIT_BYTES[units[col["dram__bytes_write.sum"]]]
-        key = short + ("_heads" if ", 128, 1>" in name else "_fc1" if "<512" in name else "")
+        key = short + ("_heads" if ", 128, 1" in name else "_fc1" if "<512" in name else "")
         traffic.setdefault(key, []).append(rd + wr)
 keys = []
 for rec in rows_out:
