@@ -36,6 +36,7 @@ constexpr int F_K0 = 10368, F_K1 = 512;
 constexpr int F_A_BYTES = F_BM * F_BK * 2;        // 16 KB
 constexpr int F_CHUNK0 = 9;                       // fc0: 162 k-blocks = 18 x 9
 constexpr int F_CHUNK1 = 8;                       // fc1: 8 k-blocks = 1 x 8
+constexpr int kSplitKMaxRows = 4096;              // fc0 batches up to here take the split-K path (36 CTAs per 128 rows)
 
 template <bool PAIR, int BN>
 struct FcCfg {
@@ -53,7 +54,7 @@ struct FcCfg {
 // BN = 256: fc0 / fc1 tiles.  BN = 128 with HEADS: the policy/value heads (512 -> 81 | 1, padded to 128 columns): a drain
 // thread owns a whole row of logits, so tanh (value, network.rs:188-202) and softmax (policy, :227-247) finish in registers.
 // SPLITK (small batches): blockIdx.z selects ONE chunk of CHUNK k-blocks; the CTA writes that chunk's raw fp32 partial sums
-// to C[z][128 rows][512] and k_fc0_reduce adds the chunks in order -- the same partial sums in the same order as the
+// to C[z][gridDim.y * 128 rows][512] and k_fc0_reduce adds the chunks in order -- the same partial sums in the same order as the
 // unsplit kernel, so a row's result stays bit-identical whatever the batch size (recorded-mode parity).
 template <int K, int CHUNK, bool PAIR, int BN = 256, bool HEADS = false, bool SPLITK = false>
 __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
         const float inv_scale = *inv_scale_p;  // undo the power-of-two weight scaling (exact)
         if constexpr (SPLITK) {
             if (row < rows) {  // raw partial sums of this chunk: C[z][row in tile][512]
-                float *dst = C + ((size_t)blockIdx.z * F_BM + (size_t)(row - m0)) * F_N + n0 + half * 128;
+                float *dst = C + ((size_t)blockIdx.z * ((size_t)gridDim.y * F_BM) + (size_t)row) * F_N + n0 + half * 128;
 #pragma unroll
                 for (int j = 0; j < 128; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
             }
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
 
 // split-K tail of fc0 for small batches: chunks added in order (bit-identical to the register accumulation of k_fc16),
 // then the same epilogue: * 2^-s + bias, lrelu, fp16 hi/lo split
-__global__ void k_fc0_reduce(const float *__restrict__ partial, int nchunks, const float *__restrict__ bias,
+__global__ void k_fc0_reduce(const float *__restrict__ partial, int nchunks, int ws_rows, const float *__restrict__ bias,
                              const float *__restrict__ inv_scale_p, __half *__restrict__ C_hi, __half *__restrict__ C_lo,
                              const uint32_t *n_req, int max_rows) {
     const int rows = (int)min(*n_req, (uint32_t)max_rows);
@@ -283,7 +284,7 @@ __global__ void k_fc0_reduce(const float *__restrict__ partial, int nchunks, con
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
     for (int z = 0; z < nchunks; ++z) {
-        const float *p = partial + ((size_t)z * F_BM + row) * F_N + j;
+        const float *p = partial + ((size_t)z * ws_rows + row) * F_N + j;
         const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
         acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
         acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
@@ -378,6 +379,8 @@ struct ActMaps {  // tensor maps over one workspace's activation buffers (each s
     CUtensorMap map0_a_hi, map0_a_lo, map1_a_hi, map1_a_lo, map2_a_hi, map2_a_lo;
     const __half *key[6] = {};  // the six buffers the maps were encoded for (a reallocation may reuse only some addresses)
     int a_rows = 0;
+    float *splitk_partial = nullptr;  // [18 chunks][splitk_rows][512] fp32 partial sums of this workspace's split-K fc0
+    int splitk_rows = 0;
 };
 struct Fc16State {
     CUtensorMap map0_b_hi, map0_b_lo;  // fc0 (B boxes of 128 rows: the pair kernel loads half tiles)
@@ -387,7 +390,6 @@ struct Fc16State {
     int next_victim = 0;
     bool weights_ready = false;
     CUtensorMap map0s_b_hi, map0s_b_lo;  // fc0 weights with 256-row boxes (one-CTA split-K kernel for small batches)
-    float *splitk_partial = nullptr;     // [18 chunks][128 rows][512] fp32
 };
 
 static Fc16State *state16_of(omk_ctx *c) {
@@ -396,7 +398,8 @@ static Fc16State *state16_of(omk_ctx *c) {
 }
 
 void fc16_free(omk_ctx *c) {
-    if (c->fc16_state) cudaFree(reinterpret_cast<Fc16State *>(c->fc16_state)->splitk_partial);
+    if (c->fc16_state)
+        for (ActMaps &m : reinterpret_cast<Fc16State *>(c->fc16_state)->acts) cudaFree(m.splitk_partial);
     delete reinterpret_cast<Fc16State *>(c->fc16_state);
     c->fc16_state = nullptr;
 }
@@ -438,7 +441,7 @@ bool fc16_prepare_weights(omk_ctx *c) {
     return true;
 }
 
-static const ActMaps *refresh_maps16(omk_ctx *c, Fc16State *s) {
+static ActMaps *refresh_maps16(omk_ctx *c, Fc16State *s) {
     const Workspace &w = c->ws;
     const __half *key[6] = {w.act0_h16, w.act0_l16, w.act1_h16, w.act1_l16, w.act2_h16, w.act2_l16};
     for (ActMaps &m : s->acts) {
@@ -470,21 +473,30 @@ static bool check_launch(const char *what) {
 // fc0: act0_h16/l16 -> act1_h16/l16 (the A operand of fc1)
 bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     Fc16State *s = state16_of(c);
-    const ActMaps *am = s->weights_ready ? refresh_maps16(c, s) : nullptr;
+    ActMaps *am = s->weights_ready ? refresh_maps16(c, s) : nullptr;
     if (!am) return false;
-    if (rows_bound <= F_BM) {
-        // Small batch (a single game's rounds of 8, Agent::new, ...): one 128-row tile would stream all of K through one
-        // CTA pair (0.18 ms); instead 2 x 18 CTAs take one chunk each and k_fc0_reduce adds the chunks in order.
+    if (rows_bound <= kSplitKMaxRows) {
+        // Small and medium batches (a single game's rounds of 8, Agent::new, an arena of 100 games, ...): the pair kernel
+        // would stream all of K through a handful of CTA pairs (0.18 ms however few tiles there are); instead every
+        // (128-row tile, N half, chunk) is one CTA and k_fc0_reduce adds the chunks in order.
         constexpr int kChunks = F_K0 / F_BK / F_CHUNK0;
-        if (!s->splitk_partial && cudaMalloc(&s->splitk_partial, sizeof(float) * (size_t)kChunks * F_BM * F_N) != cudaSuccess) return false;
+        const int mt = (rows_bound + F_BM - 1) / F_BM, ws_rows = mt * F_BM;
+        if (am->splitk_rows < ws_rows) {  // per workspace: two search lanes may run this path at the same time
+            cudaFree(am->splitk_partial);
+            am->splitk_partial = nullptr;
+            am->splitk_rows = 0;
+            if (cudaMalloc(&am->splitk_partial, sizeof(float) * (size_t)kChunks * ws_rows * F_N) != cudaSuccess) return false;
+            am->splitk_rows = ws_rows;
+        }
         using Cfg = FcCfg<false, 256>;
         auto sk = k_fc16<F_K0, F_CHUNK0, false, 256, false, true>;
         cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-        sk<<<dim3(F_N / F_BN, 1, kChunks), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
-            am->map0_a_hi, am->map0_a_lo, s->map0s_b_hi, s->map0s_b_lo, c->net.t[24], c->net.fc_inv_scale, s->splitk_partial, nullptr,
+        sk<<<dim3(F_N / F_BN, mt, kChunks), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+            am->map0_a_hi, am->map0_a_lo, s->map0s_b_hi, s->map0s_b_lo, c->net.t[24], c->net.fc_inv_scale, am->splitk_partial, nullptr,
             nullptr, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr);
-        k_fc0_reduce<<<(rows_bound * 64 + 255) / 256, 256, 0, c->stream>>>(s->splitk_partial, kChunks, c->net.t[24], c->net.fc_inv_scale,
-                                                                            c->ws.act1_h16, c->ws.act1_l16, c->ws.n_req, rows_bound);
+        k_fc0_reduce<<<(rows_bound * 64 + 255) / 256, 256, 0, c->stream>>>(am->splitk_partial, kChunks, ws_rows, c->net.t[24],
+                                                                            c->net.fc_inv_scale, c->ws.act1_h16, c->ws.act1_l16,
+                                                                            c->ws.n_req, rows_bound);
         c->launches += 2;
         return check_launch("fc0 (fp16 split, split-K)");
     }
