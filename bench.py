@@ -246,7 +246,7 @@ def main():
     ctx.debug_set_lane_min_trees(0)
     ctx.selfplay_run(1, profile=0, want_transitions=False)
     kstats, *_ = ctx.selfplay_run(max(2, steps // 2), profile=2, want_transitions=False)
-    ctx.debug_set_lane_min_trees(512)
+    ctx.debug_set_lane_min_trees(768)
     fc0_ms, fc0_launches = kstats.by_kind()["fc0"]
 
     # ---- e2e arm: granular C-ABI calls with host buffers, as the Rust alpha-zero shim would issue them ----

@@ -21,6 +21,7 @@
 // PAIR = false (fc1): one CTA per 128 x 256 tile, 2-stage ring of 96 KB stages.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = drain / epilogue (two per lane quadrant).
 #include <cstdio>
+#include <cstdlib>
 #include <cuda.h>
 
 #include "omk_internal.h"
@@ -36,7 +37,7 @@ constexpr int F_K0 = 10368, F_K1 = 512;
 constexpr int F_A_BYTES = F_BM * F_BK * 2;        // 16 KB
 constexpr int F_CHUNK0 = 9;                       // fc0: 162 k-blocks = 18 x 9
 constexpr int F_CHUNK1 = 8;                       // fc1: 8 k-blocks = 1 x 8
-constexpr int kSplitKMaxRows = 4096;              // fc0 batches up to here take the split-K path (36 CTAs per 128 rows)
+constexpr int kSplitKMaxRows = 2048;              // fc0 batches up to here take the split-K path (36 CTAs per 128 rows): 95 vs 152 us at 2048 rows, 181 vs 158 us at 4096
 
 template <bool PAIR, int BN>
 struct FcCfg {
@@ -475,7 +476,8 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     Fc16State *s = state16_of(c);
     ActMaps *am = s->weights_ready ? refresh_maps16(c, s) : nullptr;
     if (!am) return false;
-    if (rows_bound <= kSplitKMaxRows) {
+    static const int splitk_max = getenv("OMK_FC0_SPLITK_MAX") ? atoi(getenv("OMK_FC0_SPLITK_MAX")) : kSplitKMaxRows;
+    if (rows_bound <= splitk_max) {
         // Small and medium batches (a single game's rounds of 8, Agent::new, an arena of 100 games, ...): the pair kernel
         // would stream all of K through a handful of CTA pairs (0.18 ms however few tiles there are); instead every
         // (128-row tile, N half, chunk) is one CTA and k_fc0_reduce adds the chunks in order.

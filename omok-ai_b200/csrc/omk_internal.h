@@ -83,7 +83,7 @@ struct omk_ctx {
     cudaStream_t lane1_stream = nullptr;
     omk::Workspace lane1_ws;
     cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
-    int lane_min_trees = 512;       // searches over fewer trees stay on one lane (env OMK_LANE_MIN_TREES; 0 disables lanes)
+    int lane_min_trees = 768;       // searches over fewer trees stay on one lane: each lane should still fill an fc0 wave (env OMK_LANE_MIN_TREES; 0 disables lanes)
     int id_base = 0;                // first tree id of the lane in use when the id list is the identity
 
     omk::EnvRec *envs = nullptr;

@@ -75,7 +75,7 @@ def test_batch_invariance(net):
     for lo, hi in ((0, 1), (17, 18), (5, 133), (299, 300)):
         q, w = ctx.net_eval(boards[lo:hi], turns[lo:hi])
         assert q.tobytes() == p[lo:hi].tobytes() and w.tobytes() == v[lo:hi].tobytes()
-    # across the two fc0 paths: batches of <= 4096 rows take the split-K kernel (chunks reduced in order), larger ones the
+    # across the two fc0 paths: batches of <= 2048 rows take the split-K kernel (chunks reduced in order), larger ones the
     # CTA-pair kernel (chunks accumulated in registers); the sums are the same sums in the same order
     big_b, big_t = random_positions(4500, 33)
     P, V = ctx.net_eval(big_b, big_t)

@@ -179,7 +179,7 @@ def test_config3_full_size_pool_properties(omk, orc):
 
     T, count, batch = 1024, 800, 16
     runs = []
-    for lanes in ("512", "0"):
+    for lanes in ("512", "0"):  # 1024 searching trees: two lanes of 512 / one lane
         os.environ["OMK_LANE_MIN_TREES"] = lanes
         try:
             c = omk.Context(device=0, capacity_envs=4, capacity_trees=T, capacity_nodes=2048, seed=31)
