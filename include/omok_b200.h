@@ -111,7 +111,7 @@ OMK_API int32_t omk_debug_tower_timing(omk_ctx *ctx, int64_t *out64);
 OMK_API int32_t omk_debug_get_buffer(omk_ctx *ctx, int32_t which, float *out, int64_t count);
 /* Searches over at least `min_trees` trees run as two lanes (two streams, halves of the trees; per-tree results are
  * unaffected).  0 disables the second lane, e.g. to time kernels without cross-stream queueing (env OMK_LANE_MIN_TREES;
-  * default 768).                                                                                                     */
+ * default 768).                                                                                                     */
 OMK_API int32_t omk_debug_set_lane_min_trees(omk_ctx *ctx, int32_t min_trees);
 
 /* ---------------------------------------------------------------- environment
