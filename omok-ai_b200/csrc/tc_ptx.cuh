@@ -24,6 +24,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// the same without the release fence (MEMBAR.ALL.GPU + ERRBAR in SASS): for "I have finished READING" signals, where every
+// load the peer must not overtake has already returned its value (consumed before the CTA barrier that precedes the arrive)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 // spin on the phase parity; a bounded spin turns a pipeline bug into a trap instead of a hung GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -38,6 +43,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (done) return;
     }
     __trap();
+}
+
+// one thread of a converged warp (elect.sync): the single-thread tcgen05 / TMA issue paths branch on it
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ uint32_t cluster_rank() {

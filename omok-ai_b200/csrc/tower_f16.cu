@@ -18,12 +18,12 @@
 //   * a CTA needs 256 TMEM columns, 107 KB of shared memory and <= 128 registers per thread, so TWO CTAs are
 //     resident per SM: one CTA's MMA / barrier latencies hide behind the other's CUDA-core epilogues (the 3 x TF32
 //     kernel this replaces needed all 512 columns and ran one 8-warp CTA per SM, every phase exposed).
-// Warp w works on TMEM lane quadrant w%4 and channel half w/4.  Lane 0 of warps 0..2 issues the MMA chains.
+// Warp w works on TMEM lane quadrant w%4 and channel half w/4.  The elected thread of warp 0 issues the MMA chains.
 //
 // TMEM columns: X/D3 [0,128)  16-channel group kk of x: hi [16kk,16kk+8) lo [16kk+8,16kk+16); the conv2 accumulator
 //                             D3 (fp32, 128 columns) aliases it: x's TMEM copy is dead once conv0 has read it
 //               H    [128,160) 16-channel group g of the block's hidden activations, same hi/lo packing
-//               ACC  [160,256) three 32-column partial accumulators (one per product) of conv0 / conv1
+//               ACC  [160,192) the conv0 / conv1 accumulator (fp32, 32 columns); [192,256) unused (allocations are powers of two)
 #include <cstdio>
 #include <cstdlib>
 
@@ -139,21 +139,25 @@ __device__ __forceinline__ void t16_stem(const Tower16Params &P, float v0, float
         x[c + 1] = t16_lrelu(s.y);
     }
 }
-// epilogue 1 / 2 arithmetic: three partial accumulators (lo.hi, hi.lo, hi.hi) -> lrelu(sum * 2^-s + bias).
-// Scalar on purpose: the packed fp32x2 forms measured 7 % slower here (operands not in aligned register pairs), while in
-// the stem / stencil / residual / split code, where pairs are natural, scalar forms measured 1-5 % slower.  A single
-// accumulator chain per conv (no partial sums to add) was also slower: conv1 +0.7 %, conv0 +14 % -- a dependent
-// tcgen05.mma costs ~175 clk, so short parallel chains matter even with a second CTA to hide behind.  Four chains of six
-// for conv0 (a fourth accumulator in the idle H columns) lost 8 %: one more TMEM load and add per element in E1.
+// epilogue 1 / 2 arithmetic: lrelu(acc * 2^-s + bias).  Scalar on purpose: the packed fp32x2 forms measured 7 % slower here
+// (operands not in aligned register pairs), while in the stem / stencil / residual / split code, where pairs are natural,
+// scalar forms measured 1-5 % slower.
+// History of the accumulator chains: with the MMA loop rolled and its operands in vector registers, ptxas wrapped every
+// tcgen05.mma in ~30 instructions of elect / R2UR waterfall code (~175 clk per dependent MMA), and three parallel chains per
+// convolution (one per product, three partial accumulators added here) beat a single chain by 14 %.  With warp-uniform
+// operands and unrolled chains the MMAs issue back to back (tower 0.749 -> 0.658 ms) and ONE chain per convolution is
+// faster again (0.648 ms): two TMEM loads and two adds per element less in each of these epilogues.
 template <int HALF>
-__device__ __forceinline__ void t16_bias_lrelu16(const float *bias32, float inv, const float *d, const float *e, const float *f,
-                                                 float *o) {
+__device__ __forceinline__ void t16_bias_lrelu16(const float *bias32, float inv, const float *d, float *o) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = t16_lrelu(fmaf((d[c] + e[c]) + f[c], inv, bias32[HALF * 16 + c]));
+    for (int c = 0; c < 16; ++c) o[c] = t16_lrelu(fmaf(d[c], inv, bias32[HALF * 16 + c]));
 }
 // depthwise 3x3, SAME zero padding, no bias (lib.rs:204-216): 16 channels of pixel (y, x0) from the fp32 tile.
-// (Measured and rejected: a branch-free variant whose off-board taps read all-zero tile rows -- no faster, the phase is
-// bound by the 144 shared-memory wavefronts per warp of the neighbour rows, not by load -> use latency.)
+// (Measured and rejected, twice: branch-free variants whose off-board taps read zeros.  The second one used a zero-padded
+// tile -- board rows of [128 zero bytes | 9 x 144-byte entries], every tap the centre plus a constant, no bank conflicts
+// (a first padded layout with 144-byte zero entries had 2-way conflicts at every board-row boundary: +10 %) -- and, with
+// ~100 fewer instructions per warp and block, still ran 5 % slower than the per-tap bounds tests: the phase is bound by the
+// 144 shared-memory wavefronts per warp of the neighbour rows, not by its instruction count.)
 template <int HALF>
 __device__ __forceinline__ void t16_stencil(const Tower16Block &B, const float *Hpos /* tile rows of this position */, int y, int xx0,
                                             float *a) {
@@ -207,11 +211,12 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
               const float *__restrict__ images, const uint32_t *n_req, int max_rows, __half *__restrict__ act_hi,
               __half *__restrict__ act_lo) {
     extern __shared__ uint8_t t16_smem_raw[];
-    const int rows = (int)min(*n_req, (uint32_t)max_rows);
+    // (the broadcasts below tell ptxas that these values are warp-uniform: the MMA issue code then runs on uniform registers)
+    const int rows = __shfl_sync(0xffffffffu, (int)min(*n_req, (uint32_t)max_rows), 0);
     const int n_triples = (rows + 2) / 3, n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
     if (pair >= n_triples) return;  // uniform for both CTAs of the pair, before any cluster barrier
     const uint32_t rank = cluster_rank();
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int t = threadIdx.x, warp = __shfl_sync(0xffffffffu, t >> 5, 0), lane = t & 31;
     const int q = warp & 3, half = warp >> 2;
     // Row R of the pair = 128*rank + TMEM lane; position j = R/81, pixel p = R%81.
     const int R = (int)rank * 128 + q * 32 + lane;
@@ -226,8 +231,8 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     uint8_t *sm = t16_smem_raw + ((1024u - (smem_u32(t16_smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(sm);
     float *H0 = reinterpret_cast<float *>(sm + S16_H);
-    float *IMG = reinterpret_cast<float *>(sm + S16_IMG);
     float *T32 = reinterpret_cast<float *>(sm + S16_TAB);
+    float *IMG = reinterpret_cast<float *>(sm + S16_IMG);
     uint32_t *TW = reinterpret_cast<uint32_t *>(sm + S16_TAB + 8 * T16_TABSTRIDE * 4);
     const uint32_t bar_w0 = sbase + S16_BAR, bar_mma = sbase + S16_BAR + 16, bar_band = sbase + S16_BAR + 24,
                    bar_free = sbase + S16_BAR + 32, tmem_slot = sbase + S16_BAR + 40;
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);  // this warp's lane quadrant
 
     uint32_t g = 0;          // running block counter: weight buffer = g & 1, its phase parity = (g >> 1) & 1
@@ -337,22 +343,27 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             // ================= conv0: 1x1 128 -> 32 (A = X in TMEM) =================
             fence_before();
             __syncthreads();
-            if (lane == 0) {
+            if (warp == 0) {
+                if (elect_one()) {
+                    fence_after();
+                    mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+                    const uint64_t bhi = desc_sw128(wb + W16_W0HI), blo = desc_sw128(wb + W16_W0LO);
+                    const uint32_t dcol = tmem_base + TC_ACC;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint64_t off = (uint64_t)(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
+                        const uint32_t ahi = tmem_base + TC_X + 16u * kk;
+                        umma_f16_ts(dcol, ahi + 8u, bhi + off, T16_IDESC_N32, kk != 0);
+                        umma_f16_ts(dcol, ahi, blo + off, T16_IDESC_N32, 1u);
+                        umma_f16_ts(dcol, ahi, bhi + off, T16_IDESC_N32, 1u);
+                    }
+                    umma_commit(bar_mma);
+                }
+            } else if (lane == 0) {
                 fence_after();
                 if (warp == 3) {
                     issue_weights(g + 1);  // the other buffer's last reader (block g-1, or the write-out) has completed
                     mbar_expect_tx(bar_band, T16_BAND_BYTES);  // arm this block's band phase
-                }
-                if (warp < 3) {
-                    // one accumulator chain per product (lo.hi, hi.lo, hi.hi), issued in parallel from three threads: the
-                    // single-thread issue path costs ~60 clk per small MMA
-                    mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
-                    const uint32_t acol = tmem_base + TC_X + (warp == 0 ? 8u : 0u);
-                    const uint32_t bimg = wb + (warp == 1 ? W16_W0LO : W16_W0HI);
-#pragma unroll 1
-                    for (int kk = 0; kk < 8; ++kk)
-                        umma_f16_ts(tmem_base + TC_ACC + 32u * warp, acol + 16u * kk,
-                                    desc_sw128(bimg + (uint32_t)((kk >> 2) * 4096 + (kk & 3) * 32)), T16_IDESC_N32, kk != 0);
                 }
                 umma_commit(bar_mma);
             }
@@ -362,12 +373,10 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             T16_STAMP(2 + r * 8 + 0);
             // epilogue 1: + b0, lrelu -> fp32 tile for the depthwise stencil (this thread: 16 channels of its pixel)
             {
-                float d[16], e[16], f[16], o[16];
+                float d[16], o[16];
                 tmem_ld16(tlane + TC_ACC + half * 16, d);
-                tmem_ld16(tlane + TC_ACC + 32 + half * 16, e);
-                tmem_ld16(tlane + TC_ACC + 64 + half * 16, f);
                 tmem_wait_ld();
-                T16_HALF(t16_bias_lrelu16<0>(B.b0, B.inv[0], d, e, f, o), t16_bias_lrelu16<1>(B.b0, B.inv[0], d, e, f, o));
+                T16_HALF(t16_bias_lrelu16<0>(B.b0, B.inv[0], d, o), t16_bias_lrelu16<1>(B.b0, B.inv[0], d, o));
                 if (in_tile) {
                     float *hrow = H0 + (slot * kCells + p) * T16_HSTRIDE + half * 16;
 #pragma unroll
@@ -401,16 +410,23 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             // ================= conv1 pointwise: 1x1 32 -> 32 (A = H in TMEM) =================
             fence_before();
             __syncthreads();  // also: every thread's stencil reads of the tile are complete
-            if (lane == 0) {
-                fence_after();
-                if (warp == 3) mbar_arrive_cluster(peer_free);  // the peer may overwrite this CTA's mirrored band
-                if (warp < 3) {
-                    const uint32_t acol = tmem_base + TC_H + (warp == 0 ? 8u : 0u);
-                    const uint32_t bimg = wb + W16_PW + (warp == 1 ? 64u : 0u);
-#pragma unroll 1
-                    for (int ks = 0; ks < 2; ++ks)
-                        umma_f16_ts(tmem_base + TC_ACC + 32u * warp, acol + 16u * ks, desc_sw128(bimg + ks * 32), T16_IDESC_N32, ks != 0);
+            if (warp == 0) {
+                if (elect_one()) {
+                    fence_after();
+                    const uint64_t bhi = desc_sw128(wb + W16_PW), blo = bhi + 4u;
+                    const uint32_t dcol = tmem_base + TC_ACC;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t ahi = tmem_base + TC_H + 16u * ks;
+                        umma_f16_ts(dcol, ahi + 8u, bhi + (uint64_t)(2 * ks), T16_IDESC_N32, ks != 0);
+                        umma_f16_ts(dcol, ahi, blo + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
+                        umma_f16_ts(dcol, ahi, bhi + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
+                    }
+                    umma_commit(bar_mma);
                 }
+            } else if (lane == 0) {
+                fence_after();
+                if (warp == 3) mbar_arrive_cluster_relaxed(peer_free);  // the peer may overwrite this CTA's mirrored band (all stencil loads were consumed before the barrier above)
                 umma_commit(bar_mma);
             }
             T16_WAIT(bar_mma, mma_uses & 1u);
@@ -418,12 +434,10 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             fence_after();
             T16_STAMP(2 + r * 8 + 3);
             {   // epilogue 2: + b1, lrelu -> A operand of conv2
-                float d[16], e[16], f[16], o[16];
+                float d[16], o[16];
                 tmem_ld16(tlane + TC_ACC + half * 16, d);
-                tmem_ld16(tlane + TC_ACC + 32 + half * 16, e);
-                tmem_ld16(tlane + TC_ACC + 64 + half * 16, f);
                 tmem_wait_ld();
-                T16_HALF(t16_bias_lrelu16<0>(B.b1, B.inv[1], d, e, f, o), t16_bias_lrelu16<1>(B.b1, B.inv[1], d, e, f, o));
+                T16_HALF(t16_bias_lrelu16<0>(B.b1, B.inv[1], d, o), t16_bias_lrelu16<1>(B.b1, B.inv[1], d, o));
                 t16_store_group(tlane + TC_H + (uint32_t)(half * 16), o);
             }
             tmem_wait_st();
@@ -431,18 +445,22 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             // ================= conv2: 1x1 32 -> 128 (A = H in TMEM), + x, lrelu =================
             fence_before();
             __syncthreads();
-            if (lane == 0) {
-                fence_after();
-                if (warp == 0) {  // N = 128 MMAs are tensor-bound (64 clk each): one chain
-#pragma unroll 1
+            if (warp == 0) {  // N = 128 MMAs are tensor-bound (64 clk each): one chain
+                if (elect_one()) {
+                    fence_after();
+                    const uint64_t bhi0 = desc_sw128(wb + W16_W2);
+#pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
-                        const uint64_t bhi = desc_sw128(wb + W16_W2 + ks * 32), blo = desc_sw128(wb + W16_W2 + 64 + ks * 32);
+                        const uint64_t bhi = bhi0 + (uint64_t)(ks * 2), blo = bhi0 + (uint64_t)(4 + ks * 2);
                         const uint32_t ahi = tmem_base + TC_H + 16u * ks;
                         umma_f16_ts(tmem_base + TC_D3, ahi + 8u, bhi, T16_IDESC_N128, ks != 0);
                         umma_f16_ts(tmem_base + TC_D3, ahi, blo, T16_IDESC_N128, 1u);
                         umma_f16_ts(tmem_base + TC_D3, ahi, bhi, T16_IDESC_N128, 1u);
                     }
+                    umma_commit(bar_mma);
                 }
+            } else if (lane == 0) {
+                fence_after();
                 umma_commit(bar_mma);
             }
             T16_WAIT(bar_mma, mma_uses & 1u);
