@@ -149,8 +149,19 @@ __device__ __forceinline__ void t16_stem(const Tower16Params &P, float v0, float
 // faster again (0.648 ms): two TMEM loads and two adds per element less in each of these epilogues.
 template <int HALF>
 __device__ __forceinline__ void t16_bias_lrelu16(const float *bias32, float inv, const float *d, float *o) {
+#ifdef T16_E12_PACKED
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+        const float2 sv = __ffma2_rn(make_float2(d[c], d[c + 1]), make_float2(inv, inv),
+                                     make_float2(bias32[HALF * 16 + c], bias32[HALF * 16 + c + 1]));
+        const float2 u = __fmul2_rn(sv, make_float2(0.2f, 0.2f));
+        o[c] = fmaxf(sv.x, u.x);
+        o[c + 1] = fmaxf(sv.y, u.y);
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 16; ++c) o[c] = t16_lrelu(fmaf(d[c], inv, bias32[HALF * 16 + c]));
+#endif
 }
 // depthwise 3x3, SAME zero padding, no bias (lib.rs:204-216): 16 channels of pixel (y, x0) from the fp32 tile.
 // (Measured and rejected, twice: branch-free variants whose off-board taps read zeros.  The second one used a zero-padded
@@ -173,10 +184,10 @@ __device__ __forceinline__ void t16_stencil(const Tower16Block &B, const float *
 #pragma unroll
             for (int c = 0; c < 16; c += 4) {
                 const float4 h = *reinterpret_cast<const float4 *>(hp + c);
-                const float *w = &B.dw[ky * 3 + kx][HALF * 16 + c];
+                const float4 w = *reinterpret_cast<const float4 *>(&B.dw[ky * 3 + kx][HALF * 16 + c]);  // one LDCU.128
                 // packed fp32x2 FMA (sm_100): same results as two FFMAs, half the issue slots
-                const float2 lo2 = __ffma2_rn(make_float2(h.x, h.y), make_float2(w[0], w[1]), make_float2(a[c + 0], a[c + 1]));
-                const float2 hi2 = __ffma2_rn(make_float2(h.z, h.w), make_float2(w[2], w[3]), make_float2(a[c + 2], a[c + 3]));
+                const float2 lo2 = __ffma2_rn(make_float2(h.x, h.y), make_float2(w.x, w.y), make_float2(a[c + 0], a[c + 1]));
+                const float2 hi2 = __ffma2_rn(make_float2(h.z, h.w), make_float2(w.z, w.w), make_float2(a[c + 2], a[c + 3]));
                 a[c + 0] = lo2.x; a[c + 1] = lo2.y; a[c + 2] = hi2.x; a[c + 3] = hi2.y;
             }
         }
@@ -337,6 +348,11 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
         tmem_wait_st();
         T16_STAMP(1);
 
+#ifdef T16_UNROLL_BLOCKS
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
         for (int r = 0; r < 3; ++r, ++g) {
             const Tower16Block &B = P.blk[r];
             const uint32_t wb = sbase + S16_W + (g & 1u) * W16_BYTES;
