@@ -376,8 +376,27 @@ static bool encode_map16(CUtensorMap *map, __half *ptr, uint64_t rows, uint32_t 
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 3-D fp16 view [triple][243 pixel rows][128 channels] of a tower output array for k_tower16's TMA write-out: boxes of 32
+// rows x 32 channels (64 bytes), SWIZZLE_64B; a CTA pair's 13 padding rows (>= 243) fall outside dimension 1 and are clipped
+static bool encode_map_tower_store(CUtensorMap *map, __half *ptr, uint64_t rows) {
+    static PFN_encodeTiled16 fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+        fn = (PFN_encodeTiled16)p;
+    }
+    const cuuint64_t dims[3] = {128, 243, (rows + 2) / 3};  // the arrays carry two rows of slack for the last triple
+    const cuuint64_t strides[2] = {128 * sizeof(__half), 243 * 128 * sizeof(__half)};
+    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct ActMaps {  // tensor maps over one workspace's activation buffers (each search lane has its own workspace)
     CUtensorMap map0_a_hi, map0_a_lo, map1_a_hi, map1_a_lo, map2_a_hi, map2_a_lo;
+    CUtensorMap tower_st_hi, tower_st_lo;  // k_tower16's write-out into act0
     const __half *key[6] = {};  // the six buffers the maps were encoded for (a reallocation may reuse only some addresses)
     int a_rows = 0;
     float *splitk_partial = nullptr;  // [18 chunks][splitk_rows][512] fp32 partial sums of this workspace's split-K fc0
@@ -459,9 +478,19 @@ static ActMaps *refresh_maps16(omk_ctx *c, Fc16State *s) {
     if (!encode_map16(&m.map1_a_lo, w.act1_l16, (uint64_t)w.act_rows, F_BM, F_K1)) return nullptr;
     if (!encode_map16(&m.map2_a_hi, w.act2_h16, (uint64_t)w.act_rows, F_BM, F_K1)) return nullptr;
     if (!encode_map16(&m.map2_a_lo, w.act2_l16, (uint64_t)w.act_rows, F_BM, F_K1)) return nullptr;
+    if (!encode_map_tower_store(&m.tower_st_hi, w.act0_h16, (uint64_t)w.act_rows)) return nullptr;
+    if (!encode_map_tower_store(&m.tower_st_lo, w.act0_l16, (uint64_t)w.act_rows)) return nullptr;
     for (int i = 0; i < 6; ++i) m.key[i] = key[i];
     m.a_rows = w.act_rows;
     return &m;
+}
+
+bool fc16_tower_store_maps(omk_ctx *c, const void **map_hi, const void **map_lo) {
+    ActMaps *am = refresh_maps16(c, state16_of(c));
+    if (!am) return false;
+    *map_hi = &am->tower_st_hi;
+    *map_lo = &am->tower_st_lo;
+    return true;
 }
 
 static bool check_launch(const char *what) {

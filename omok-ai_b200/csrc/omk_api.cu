@@ -77,7 +77,8 @@ bool ensure_activations(omk_ctx *c, int rows) {
     w.act_rows = 0;
     w.act_fp32 = false;
     const size_t r = (size_t)rows;
-    const size_t sizes[] = {sizeof(__half) * r * 10368, sizeof(__half) * r * 10368, sizeof(__half) * r * 512, sizeof(__half) * r * 512,
+    // (act0: two rows of slack -- k_tower16 stores whole position triples, the last one may reach past `rows`)
+    const size_t sizes[] = {sizeof(__half) * (r + 2) * 10368, sizeof(__half) * (r + 2) * 10368, sizeof(__half) * r * 512, sizeof(__half) * r * 512,
                             sizeof(__half) * r * 512, sizeof(__half) * r * 512,
                             sizeof(float) * r * 512, sizeof(float) * r * 128, sizeof(float) * r * 10368, sizeof(float) * r * 512};
     for (int i = 0; i < (want_fp32 ? 10 : 8); ++i) {

@@ -165,6 +165,8 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound);
 bool launch_fc1_f16(omk_ctx *c, int rows_bound);
 bool launch_heads_f16(omk_ctx *c, int rows_bound);
 void fc16_free(omk_ctx *c);
+// tensor maps (CUtensorMap) of k_tower16's TMA write-out over the current workspace's act0_h16 / act0_l16
+bool fc16_tower_store_maps(omk_ctx *c, const void **map_hi, const void **map_lo);
 void launch_f32_to_split16(omk_ctx *c, const float *x, __half *hi, __half *lo, long long n);
 void launch_split16_to_f32(omk_ctx *c, const __half *hi, const __half *lo, float *x, long long n);
 

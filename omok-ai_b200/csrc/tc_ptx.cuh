@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_fp16.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace omk {
@@ -87,6 +88,18 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void *map, u
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
         : "memory");
+}
+// TMA stores (shared -> global through a tensor map, bulk async-group completion)
+__device__ __forceinline__ void tma_store_3d(const void *map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // sources may be overwritten
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }        // writes are complete
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void prefetch_map(const void *map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map)); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

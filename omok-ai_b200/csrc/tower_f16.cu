@@ -67,7 +67,7 @@ constexpr int S16_BAR = S16_TAB + 2 * 8 * T16_TABSTRIDE * 4;  // 108448
 constexpr int T16_SMEM_BYTES = S16_BAR + 64 + 1024;           // 109536: two CTAs per SM
 constexpr uint32_t T16_BAND_BYTES = 10 * 32 * 4;              // mirrored stencil band: 10 pixel rows x 32 channels fp32
 constexpr uint32_t T16_IDESC_N32 = idesc_f16(128, 32), T16_IDESC_N128 = idesc_f16(128, 128);
-static_assert(W16_BYTES == 8 * 32 * T16_HSTRIDE * 4, "the idle weight buffer doubles as eight per-warp staging tiles");
+static_assert(W16_BYTES == 8 * 4608, "the idle weight buffer doubles as eight per-warp staging tiles (4 KB used, 512-byte aligned)");
 static_assert(S16_BAR % 8 == 0, "mbarriers are 8-byte aligned");
 
 __device__ long long g_t16_dbg[64];  // phase timestamps of CTA 0's second iteration (omk_debug_tower_timing)
@@ -87,38 +87,35 @@ __device__ __forceinline__ void t16_store_group(uint32_t taddr, const float *v) 
     tmem_st16(taddr, w);
 }
 
-// Coalesced write-out of one warp's 32 pixel rows x 64 channels as fp16 hi / lo (the A operand of fc0).  A thread owns a
-// 128-byte segment of a row in each array, so direct per-thread stores would make every warp instruction touch 32
-// different cache lines.  Instead each warp transposes through a 4.6 KB staging tile, 32 channels at a time: a tile row
-// is [hi 64 B | lo 64 B]; on the way out four lanes cover one 64-byte run.
-// off16 = offset (16-byte units) of this lane's row segment in the fp16 arrays, or 0xFFFFFFFF for a padded / out-of-batch row.
-__device__ __forceinline__ void t16_store_out(uint32_t *stage, int lane, uint32_t off16, const float *x, __half *act_hi,
-                                              __half *act_lo) {
-    uint32_t orow[8];  // offsets of the eight rows this lane writes (row it*4 + lane/8), fetched once
+// TMA write-out of one warp's 32 pixel rows x 64 channels as fp16 hi / lo (the A operand of fc0).  The arrays are viewed as
+// [triple][243 pixel rows][128 channels]: the pair's rows are one contiguous block, a warp's piece of it is a box of 32
+// rows x 32 channels (64 bytes) per pass, hi and lo, and the pair's 13 padding rows (>= 243) are clipped by the tensor map.
+// The warp stages the box in its 4 KB tile of the idle weight buffer in the SWIZZLE_64B pattern (16-byte chunk index ^=
+// (row >> 1) & 3: conflict-free stores) and one lane issues cp.async.bulk.tensor stores: no per-thread global stores, no
+// LSU queue to drain before the next iteration's first shared-memory load (the per-thread STG.128 form -- 16 per thread,
+// eight 64-byte segments per instruction -- cost 11 % of the kernel in L1 tag cycles).
+// One pass = 32 channels (x32) of the warp's 32 rows; the caller makes sure the previous pass's stores have read the tile.
+__device__ __forceinline__ void t16_store_pass(uint32_t tile, int lane, const float *x32, const CUtensorMap *map_hi,
+                                               const CUtensorMap *map_lo, int ch, int r0, int tr) {
+    const uint32_t rowoff = (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) orow[it] = __shfl_sync(0xffffffffu, off16, it * 4 + (lane >> 3));
-    uint4 *dst = reinterpret_cast<uint4 *>((lane & 4) ? act_lo : act_hi);
-#pragma unroll
-    for (int cp = 0; cp < 2; ++cp) {  // two passes of 32 channels
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint4 h, l;
-            const float *v = x + cp * 32 + k * 8;
-            split2_f16(v[0], v[1], h.x, l.x);
-            split2_f16(v[2], v[3], h.y, l.y);
-            split2_f16(v[4], v[5], h.z, l.z);
-            split2_f16(v[6], v[7], h.w, l.w);
-            *reinterpret_cast<uint4 *>(stage + lane * T16_HSTRIDE + k * 4) = h;
-            *reinterpret_cast<uint4 *>(stage + lane * T16_HSTRIDE + 16 + k * 4) = l;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + (lane >> 3), seg = lane & 7;  // seg 0..3: hi 16-byte pieces, 4..7: lo pieces
-            const uint4 val = *reinterpret_cast<const uint4 *>(stage + rr * T16_HSTRIDE + seg * 4);
-            if (orow[it] != 0xFFFFFFFFu) dst[(size_t)orow[it] + cp * 4 + (seg & 3)] = val;
-        }
-        __syncwarp();
+    for (int k = 0; k < 4; ++k) {
+        uint4 h, l;
+        const float *v = x32 + k * 8;
+        split2_f16(v[0], v[1], h.x, l.x);
+        split2_f16(v[2], v[3], h.y, l.y);
+        split2_f16(v[4], v[5], h.z, l.z);
+        split2_f16(v[6], v[7], h.w, l.w);
+        const uint32_t a = tile + rowoff + (((uint32_t)k ^ sw) << 4);
+        sts128(a, h);
+        sts128(a + 2048u, l);
+    }
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_3d(map_hi, tile, ch, r0, tr);
+        tma_store_3d(map_lo, tile + 2048u, ch, r0, tr);
+        bulk_commit();
     }
 }
 
@@ -208,19 +205,43 @@ __device__ __forceinline__ void t16_residual32(const Tower16Block &B, int c0, co
         x[c + 1] = fmaxf(tt.y, u.y);
     }
 }
-// one float of the reference's 243-float input slot (encoder.rs:22-43) as a bit: same values as image_value()
-__device__ __forceinline__ uint32_t t16_image_bit(const NNIn &in, int f) {
-    if (f >= 2 * kCells) return (in.meta & 1u) ^ 1u;  // turn plane: 1.0 when black is to move
-    const uint32_t persp = (in.meta ^ (in.meta >> 1)) & 1u;  // EnvTurnMode::Opponent flips the perspective
-    return ((uint32_t)(f & 1) == persp ? bit81(in.black, f >> 1) : bit81(in.white, f >> 1)) ? 1u : 0u;
+// The three input floats of one pixel as bits.  The reference's 243-float slot (encoder.rs:22-43) read as [81][3] puts
+// floats 3 pc .. 3 pc + 2 at pixel pc: for pc < 54 they are (cell, plane) entries f -> (f >> 1, f & 1) of the interleaved
+// stone planes -- two neighbouring cells A, B = A + 1 -- and for pc >= 54 (f >= 162) all three lie in the turn plane.
+// Which words of the request row a thread needs never changes, so it loads just those (5 words instead of the 32-byte
+// row) and the per-iteration work is a handful of shifts and selects (same values as image_value()).
+struct T16Req { uint32_t bA, wA, bB, wB, meta; };
+struct T16ReqSpec { int wordA, wordB; uint32_t sA, sB, odd, turn; };  // thread-invariant
+__device__ __forceinline__ T16ReqSpec t16_req_spec(int pc) {
+    T16ReqSpec q;
+    q.turn = pc >= 54;
+    const int f0 = q.turn ? 0 : 3 * pc, cA = f0 >> 1, cB = cA + 1;
+    q.wordA = cA >> 5; q.sA = cA & 31; q.wordB = cB >> 5; q.sB = cB & 31; q.odd = f0 & 1;
+    return q;
+}
+__device__ __forceinline__ T16Req t16_req_load(const NNIn *row, const T16ReqSpec &q) {
+    const uint32_t *rp = reinterpret_cast<const uint32_t *>(row);
+    T16Req r;
+    r.bA = rp[q.wordA]; r.wA = rp[3 + q.wordA]; r.bB = rp[q.wordB]; r.wB = rp[3 + q.wordB]; r.meta = rp[6];
+    return r;
+}
+__device__ __forceinline__ uint32_t t16_req_combo(const T16Req &r, const T16ReqSpec &q) {
+    const uint32_t bA = (r.bA >> q.sA) & 1u, wA = (r.wA >> q.sA) & 1u, bB = (r.bB >> q.sB) & 1u, wB = (r.wB >> q.sB) & 1u;
+    const uint32_t persp = (r.meta ^ (r.meta >> 1)) & 1u;  // EnvTurnMode::Opponent flips the perspective
+    // plane k holds black where k == persp.  even f0: (A, 0) (A, 1) (B, 0); odd f0: (A, 1) (B, 0) (B, 1)
+    const bool e = (q.odd ^ persp) != 0;              // "plane (f0 & 1) is the white one"
+    const uint32_t bY = q.odd ? bB : bA, wY = q.odd ? wB : wA;
+    const uint32_t ch0 = e ? wA : bA, ch1 = e ? bY : wY, ch2 = e ? wB : bB;
+    const uint32_t stones = ch0 | (ch1 << 1) | (ch2 << 2);
+    return q.turn ? ((r.meta & 1u) ^ 1u) * 7u : stones;  // turn plane: 1.0 when black is to move
 }
 #define T16_HALF(call_0, call_1) do { if (half == 0) { call_0; } else { call_1; } } while (0)
 
 template <bool STAMPS>
 __global__ void __launch_bounds__(T16_THREADS, 2)
     k_tower16(const uint8_t *__restrict__ wimg, const __grid_constant__ Tower16Params P, const NNIn *__restrict__ nn_in,
-              const float *__restrict__ images, const uint32_t *n_req, int max_rows, __half *__restrict__ act_hi,
-              __half *__restrict__ act_lo) {
+              const float *__restrict__ images, const uint32_t *n_req, int max_rows, const __grid_constant__ CUtensorMap map_hi,
+              const __grid_constant__ CUtensorMap map_lo) {
     extern __shared__ uint8_t t16_smem_raw[];
     // (the broadcasts below tell ptxas that these values are warp-uniform: the MMA issue code then runs on uniform registers)
     const int rows = __shfl_sync(0xffffffffu, (int)min(*n_req, (uint32_t)max_rows), 0);
@@ -298,8 +319,9 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     if (t == 0) issue_weights(0);
 
     // boards path: a thread needs only the request row of ITS position (prefetched one iteration ahead)
-    NNIn cur{};
-    if (!images) cur = nn_in[min(pair * 3 + j, rows - 1)];
+    const T16ReqSpec spec = t16_req_spec(in_tile ? p : 0);
+    T16Req cur{};
+    if (!images) cur = t16_req_load(nn_in + min(pair * 3 + j, rows - 1), spec);
     int pos_iter = 0;
     for (int tr = pair; tr < n_triples; tr += n_pairs, ++pos_iter) {
         [[maybe_unused]] const bool dbg_on = blockIdx.x == 0 && pos_iter == 1;
@@ -323,10 +345,9 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             for (int c = 0; c < 4; ++c) t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c * 16), x + c * 16);
         } else {
             // ---- packed boards: the stem of this pixel is a table row ----
-            const int pc = in_tile ? p : 0;
-            const uint32_t combo = t16_image_bit(cur, 3 * pc) | (t16_image_bit(cur, 3 * pc + 1) << 1) | (t16_image_bit(cur, 3 * pc + 2) << 2);
+            const uint32_t combo = t16_req_combo(cur, spec);
             // prefetch the next triple's request row: its global-load latency hides behind this whole iteration
-            if (tr + n_pairs < n_triples) cur = nn_in[min((tr + n_pairs) * 3 + j, rows - 1)];
+            if (tr + n_pairs < n_triples) cur = t16_req_load(nn_in + min((tr + n_pairs) * 3 + j, rows - 1), spec);
             const float4 *tx = reinterpret_cast<const float4 *>(T32 + combo * T16_TABSTRIDE + half * 64);
             const uint4 *tw = reinterpret_cast<const uint4 *>(TW + combo * T16_TABSTRIDE + half * 64);
 #pragma unroll
@@ -357,6 +378,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             const Tower16Block &B = P.blk[r];
             const uint32_t wb = sbase + S16_W + (g & 1u) * W16_BYTES;
             // ================= conv0: 1x1 128 -> 32 (A = X in TMEM) =================
+            if (r == 0 && lane == 0) bulk_wait_read0();  // the write-out's TMA stores have read their staging tiles: the weight prefetch below may overwrite them
             fence_before();
             __syncthreads();
             if (warp == 0) {
@@ -494,23 +516,28 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                 if (r < 2) {
                     t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16), x + c2 * 16);
                     t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16 + 16), x + c2 * 16 + 16);
+                } else {
+                    // ---- flatten NHWC (network.rs:127-137): the tower's output leaves as fp16 hi / lo, 32 channels per
+                    // pass.  This block's weight buffer is idle now (conv2 has completed) and holds the staging tiles;
+                    // the first pass's TMA reads overlap the second half of this epilogue.
+                    const uint32_t tile = wb + (uint32_t)warp * 4608u;
+                    if (c2) {
+                        if (lane == 0) bulk_wait_read0();
+                        __syncwarp();
+                    }
+                    t16_store_pass(tile, lane, x + c2 * 16, &map_hi, &map_lo, half * 64 + c2 * 16, (int)rank * 128 + q * 32, tr);
                 }
             }
             tmem_wait_st();
             T16_STAMP(2 + r * 8 + 6);
         }
-        // ---- flatten NHWC (network.rs:127-137): this thread's pixel row, its 64 channels, as fp16 hi / lo ----
         T16_STAMP(30);
-        {   // the weight buffer of the block just finished is idle until the next conv0 phase: staging tiles live there
-            uint32_t *stage = reinterpret_cast<uint32_t *>(sm + S16_W + ((g - 1u) & 1u) * W16_BYTES) + warp * (32 * T16_HSTRIDE);
-            const uint32_t off16 = real ? (uint32_t)row * 1296u + (uint32_t)(p * 16 + half * 8) : 0xFFFFFFFFu;
-            t16_store_out(stage, lane, off16, x, act_hi, act_lo);
-        }
         T16_STAMP(31);
     }
     // (timestamps: 0 start, 1 stem done, then per block: conv0 done, E1+sync, dw stored, conv1 done, E2 stored, conv2 done, E3 stored)
     // drain the weight prefetch that was issued one block ahead, then release TMEM
     if (t == 0) mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+    if (lane == 0) bulk_wait_all0();  // this warp's TMA stores are complete
     fence_before();
     __syncthreads();
     cluster_sync_all();  // no mirrored store or remote arrival is in flight once both CTAs are here
@@ -672,8 +699,10 @@ bool launch_tower_f16(omk_ctx *c, const float *images_dev, int rows_bound) {
     const Tower16Params &params = *reinterpret_cast<const Tower16Params *>(c->tower16_params_host);
     const NNIn *nn_in = c->ws.nn_in;
     const uint32_t *n_req = c->ws.n_req;
-    __half *ah = c->ws.act0_h16, *al = c->ws.act0_l16;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, wimg, params, nn_in, images_dev, n_req, rows_bound, ah, al);
+    const void *mh = nullptr, *ml = nullptr;  // tensor maps of the write-out over this workspace's act0 arrays
+    if (!fc16_tower_store_maps(c, &mh, &ml)) return false;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, wimg, params, nn_in, images_dev, n_req, rows_bound,
+                                             *reinterpret_cast<const CUtensorMap *>(mh), *reinterpret_cast<const CUtensorMap *>(ml));
     if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_tower16): %s\n", cudaGetErrorString(e));
     c->launches++;
     return e == cudaSuccess;
