@@ -165,7 +165,9 @@ __device__ __forceinline__ void t16_bias_lrelu16(const float *bias32, float inv,
 // tile -- board rows of [128 zero bytes | 9 x 144-byte entries], every tap the centre plus a constant, no bank conflicts
 // (a first padded layout with 144-byte zero entries had 2-way conflicts at every board-row boundary: +10 %) -- and, with
 // ~100 fewer instructions per warp and block, still ran 5 % slower than the per-tap bounds tests: the phase is bound by the
-// 144 shared-memory wavefronts per warp of the neighbour rows, not by its instruction count.)
+// 144 shared-memory wavefronts per warp of the neighbour rows, not by its instruction count.  Taking the centre tap from
+// the thread's own epilogue-1 registers instead of the tile (four loads less) was 6 % slower: sixteen more live registers
+// across the band barrier.)
 template <int HALF>
 __device__ __forceinline__ void t16_stencil(const Tower16Block &B, const float *Hpos /* tile rows of this position */, int y, int xx0,
                                             float *a) {
