@@ -330,7 +330,8 @@ def main():
                              "chain per tree (ncu: 42 % fixed-latency waits), at 65 536 trees by issue slots (78 %) with 5 % DRAM "
                              "traffic because a round's re-reads of the root rows are L1 hits (DESIGN.md 3, profiles/r01_tree_pool_sweep.json); "
                              "hidden behind the other search lane's fc0 in the timed region",
-                     "traffic": None}
+                     # one k_select_expand + one k_apply launch at 1024 searching trees (ncu capture with the hash evaluator)
+                     "traffic": (traffic.get("k_select_expand", 0.0) + traffic.get("k_apply", 0.0)) or None}
         roof_env = None
         try:
             n_env = 1 << 24
@@ -353,7 +354,7 @@ def main():
             env_gbs = n_env * 78 / (env_ms * 1e-3) / 1e9
             roof_env = {"bound": "hbm", "kernel": "k_env_step (lane per board, 32-byte packed records; BASELINE configs[1] shape scaled to 16 Mi boards)",
                         "achieved": env_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": env_gbs / peaks["hbm_gbs"],
-                        "avg_launch_ms": env_ms, "board_steps_per_s": n_env / (env_ms * 1e-3), "traffic": None}
+                        "avg_launch_ms": env_ms, "board_steps_per_s": n_env / (env_ms * 1e-3), "traffic": traffic.get("k_env_step")}
             ectx.close()
             del acts, st, legal
         except Exception as exc:  # the headline line must still print

@@ -167,7 +167,8 @@ __device__ __forceinline__ void t16_bias_lrelu16(const float *bias32, float inv,
 // ~100 fewer instructions per warp and block, still ran 5 % slower than the per-tap bounds tests: the phase is bound by the
 // 144 shared-memory wavefronts per warp of the neighbour rows, not by its instruction count.  Taking the centre tap from
 // the thread's own epilogue-1 registers instead of the tile (four loads less) was 6 % slower: sixteen more live registers
-// across the band barrier.)
+// across the band barrier.  Loading the fp32 residual rows of the stem table behind block 0's conv2 instead of in the stem
+// phase: 20 % slower -- this kernel lives at 128 registers and every change of live ranges shows.)
 template <int HALF>
 __device__ __forceinline__ void t16_stencil(const Tower16Block &B, const float *Hpos /* tile rows of this position */, int y, int xx0,
                                             float *a) {
@@ -350,8 +351,8 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             const uint32_t combo = t16_req_combo(cur, spec);
             // prefetch the next triple's request row: its global-load latency hides behind this whole iteration
             if (tr + n_pairs < n_triples) cur = t16_req_load(nn_in + min((tr + n_pairs) * 3 + j, rows - 1), spec);
-            const float4 *tx = reinterpret_cast<const float4 *>(T32 + combo * T16_TABSTRIDE + half * 64);
             const uint4 *tw = reinterpret_cast<const uint4 *>(TW + combo * T16_TABSTRIDE + half * 64);
+            const float4 *tx = reinterpret_cast<const float4 *>(T32 + combo * T16_TABSTRIDE + half * 64);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const float4 v = tx[c];
