@@ -20,7 +20,9 @@ standing in for TensorFlow-CPU, on a bounded sample of the same workload.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import importlib
+import io
 import json
 import os
 import subprocess
@@ -71,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -80,7 +82,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
 
     def stop(self):
         if not self.proc:
@@ -90,8 +98,16 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        # samples taken inside the timed region; nvidia-smi needs up to a second to start on an 8-GPU box, so it is started
+        # before the warm-up and, should a short region hold no sample, the nearest ones (+-1 s, same load) stand in
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        window = "timed region"
+        if not rows:
+            rows = [r for t, r in self.rows if t0 - 1.0 <= t <= t1 + 1.0]
+            window = "within 1 s of the timed region (same workload running)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -102,7 +118,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -229,15 +245,19 @@ def main():
             dist.barrier()
 
     # ---- device-resident arm: `value` ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     ctx.selfplay_run(warm, profile=0, want_transitions=False)
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_start()
     stats, *_ = ctx.selfplay_run(steps, profile=0, want_transitions=False)
     barrier()
-    clocks = sampler.stop()
+    sampler.mark_end()
     launches = ctx.launch_count - launches0
+    ctx.selfplay_run(1, profile=0, want_transitions=False)  # keeps the load on while the last samples arrive (untimed)
+    barrier()
+    clocks = sampler.stop()
     ms = float(stats.gpu_ms)
     sims, positions, nn_evals = int(stats.simulations), int(stats.positions), int(stats.nn_evals)
     # Kernel durations for the rooflines: the timed region above runs two search lanes on two streams, where a CUDA-event
@@ -399,4 +419,15 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # ONE JSON line on stdout: libraries (NCCL prints its version banner to the C stdout of rank 0) write to stderr instead
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = io.StringIO()
+    with contextlib.redirect_stdout(_buf):
+        main()
+    sys.stdout.flush()
+    os.dup2(_real_stdout, 1)
+    out = [l for l in _buf.getvalue().splitlines() if l.startswith("{")]
+    if out:
+        print(out[-1], flush=True)
