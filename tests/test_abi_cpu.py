@@ -44,3 +44,20 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower(), f"{f} refers to the oracle"
+
+
+def test_rust_sys_crate_declares_every_entry_point_with_the_same_arity(omk):
+    """shims/omok-b200-sys cannot be compiled here (no Rust toolchain): at least keep its `extern "C"` block in step with
+    the header -- every declared symbol present, same number of parameters."""
+    import re
+
+    header = open(os.path.join(ROOT, "include", "omok_b200.h")).read()
+    rust = open(os.path.join(ROOT, "shims", "omok-b200-sys", "src", "lib.rs")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    for name in omk.declared_symbols():
+        c = re.search(r"\b" + name + r"\s*\(([^)]*)\)", header)
+        r = re.search(r"pub fn " + name + r"\s*\(([^)]*)\)", rust)
+        assert c and r, name
+        c_args = [a for a in c.group(1).split(",") if a.strip() and a.strip() != "void"]
+        r_args = [a for a in r.group(1).split(",") if a.strip()]
+        assert len(c_args) == len(r_args), (name, c_args, r_args)
