@@ -215,7 +215,7 @@ typedef struct {
 } omk_selfplay_stats;
 
 OMK_API int32_t omk_selfplay_begin(omk_ctx *ctx, const omk_selfplay_config *cfg);
-/* plays `plies` plies on every game; transitions are copied to out_* (HOST, each may
+/* plays `plies` plies on every game; transitions stream through a pinned ring to out_* (HOST, each may
  * be NULL) in (ply, game) order: boards[plies*n*81], policy[plies*n*81], status[plies*n] */
 OMK_API int32_t omk_selfplay_run(omk_ctx *ctx, int32_t plies, int32_t profile, uint8_t *out_boards, float *out_policy,
                          int8_t *out_status, int32_t *out_actions, omk_selfplay_stats *stats);

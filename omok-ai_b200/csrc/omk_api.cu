@@ -295,6 +295,17 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
     for (void *p : ptrs) cudaFree(p);
     for (int i = 0; i < kNetTensors; ++i) cudaFree(c->net.t[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->sp_copy_stream) {
+        cudaStreamSynchronize(c->sp_copy_stream);
+        for (int i = 0; i < omk_ctx::kSpRing; ++i) {
+            cudaEventDestroy(c->sp_ev_rec[i][0]);
+            cudaEventDestroy(c->sp_ev_rec[i][1]);
+            cudaEventDestroy(c->sp_ev_copy[i]);
+        }
+        cudaStreamDestroy(c->sp_copy_stream);
+    }
+    cudaFree(c->sp_ring_dev);
+    if (c->sp_ring_host) cudaFreeHost(c->sp_ring_host);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -772,6 +783,20 @@ struct SpLayout {
     unsigned long long *counters;  // [0] games finished
     size_t bytes;
 };
+// one ply slot of the transition ring: [boards n*81 u8 | policy n*81 f32 | actions n i32 | status n i8], 256-byte aligned parts
+struct SpSlot {
+    size_t off_boards, off_policy, off_actions, off_status, bytes;
+};
+static SpSlot sp_slot_layout(int n) {
+    SpSlot s;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    s.off_boards = 0;
+    s.off_policy = up((size_t)n * kCells);
+    s.off_actions = s.off_policy + up((size_t)n * kCells * sizeof(float));
+    s.off_status = s.off_actions + up((size_t)n * sizeof(int32_t));
+    s.bytes = s.off_status + up((size_t)n);
+    return s;
+}
 static SpLayout sp_layout(omk_ctx *c, int n) {
     SpLayout L;
     uint8_t *base = reinterpret_cast<uint8_t *>(c->sp_buf);
@@ -811,6 +836,25 @@ extern "C" int32_t omk_selfplay_begin(omk_ctx *c, const omk_selfplay_config *cfg
     CK(cudaMalloc(&c->sp_buf, L.bytes));
     CK(cudaMemsetAsync(c->sp_buf, 0, L.bytes, c->stream));
     const SpLayout M = sp_layout(c, n);
+    // transition ring: device slots + pinned host mirror + copy stream + events
+    const SpSlot slot = sp_slot_layout(n);
+    if (slot.bytes != c->sp_ring_slot_bytes) {
+        cudaFree(c->sp_ring_dev);
+        if (c->sp_ring_host) cudaFreeHost(c->sp_ring_host);
+        c->sp_ring_dev = c->sp_ring_host = nullptr;
+        c->sp_ring_slot_bytes = 0;
+        CK(cudaMalloc(&c->sp_ring_dev, slot.bytes * omk_ctx::kSpRing));
+        CK(cudaHostAlloc(&c->sp_ring_host, slot.bytes * omk_ctx::kSpRing, cudaHostAllocDefault));
+        c->sp_ring_slot_bytes = slot.bytes;
+    }
+    if (!c->sp_copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->sp_copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < omk_ctx::kSpRing; ++i) {
+            CK(cudaEventCreateWithFlags(&c->sp_ev_rec[i][0], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->sp_ev_rec[i][1], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->sp_ev_copy[i], cudaEventDisableTiming));
+        }
+    }
     // Agent::new for all 2n trees (stream id = tree id); then cache the root's raw policy for restarts:
     // evaluating the empty board is deterministic, so reusing it is bit-identical to evaluating it again
     launch_reset_requests(c);
@@ -839,18 +883,26 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
     float *root_policy = L.root_policy;
     unsigned long long *counters = L.counters;
 
-    // transition staging on the device: [ply][game]
+    // Transitions stream through a ring of kSpRing ply slots: the ply's kernels record into device slot ply % kSpRing, the
+    // slice is copied to the pinned host mirror on the copy stream while later plies search, and the host drains a slot
+    // into the caller's [ply][game] arrays just before the device reuses it (the host thread is then at most kSpRing
+    // plies ahead of the GPU).
+    constexpr int kRing = omk_ctx::kSpRing;
     const size_t tot = (size_t)plies * (size_t)n;
-    uint8_t *d_boards = nullptr;
-    float *d_policy = nullptr;
-    int8_t *d_status = nullptr;
-    int32_t *d_actions = nullptr;
-    if (tot) {
-        CK(cudaMalloc(&d_boards, tot * kCells));
-        CK(cudaMalloc(&d_policy, tot * kCells * sizeof(float)));
-        CK(cudaMalloc(&d_status, tot));
-        CK(cudaMalloc(&d_actions, tot * sizeof(int32_t)));
-    }
+    const SpSlot slot = sp_slot_layout(n);
+    const bool want_out = out_boards || out_policy || out_status || out_actions;
+    size_t d2h = 0;
+    auto dev_slot = [&](int ply) { return c->sp_ring_dev + (size_t)(ply % kRing) * slot.bytes; };
+    auto drain = [&](int ply) -> int32_t {  // pinned slot of `ply` -> the caller's arrays
+        CK(cudaEventSynchronize(c->sp_ev_copy[ply % kRing]));
+        const uint8_t *h = c->sp_ring_host + (size_t)(ply % kRing) * slot.bytes;
+        const size_t row = (size_t)ply * n;
+        if (out_boards) memcpy(out_boards + row * kCells, h + slot.off_boards, (size_t)n * kCells);
+        if (out_policy) memcpy(out_policy + row * kCells, h + slot.off_policy, (size_t)n * kCells * sizeof(float));
+        if (out_actions) memcpy(out_actions + row, h + slot.off_actions, (size_t)n * sizeof(int32_t));
+        if (out_status) memcpy(out_status + row, h + slot.off_status, (size_t)n);
+        return OMK_OK;
+    };
     unsigned long long h_before[2] = {0, 0}, h_after[2] = {0, 0}, h_fin0 = 0, h_fin1 = 0;
     CK(cudaMemcpyAsync(h_before, c->dev_sims, sizeof h_before, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&h_fin0, counters, sizeof h_fin0, cudaMemcpyDeviceToHost, c->stream));
@@ -860,7 +912,6 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
     auto span_begin = [&](int kind) { return prof_begin(c, kind, 2); };
     auto span_end = [&](bool sp) { prof_end(c, sp); };
 
-    size_t d2h = 0;
     // Two search lanes (halves of the games) when the pool is large enough: two independent kernel chains on two streams.
     const int lanes = lanes_for(c, n);
     const int lane_n[2] = {lanes == 2 ? (n + 1) / 2 : n, lanes == 2 ? n / 2 : 0};
@@ -874,6 +925,15 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
     CK(cudaEventRecord(c->ev0, c->stream));
     if (lanes == 2) lanes_fork(c);
     for (int ply = 0; ply < plies; ++ply) {
+        if (want_out && ply >= kRing) {  // the slot this ply records into still holds ply - kRing: hand it to the caller first
+            int32_t rc_d = drain(ply - kRing);
+            if (rc_d) return rc_d;
+        }
+        uint8_t *ds = dev_slot(ply);
+        uint8_t *d_boards = ds + slot.off_boards;
+        float *d_policy = reinterpret_cast<float *>(ds + slot.off_policy);
+        int32_t *d_actions = reinterpret_cast<int32_t *>(ds + slot.off_actions);
+        int8_t *d_status = reinterpret_cast<int8_t *>(ds + slot.off_status);
         for (int l = 0; l < lanes; ++l) {
             LaneScope scope(c, l, 0);
             const int g0 = lane_g0[l], nl = lane_n[l];
@@ -899,7 +959,7 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
         for (int l = 0; l < lanes; ++l) {
             LaneScope scope(c, l, 0);
             const int g0 = lane_g0[l], nl = lane_n[l];
-            const size_t row = (size_t)ply * n + g0;
+            const size_t row = (size_t)g0;  // within the ply's ring slot
             bool sp = span_begin(OMK_K_MOVE);
             launch_sample(c, mover + g0, nl, modes + g0, temps + g0, actions + g0, policy_out + (size_t)g0 * kCells, nullptr);
             launch_sp_record(c, nl, mover + g0, actions + g0, policy_out + (size_t)g0 * kCells, d_boards + row * kCells,
@@ -918,6 +978,17 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
             launch_new_games(c, other + g0, nl, nullptr, status + g0, root_policy);
             launch_sp_advance(c, g0, nl, status, counters);
             span_end(sp);
+            if (want_out) CK(cudaEventRecord(c->sp_ev_rec[ply % kRing][l], c->stream));
+        }
+        if (want_out) {  // this ply's slice -> pinned host mirror, behind both lanes' recording kernels
+            for (int l = 0; l < lanes; ++l) CK(cudaStreamWaitEvent(c->sp_copy_stream, c->sp_ev_rec[ply % kRing][l], 0));
+            uint8_t *hs = c->sp_ring_host + (size_t)(ply % kRing) * slot.bytes;
+            if (out_boards) { CK(cudaMemcpyAsync(hs + slot.off_boards, d_boards, (size_t)n * kCells, cudaMemcpyDeviceToHost, c->sp_copy_stream)); d2h += (size_t)n * kCells; }
+            if (out_policy) { CK(cudaMemcpyAsync(hs + slot.off_policy, d_policy, (size_t)n * kCells * sizeof(float), cudaMemcpyDeviceToHost, c->sp_copy_stream)); d2h += (size_t)n * kCells * 4; }
+            if (out_actions) { CK(cudaMemcpyAsync(hs + slot.off_actions, d_actions, (size_t)n * 4, cudaMemcpyDeviceToHost, c->sp_copy_stream)); d2h += (size_t)n * 4; }
+            if (out_status) { CK(cudaMemcpyAsync(hs + slot.off_status, d_status, (size_t)n, cudaMemcpyDeviceToHost, c->sp_copy_stream)); d2h += (size_t)n; }
+            CK(cudaEventRecord(c->sp_ev_copy[ply % kRing], c->sp_copy_stream));
+            // the device slot is recorded into again kRing plies from now: by then the host has waited for this copy (drain)
         }
     }
     if (lanes == 2) {
@@ -927,16 +998,14 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
     if (lanes == 2) lanes_join(c);
     launch_reset_requests(c);  // folds the last round's request count into the evaluator total
     CK(cudaEventRecord(c->ev1, c->stream));
-    if (tot) {
-        if (out_boards) { CK(cudaMemcpyAsync(out_boards, d_boards, tot * kCells, cudaMemcpyDeviceToHost, c->stream)); d2h += tot * kCells; }
-        if (out_policy) { CK(cudaMemcpyAsync(out_policy, d_policy, tot * kCells * sizeof(float), cudaMemcpyDeviceToHost, c->stream)); d2h += tot * kCells * 4; }
-        if (out_status) { CK(cudaMemcpyAsync(out_status, d_status, tot, cudaMemcpyDeviceToHost, c->stream)); d2h += tot; }
-        if (out_actions) { CK(cudaMemcpyAsync(out_actions, d_actions, tot * 4, cudaMemcpyDeviceToHost, c->stream)); d2h += tot * 4; }
-    }
+    if (want_out)
+        for (int ply = plies > kRing ? plies - kRing : 0; ply < plies; ++ply) {  // the slots still in flight
+            int32_t rc_d = drain(ply);
+            if (rc_d) return rc_d;
+        }
     CK(cudaMemcpyAsync(h_after, c->dev_sims, sizeof h_after, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&h_fin1, counters, sizeof h_fin1, cudaMemcpyDeviceToHost, c->stream));
     int32_t rc = check_device_error(c);
-    cudaFree(d_boards); cudaFree(d_policy); cudaFree(d_status); cudaFree(d_actions);
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->simulations = (int64_t)(h_after[0] - h_before[0]);

@@ -106,6 +106,14 @@ struct omk_ctx {
     bool sp_active = false;
     int32_t *sp_ply = nullptr;        // [n_games] device ply counters
     void *sp_buf = nullptr;           // per-game scratch (ids, actions, modes, status, cached root policy)
+    // Transition ring of the self-play driver (BASELINE config 4: positions streamed to the host replay buffer): kSpRing
+    // ply slots on the device, mirrored in pinned host memory; a ply's slice leaves on `sp_copy_stream` while the next
+    // plies search.  Allocated by omk_selfplay_begin for sp_cfg.n_games.
+    static constexpr int kSpRing = 4;
+    uint8_t *sp_ring_dev = nullptr, *sp_ring_host = nullptr;  // kSpRing x [boards n*81 | policy n*81 f32 | actions n i32 | status n]
+    size_t sp_ring_slot_bytes = 0;
+    cudaStream_t sp_copy_stream = nullptr;
+    cudaEvent_t sp_ev_rec[kSpRing][2] = {}, sp_ev_copy[kSpRing] = {};
     // pinned host staging
     void *pinned = nullptr;
     size_t pinned_bytes = 0;

@@ -212,3 +212,35 @@ def test_config3_full_size_pool_properties(omk, orc):
                 assert_tree_equal(c, int(t), agent, f"full-size tree {t}")
         c.close()
     assert runs[0] == runs[1], "two search lanes must not change any tree"
+
+
+def test_selfplay_driver_ring_matches_granular_calls(omk):
+    """The device-resident self-play driver streams its transitions through a ring of four ply slots (pinned host mirror,
+    copy stream).  Seven plies (> the ring depth) of the driver must give, ply by ply, the boards / visit policies /
+    actions / statuses of the same games played through the granular calls (search, sample, play, ensure_action, play)."""
+    G, plies, count, batch, eps, alpha, temp, threshold = 6, 7, 64, 16, 0.25, 0.03, 1.0, 3
+    a = omk.Context(device=0, capacity_envs=4, capacity_trees=2 * G, capacity_nodes=2048, seed=77)
+    a.selfplay_begin(G, count, batch, eps, alpha, temp, threshold, omk.EVAL_HASH)
+    stats, boards, policy, status, actions = a.selfplay_run(plies, profile=0, want_transitions=True)
+    a.close()
+    assert int(stats.positions) == G * plies and int(stats.d2h_bytes) == G * plies * (81 + 81 * 4 + 4 + 1)
+    boards, policy = boards.reshape(plies, G, 81), policy.reshape(plies, G, 81)
+    status, actions = status.reshape(plies, G), actions.reshape(plies, G)
+
+    b = omk.Context(device=0, capacity_envs=4, capacity_trees=2 * G, capacity_nodes=2048, seed=77)
+    b.pool_new_games(n=2 * G, evaluator=omk.EVAL_HASH)  # black = tree 2g, white = 2g + 1, stream id = tree id
+    for ply in range(plies):
+        mids = [2 * g + (ply % 2) for g in range(G)]
+        oids = [2 * g + 1 - (ply % 2) for g in range(G)]
+        b.pool_search(ids=mids, count=count, batch_size=batch, epsilon=eps, alpha=alpha, evaluator=omk.EVAL_HASH)
+        before = np.stack([b.pool_get_env(t)[0] for t in mids])
+        acts, pol = b.pool_sample(ids=mids, modes=[1 if ply < threshold else 0] * G, temperatures=[temp] * G)
+        st = b.pool_play(acts, ids=mids)
+        b.pool_ensure_action(acts, ids=oids, evaluator=omk.EVAL_HASH)
+        b.pool_play(acts, ids=oids)
+        assert [int(x) for x in acts] == [int(x) for x in actions[ply]], f"ply {ply}: actions"
+        assert pol.tobytes() == policy[ply].tobytes(), f"ply {ply}: visit policies"
+        assert np.array_equal(before, boards[ply]), f"ply {ply}: boards (state the move was chosen in)"
+        assert [int(x) for x in st] == [int(x) for x in status[ply]], f"ply {ply}: status"
+        assert all(int(x) == 0 for x in st), "the fixture horizon is too short for a game to end"
+    b.close()
