@@ -146,19 +146,8 @@ __device__ __forceinline__ void t16_stem(const Tower16Params &P, float v0, float
 // faster again (0.648 ms): two TMEM loads and two adds per element less in each of these epilogues.
 template <int HALF>
 __device__ __forceinline__ void t16_bias_lrelu16(const float *bias32, float inv, const float *d, float *o) {
-#ifdef T16_E12_PACKED
-#pragma unroll
-    for (int c = 0; c < 16; c += 2) {
-        const float2 sv = __ffma2_rn(make_float2(d[c], d[c + 1]), make_float2(inv, inv),
-                                     make_float2(bias32[HALF * 16 + c], bias32[HALF * 16 + c + 1]));
-        const float2 u = __fmul2_rn(sv, make_float2(0.2f, 0.2f));
-        o[c] = fmaxf(sv.x, u.x);
-        o[c + 1] = fmaxf(sv.y, u.y);
-    }
-#else
 #pragma unroll
     for (int c = 0; c < 16; ++c) o[c] = t16_lrelu(fmaf(d[c], inv, bias32[HALF * 16 + c]));
-#endif
 }
 // depthwise 3x3, SAME zero padding, no bias (lib.rs:204-216): 16 channels of pixel (y, x0) from the fp32 tile.
 // (Measured and rejected, twice: branch-free variants whose off-board taps read zeros.  The second one used a zero-padded
@@ -372,11 +361,8 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
         tmem_wait_st();
         T16_STAMP(1);
 
-#ifdef T16_UNROLL_BLOCKS
-#pragma unroll
-#else
+        // (rolled on purpose: unrolled three times the constant-bank offsets become immediates, but 9.4k instructions of code run no faster)
 #pragma unroll 1
-#endif
         for (int r = 0; r < 3; ++r, ++g) {
             const Tower16Block &B = P.blk[r];
             const uint32_t wb = sbase + S16_W + (g & 1u) * W16_BYTES;
