@@ -290,6 +290,11 @@ def main():
         h2d += mover.nbytes * 5 + modes.nbytes + games * 4 + acts.nbytes * 3
         d2h += acts.nbytes + pol.nbytes + st.nbytes * 2 + 4 * 3
         assert (st == 0).all() or p >= 8, "a game ended implausibly early"
+        done = np.nonzero(st != 0)[0]
+        if len(done):  # a finished game starts over with two fresh agents, as the trainer's episode loop does (src/trainer.rs:101-121)
+            fresh = np.concatenate([ids_b[done], ids_w[done]]).astype(np.int32)
+            ctx.pool_new_games(ids=fresh, evaluator=omk.EVAL_NET)
+            h2d += fresh.nbytes
     barrier()
     e2e_s = time.perf_counter() - t0
 
