@@ -412,10 +412,10 @@ def main():
             "roofline_env": roof_env,
         }
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_selfplay_sample(1, 0)
+            r = cpu_selfplay_sample(4, 0)  # ~12 s of CPU work on 16 cores
             line["cpu_baseline"] = {
                 "value": r["sims"] / r["seconds"], "unit": "simulations/s", "cores": r["cores"], "kind": "port",
-                "sample": f"{r['trees']} concurrent trees x 1 ply x {COUNT} sims/move; C oracle (pthreads over trees) + "
+                "sample": f"{r['trees']} concurrent trees x 4 plies x {COUNT} sims/move; C oracle (pthreads over trees) + "
                           "PyTorch-CPU fp32 network standing in for TensorFlow-CPU"}
         print(json.dumps(line), flush=True)
     ctx.close()
