@@ -189,13 +189,15 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
-    return {"workload": f"BASELINE configs[2]: batched MCTS, {GAMES_PER_GPU} concurrent trees per GPU x {COUNT} sims/move, "
+def workload_config(n_gpus, games=GAMES_PER_GPU):
+    which = "BASELINE configs[2]" if games == GAMES_PER_GPU else f"BASELINE configs[2] shape at {games} games per GPU"
+    lanes = f"two search lanes (streams) of {games // 2} games each" if games >= 768 else "one search lane"
+    return {"workload": f"{which}: batched MCTS, {games} concurrent trees per GPU x {COUNT} sims/move, "
                         f"rounds of {BATCH}, eps {EPS}, alpha {ALPHA}, random-init residual policy/value net; "
                         "trainer-shaped self-play (2 trees per game, ensure_action_exists + re-root each ply)",
-            "games_per_gpu": GAMES_PER_GPU, "trees_per_gpu": 2 * GAMES_PER_GPU, "sims_per_move": COUNT,
+            "games_per_gpu": games, "trees_per_gpu": 2 * games, "sims_per_move": COUNT,
             "nn_batch_per_tree": BATCH, "capacity_nodes": CAP_NODES,
-            "parallelism": f"games sharded x{n_gpus}, no collective; per GPU two search lanes (streams) of 512 games each",
+            "parallelism": f"games sharded x{n_gpus}, no collective; per GPU {lanes}",
             "l2": "no flush: each network launch streams a 333 MB fc0 input (>> 126 MB L2) and ~2.9 GB of tree records are resident"}
 
 
@@ -399,7 +401,7 @@ def main():
             "positions_per_sec": positions / (ms * 1e-3), "nn_evals_per_sec": nn_evals / (ms * 1e-3),
             "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, games),
             "clocks": clocks,
             "e2e": {"value": e2e_sims / e2e_s, "unit": "simulations/s", "h2d_bytes_per_step": h2d // e2e_steps,
                     "d2h_bytes_per_step": d2h // e2e_steps,
