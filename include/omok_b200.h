@@ -14,7 +14,9 @@
  *   - one context = one CUDA device = one host thread at a time (many contexts OK).
  *   - there is NO CPU fallback: without a CUDA device omk_ctx_create fails.
  *   - ids are slots in the context's pools: env ids in [0, capacity_envs),
- *     tree ids in [0, capacity_trees).  `ids == NULL` means 0..n-1.
+ *     tree ids in [0, capacity_trees).  `ids == NULL` means 0..n-1.  The ids of one
+ *     call must be unique (OMK_ERR_INVALID otherwise): every listed slot gets its own
+ *     lane / warp, two of them on one record would race.
  *
  * Encodings (match the reference's enum declaration order)
  *   cell  : 0 Empty, 1 Black, 2 White          environment/src/lib.rs:4-9
@@ -102,8 +104,8 @@ OMK_API int32_t omk_net_eval_images(omk_ctx *ctx, const float *images, int32_t n
  * Kernel choice for fc0 + fc1 + heads, and for the tower: 1 = the tcgen05 kernels (3-pass fp16 hi/lo split; the product
  * path and the default), 0 = the fp32 CUDA-core kernels kept in the library as an A/B check of each layer (env
  * OMK_FC0=simt / OMK_TOWER=simt at context creation).  omk_debug_get_buffer copies an intermediate activation buffer to
- * the host: 8 = tower output and 9 = fc0 output of the tensor-core path (hi + lo), 0 = tower output, 1 = fc0 output,
- * 3 = head logits of the CUDA-core path.                                                                           */
+ * the host: 8 = tower output, 9 = fc0 output and 10 = fc1 output of the tensor-core path (hi + lo), 0 = tower output,
+ * 1 = fc0 output, 2 = fc1 output, 3 = head logits of the CUDA-core path.                                                                           */
 OMK_API int32_t omk_debug_set_fc0_mode(omk_ctx *ctx, int32_t mode);
 OMK_API int32_t omk_debug_set_tower_mode(omk_ctx *ctx, int32_t mode);
 /* clock64 phase timestamps of one iteration inside k_tower16 (64 values; tests/tools/check_f16.py) */
@@ -161,6 +163,10 @@ OMK_API int32_t omk_pool_play(omk_ctx *ctx, const int32_t *ids, const int32_t *a
 /* Agent.env of one tree */
 OMK_API int32_t omk_pool_get_env(omk_ctx *ctx, int32_t id, uint8_t *out_board, uint8_t *out_turn,
                          uint16_t *out_legal_count);
+/* Agent.env of n trees in one call (the root node's environment): out_boards[n*81], out_turns[n],
+ * out_legal_counts[n], out_status[n] = the root's GameStatus (any may be NULL).  One launch, one synchronisation. */
+OMK_API int32_t omk_pool_get_envs(omk_ctx *ctx, const int32_t *ids, int32_t n, uint8_t *out_boards, uint8_t *out_turns,
+                          uint16_t *out_legal_counts, int8_t *out_status);
 /* root node: n, w, p, status, policy[81] (any may be NULL) */
 OMK_API int32_t omk_pool_root_stats(omk_ctx *ctx, int32_t id, uint64_t *out_n, float *out_w, float *out_p,
                             int32_t *out_status, float *out_policy);

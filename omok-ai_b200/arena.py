@@ -28,11 +28,13 @@ def _play_moves(ctx, ids, actions, evaluator):
 
 
 def play_match(ctx_left, ctx_right, game_count: int = 100, count: int = 800, batch_size: int = 8, epsilon: float = 0.0,
-               alpha: float = 1.0, evaluator: int = B.EVAL_NET):
-    """Returns (left_wins, right_wins, draws).  Each context holds one model; it needs `game_count // 2` trees."""
+               alpha: float = 1.0, evaluator: int = B.EVAL_NET, moves_out: list | None = None):
+    """Returns (left_wins, right_wins, draws).  Each context holds one model; it needs `game_count // 2` trees.
+    `moves_out`, if given, receives one move list per game: first the `half` games left opens, then those right opens."""
     half = game_count // 2
     wins = {"left": 0, "right": 0, "draw": 0}
-    for first, second, first_name, second_name in ((ctx_left, ctx_right, "left", "right"), (ctx_right, ctx_left, "right", "left")):
+    log = [[] for _ in range(2 * half)]
+    for leg, (first, second, first_name, second_name) in enumerate(((ctx_left, ctx_right, "left", "right"), (ctx_right, ctx_left, "right", "left"))):
         ids = np.arange(half, dtype=np.int32)
         first.pool_new_games(ids=ids, evaluator=evaluator)
         second.pool_new_games(ids=ids, evaluator=evaluator)
@@ -41,6 +43,8 @@ def play_match(ctx_left, ctx_right, game_count: int = 100, count: int = 800, bat
         while live.size:
             mover.pool_search(ids=live, count=count, batch_size=batch_size, epsilon=epsilon, alpha=alpha, evaluator=evaluator)
             actions, _ = mover.pool_sample(ids=live, modes=np.full(live.size, B.SAMPLE_BEST, np.uint8))
+            for g, a in zip(live, actions):
+                log[leg * half + int(g)].append(int(a))
             status = mover.pool_play(actions, ids=live)
             # BlackWin / WhiteWin: the player who just moved made five (main.rs:61-75 maps it to the side to move first)
             done = status != 0
@@ -51,6 +55,8 @@ def play_match(ctx_left, ctx_right, game_count: int = 100, count: int = 800, bat
                 _play_moves(other, live[keep], actions[keep], evaluator)
             live = live[keep]
             mover, other, mover_name, other_name = other, mover, other_name, mover_name
+    if moves_out is not None:
+        moves_out[:] = log
     return wins["left"], wins["right"], wins["draw"]
 
 
@@ -81,18 +87,24 @@ def naive_moves(ctx, boards: np.ndarray, turns: np.ndarray, rng: np.random.Gener
 
 
 def play_against_naive_player(ctx, episode_count: int = 100, count: int = 800, batch_size: int = 16, epsilon: float = 0.25,
-                              alpha: float = 0.03, evaluator: int = B.EVAL_NET, seed: int = 0):
-    """Returns (black_win, white_win, draw): the naive player moves first (Black), the model answers (White)."""
+                              alpha: float = 0.03, evaluator: int = B.EVAL_NET, seed: int = 0, moves_out: list | None = None):
+    """Returns (black_win, white_win, draw): the naive player moves first (Black), the model answers (White).
+
+    The naive player's random choices come from `numpy.random.default_rng(seed)`, one draw per live game without a
+    forced move, games in ascending id order (the reference draws from thread_rng() in its swap_remove order,
+    trainer.rs:498-563: unreproducible; the order of independent games does not change any single game).
+    `moves_out`, if given, receives one list of actions per game (both players' moves in playing order)."""
     rng = np.random.default_rng(seed)
     ids = np.arange(episode_count, dtype=np.int32)
     ctx.pool_new_games(ids=ids, evaluator=evaluator)
     result = np.zeros(4, dtype=np.int64)
+    log = [[] for _ in range(episode_count)]
     live = ids
     while live.size:
-        envs = [ctx.pool_get_env(int(t)) for t in live]
-        boards = np.stack([e[0] for e in envs])
-        turns = np.array([e[1] for e in envs], dtype=np.uint8)
+        boards, turns, _, _ = ctx.pool_get_envs(ids=live)  # one launch + one synchronisation for all live games
         actions = naive_moves(ctx, boards, turns, rng)
+        for g, a in zip(live, actions):
+            log[int(g)].append(int(a))
         status = _play_moves(ctx, live, actions, evaluator)
         np.add.at(result, status[status != 0].astype(np.int64), 1)
         live = live[status == 0]
@@ -100,7 +112,11 @@ def play_against_naive_player(ctx, episode_count: int = 100, count: int = 800, b
             break
         ctx.pool_search(ids=live, count=count, batch_size=batch_size, epsilon=epsilon, alpha=alpha, evaluator=evaluator)
         actions, _ = ctx.pool_sample(ids=live, modes=np.full(live.size, B.SAMPLE_BEST, np.uint8))
+        for g, a in zip(live, actions):
+            log[int(g)].append(int(a))
         status = ctx.pool_play(actions, ids=live)
         np.add.at(result, status[status != 0].astype(np.int64), 1)
         live = live[status == 0]
+    if moves_out is not None:
+        moves_out[:] = log
     return int(result[2]), int(result[3]), int(result[1])

@@ -122,6 +122,7 @@ def load_library():
     L.omk_pool_ensure_action.argtypes = [vp, vp, vp, i32, i32]
     L.omk_pool_play.argtypes = [vp, vp, vp, i32, vp]
     L.omk_pool_get_env.argtypes = [vp, i32, vp, vp, vp]
+    L.omk_pool_get_envs.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.omk_pool_root_stats.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.omk_pool_root_children.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.omk_pool_tree_info.argtypes = [vp, i32, vp, vp]
@@ -329,6 +330,17 @@ class Context:
         legal = C.c_uint16()
         self._check(self.L.omk_pool_get_env(self.h, tree, _ptr(board), C.byref(turn), C.byref(legal)))
         return board, turn.value, legal.value
+
+    def pool_get_envs(self, ids=None, n=None):
+        """Agent.env of many trees in one call: (boards [n,81], turns [n], legal counts [n], root status [n])."""
+        ids = _ids(ids)
+        n = len(ids) if ids is not None else n
+        boards = np.zeros((n, CELLS), dtype=np.uint8)
+        turns = np.zeros(n, dtype=np.uint8)
+        legal = np.zeros(n, dtype=np.uint16)
+        status = np.zeros(n, dtype=np.int8)
+        self._check(self.L.omk_pool_get_envs(self.h, _ptr(ids), n, _ptr(boards), _ptr(turns), _ptr(legal), _ptr(status)))
+        return boards, turns, legal, status
 
     def pool_root_stats(self, tree: int):
         n = C.c_uint64()

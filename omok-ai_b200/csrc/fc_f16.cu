@@ -35,8 +35,21 @@ constexpr int F_BM = 128, F_BN = 256, F_BK = 64;  // BK fp16 elements = one 128-
 constexpr int F_N = 512;
 constexpr int F_K0 = 10368, F_K1 = 512;
 constexpr int F_A_BYTES = F_BM * F_BK * 2;        // 16 KB
-constexpr int F_CHUNK0 = 9;                       // fc0: 162 k-blocks = 18 x 9
-constexpr int F_CHUNK1 = 8;                       // fc1: 8 k-blocks = 1 x 8
+// k-blocks accumulated in tensor memory between two drains into fp32 registers.  The tensor-core accumulator truncates,
+// so the error of a layer grows with the chunk length; profiles/r02_net_error_study.json has error and time per choice
+// (A/B builds: -DOMK_F_CHUNK0=.. -DOMK_F_CHUNK1=.. -DOMK_F_CHUNKH=..).
+#ifndef OMK_F_CHUNK0
+#define OMK_F_CHUNK0 9
+#endif
+#ifndef OMK_F_CHUNK1
+#define OMK_F_CHUNK1 8
+#endif
+#ifndef OMK_F_CHUNKH
+#define OMK_F_CHUNKH 8
+#endif
+constexpr int F_CHUNK0 = OMK_F_CHUNK0;            // fc0: 162 k-blocks = 18 x 9
+constexpr int F_CHUNK1 = OMK_F_CHUNK1;            // fc1: 8 k-blocks
+constexpr int F_CHUNKH = OMK_F_CHUNKH;            // heads: 8 k-blocks
 constexpr int kSplitKMaxRows = 2048;              // fc0 batches up to here take the split-K path (36 CTAs per 128 rows): 95 vs 152 us at 2048 rows, 181 vs 158 us at 4096
 
 template <bool PAIR, int BN>
@@ -582,7 +595,7 @@ bool launch_heads_f16(omk_ctx *c, int rows_bound) {
     const ActMaps *am = s->weights_ready ? refresh_maps16(c, s) : nullptr;
     if (!am) return false;
     using Cfg = FcCfg<false, 128>;
-    auto kern = k_fc16<F_K1, F_CHUNK1, false, 128, true>;
+    auto kern = k_fc16<F_K1, F_CHUNKH, false, 128, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     const int mt = (rows_bound + F_BM - 1) / F_BM;
     kern<<<dim3(1, mt), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(

@@ -409,10 +409,13 @@ void launch_net_init_random(omk_ctx *c, uint64_t seed) {
     }
 }
 
-void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
+// false: a launch, a tensor-map encode or an activation-buffer allocation failed -- ws.P / ws.V hold nothing the caller may
+// use (the message went to stderr); callers must not run k_apply on them and return OMK_ERR_CUDA.
+bool net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     cudaFuncSetAttribute(k_tower, cudaFuncAttributeMaxDynamicSharedMemorySize, kTowerSmemBytes);
     if (max_rows > c->ws.max_rows) max_rows = c->ws.max_rows;
-    if (max_rows <= 0) return;
+    if (max_rows <= 0) return true;
+    bool ok = true;
     TowerWeights tw;
     tw.conv_w = c->net.t[0];
     tw.conv_b = c->net.t[1];
@@ -423,7 +426,7 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     }
     if (!ensure_activations(c, max_rows)) {
         fprintf(stderr, "omok_b200: activation workspace allocation failed (%d rows)\n", max_rows);
-        return;
+        return false;
     }
     const int tower_grid = max_rows < c->n_sms ? max_rows : c->n_sms;
     const int mt = (max_rows + GM - 1) / GM;
@@ -432,7 +435,7 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     // in-library A/B check of each layer.  A mixed setting goes through an explicit conversion pass.
     bool sp = prof_begin(c, OMK_K_TOWER, 1);
     if (c->tower_mode == 1) {
-        launch_tower_f16(c, images_dev, max_rows);
+        ok = launch_tower_f16(c, images_dev, max_rows) && ok;
         c->launches--;  // counted once below with the other network kernels
         if (c->fc0_mode == 0) launch_split16_to_f32(c, c->ws.act0_h16, c->ws.act0_l16, c->ws.act0, n0);
     } else {
@@ -443,7 +446,7 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     prof_end(c, sp);
     sp = prof_begin(c, OMK_K_FC0, 1);
     if (c->fc0_mode == 1) {
-        launch_fc0_f16(c, max_rows);
+        ok = launch_fc0_f16(c, max_rows) && ok;
         c->launches--;
     } else {
         k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act0, c->net.t[23], c->net.t[24], c->ws.act1, c->ws.n_req,
@@ -453,7 +456,7 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     prof_end(c, sp);
     sp = prof_begin(c, OMK_K_FC1, 2);
     if (c->fc0_mode == 1) {
-        launch_fc1_f16(c, max_rows);
+        ok = launch_fc1_f16(c, max_rows) && ok;
         c->launches--;
     } else {
         k_gemm<<<dim3(kFc / GN, mt), 256, 0, c->stream>>>(c->ws.act1, c->net.t[25], c->net.t[26], c->ws.act2, c->ws.n_req,
@@ -462,7 +465,7 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     prof_end(c, sp);
     sp = prof_begin(c, OMK_K_HEADS, 2);
     if (c->fc0_mode == 1) {  // heads GEMM + tanh / softmax in one tensor-core kernel
-        launch_heads_f16(c, max_rows);
+        ok = launch_heads_f16(c, max_rows) && ok;
     } else {
         k_gemm<<<dim3(1, mt), 256, 0, c->stream>>>(c->ws.act2, c->net.heads_w, c->net.heads_b, c->ws.logits, c->ws.n_req, max_rows,
                                                    128, kFc, 0);
@@ -471,6 +474,11 @@ void net_forward(omk_ctx *c, const float *images_dev, int max_rows) {
     }
     prof_end(c, sp);
     c->launches += 3;  // tower, fc0, fc1 (launch_heads_f16 / the CUDA-core heads counted above)
+    if (cudaPeekAtLastError() != cudaSuccess) {
+        fprintf(stderr, "omok_b200: network forward: %s\n", cudaGetErrorString(cudaPeekAtLastError()));
+        ok = false;
+    }
+    return ok;
 }
 
 }  // namespace omk

@@ -41,12 +41,36 @@ extern "C" const char *omk_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t omk_version(void) { return 100; }
 
 // ------------------------------------------------------------------ workspace
+// grow-only device scratch slot i of the context (every call that uses it synchronises the stream before it returns)
+template <typename T>
+static int32_t scratch_dev(omk_ctx *c, int i, size_t count, T **out) {
+    omk_ctx::Scratch &s = c->scratch[i];
+    const size_t bytes = count * sizeof(T);
+    if (bytes > s.cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(s.p);
+        s.p = nullptr;
+        s.cap = 0;
+        const size_t want = (bytes + 4095) & ~(size_t)4095;
+        CK(cudaMalloc(&s.p, want));
+        s.cap = want;
+    }
+    *out = reinterpret_cast<T *>(s.p);
+    return OMK_OK;
+}
+#define SCRATCH(i, count, ptr)                          \
+    do {                                                \
+        int32_t rc__ = scratch_dev(c, (i), (count), &(ptr)); \
+        if (rc__) return rc__;                          \
+    } while (0)
+
 static int32_t ensure_workspace(omk_ctx *c, int rows) {
     rows = (rows + 255) / 256 * 256;  // whole 256-row CTA-pair tiles
     if (rows <= c->ws.max_rows) return OMK_OK;
     CK(cudaStreamSynchronize(c->stream));
     Workspace &w = c->ws;
     cudaFree(w.nn_in); cudaFree(w.req_tree); cudaFree(w.req_node); cudaFree(w.P); cudaFree(w.V);
+    w.nn_in = nullptr; w.req_tree = nullptr; w.req_node = nullptr; w.P = nullptr; w.V = nullptr;  // a failed cudaMalloc below must not leave dangling pointers for omk_ctx_destroy
     w.max_rows = 0;
     CK(cudaMalloc(&w.nn_in, sizeof(NNIn) * (size_t)rows));
     CK(cudaMalloc(&w.req_tree, sizeof(uint32_t) * (size_t)rows));
@@ -162,8 +186,21 @@ static int32_t stage_ids(omk_ctx *c, const int32_t *ids, int n, const int32_t **
     *out = nullptr;
     if (n < 0 || n > limit) return fail(OMK_ERR_INVALID, "n out of range for the pool capacity");
     if (!ids) return OMK_OK;
-    for (int i = 0; i < n; ++i)
-        if (ids[i] < 0 || ids[i] >= limit) return fail(OMK_ERR_INVALID, "id out of range");
+    // ids must be unique: the kernels give every listed slot its own lane / warp, and two of them on one record would
+    // race (n_nodes bump, edge statistics, the in-place compaction of k_play)
+    if ((int)c->id_seen.size() < limit) c->id_seen.assign((size_t)limit, 0);
+    bool bad = false, dup = false;
+    int filled = 0;
+    for (; filled < n && !bad && !dup; ++filled) {
+        const int32_t id = ids[filled];
+        if (id < 0 || id >= limit) bad = true;
+        else if (c->id_seen[(size_t)id]) dup = true;
+        else c->id_seen[(size_t)id] = 1;
+    }
+    for (int i = 0; i < filled; ++i)
+        if (ids[i] >= 0 && ids[i] < limit) c->id_seen[(size_t)ids[i]] = 0;
+    if (bad) return fail(OMK_ERR_INVALID, "id out of range");
+    if (dup) return fail(OMK_ERR_INVALID, "duplicate id in the id list (ids must be unique within one call)");
     CK(cudaMemcpyAsync(c->ws.ids, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     *out = c->ws.ids;
     return OMK_OK;
@@ -191,14 +228,22 @@ void prof_end(omk_ctx *c, bool opened) {
 }
 }  // namespace omk
 
-static void run_evaluator(omk_ctx *c, int evaluator, int rows_bound) {
+// false: the evaluator did not run to the end of its launch sequence (ws.P / ws.V are stale): the caller returns
+// OMK_ERR_CUDA WITHOUT launching k_apply, which would write those rows into tree policies and back up garbage values
+static bool run_evaluator(omk_ctx *c, int evaluator, int rows_bound) {
     if (evaluator == OMK_EVAL_HASH) {
         const bool sp = prof_begin(c, OMK_K_HASH, 2);
         launch_eval_hash(c, rows_bound);
         prof_end(c, sp);
-    } else
-        net_forward(c, nullptr, rows_bound);
+        return true;
+    }
+    return net_forward(c, nullptr, rows_bound);
 }
+#define RUN_EVAL(c, evaluator, rows)                                                                                   \
+    do {                                                                                                               \
+        if (!run_evaluator((c), (evaluator), (rows)))                                                                  \
+            return fail(OMK_ERR_CUDA, "the evaluator failed to launch (see stderr); no result was applied to the trees"); \
+    } while (0)
 
 static int32_t check_evaluator(omk_ctx *c, int evaluator) {
     if (evaluator != OMK_EVAL_NET && evaluator != OMK_EVAL_HASH) return fail(OMK_ERR_INVALID, "unknown evaluator");
@@ -281,6 +326,7 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
                     c->net.fc1_wt_h16, c->net.fc1_wt_l16, c->net.fc_inv_scale, c->net.fc_absmax, c->net.tower16_wimg,
                     c->net.tower16_pimg, c->net.tower16_absmax};
     fc16_free(c);
+    for (omk_ctx::Scratch &sc : c->scratch) cudaFree(sc.p);
     free(c->tower16_params_host);
     if (c->lane1_stream) {
         cudaStreamSynchronize(c->lane1_stream);
@@ -323,6 +369,8 @@ extern "C" void *omk_ctx_stream(omk_ctx *c) { return (void *)c->stream; }
 extern "C" int64_t omk_ctx_launch_count(omk_ctx *c) { return c->launches; }
 
 // ------------------------------------------------------------------ network
+static int32_t sp_refresh_root_policy(omk_ctx *c);  // self-play driver: re-evaluate the cached empty-board prior
+
 extern "C" int32_t omk_net_load_params(omk_ctx *c, const float *const *tensors, const int64_t *lens) {
     CK(cudaSetDevice(c->device));
     for (int i = 0; i < kNetTensors; ++i)
@@ -335,7 +383,7 @@ extern "C" int32_t omk_net_load_params(omk_ctx *c, const float *const *tensors, 
     if (!tower16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split tower weight preparation failed");
     CK(cudaStreamSynchronize(c->stream));
     c->net.loaded = true;
-    return OMK_OK;
+    return sp_refresh_root_policy(c);
 }
 extern "C" int32_t omk_net_get_params(omk_ctx *c, float *const *tensors, const int64_t *lens) {
     CK(cudaSetDevice(c->device));
@@ -356,11 +404,11 @@ extern "C" int32_t omk_net_init_random(omk_ctx *c, uint64_t seed) {
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     c->net.loaded = true;
-    return OMK_OK;
+    return sp_refresh_root_policy(c);
 }
 
 static int32_t net_eval_common(omk_ctx *c, int n, const float *images_dev, float *out_p, float *out_v) {
-    net_forward(c, images_dev, n);
+    if (!net_forward(c, images_dev, n)) return fail(OMK_ERR_CUDA, "the network forward failed to launch (see stderr)");
     // P rows are padded to 96 floats on the device; compact on the way out
     CK(cudaMemcpy2DAsync(out_p, sizeof(float) * kCells, c->ws.P, sizeof(float) * kRow, sizeof(float) * kCells, (size_t)n,
                          cudaMemcpyDeviceToHost, c->stream));
@@ -379,15 +427,12 @@ extern "C" int32_t omk_net_eval(omk_ctx *c, const uint8_t *boards, const uint8_t
     int32_t rc = ensure_workspace(c, n);
     if (rc) return rc;
     uint8_t *d_boards = nullptr, *d_turns = nullptr;
-    CK(cudaMalloc(&d_boards, (size_t)n * kCells));
-    CK(cudaMalloc(&d_turns, (size_t)n));
+    SCRATCH(0, (size_t)n * kCells, d_boards);
+    SCRATCH(1, (size_t)n, d_turns);
     CK(cudaMemcpyAsync(d_boards, boards, (size_t)n * kCells, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_turns, turns, (size_t)n, cudaMemcpyHostToDevice, c->stream));
     launch_pack_boards(c, d_boards, d_turns, n, mode);
-    rc = net_eval_common(c, n, nullptr, out_p, out_v);
-    cudaFree(d_boards);
-    cudaFree(d_turns);
-    return rc;
+    return net_eval_common(c, n, nullptr, out_p, out_v);
 }
 
 extern "C" int32_t omk_net_eval_images(omk_ctx *c, const float *images, int32_t n, float *out_p, float *out_v) {
@@ -398,13 +443,11 @@ extern "C" int32_t omk_net_eval_images(omk_ctx *c, const float *images, int32_t 
     int32_t rc = ensure_workspace(c, n);
     if (rc) return rc;
     float *d_img = nullptr;
-    CK(cudaMalloc(&d_img, sizeof(float) * (size_t)n * 243));
+    SCRATCH(0, (size_t)n * 243, d_img);
     CK(cudaMemcpyAsync(d_img, images, sizeof(float) * (size_t)n * 243, cudaMemcpyHostToDevice, c->stream));
     const uint32_t nn = (uint32_t)n;
     CK(cudaMemcpyAsync(c->ws.n_req, &nn, sizeof nn, cudaMemcpyHostToDevice, c->stream));
-    rc = net_eval_common(c, n, d_img, out_p, out_v);
-    cudaFree(d_img);
-    return rc;
+    return net_eval_common(c, n, d_img, out_p, out_v);
 }
 
 // ------------------------------------------------------------------ diagnostics
@@ -431,14 +474,16 @@ extern "C" int32_t omk_debug_tower_timing(omk_ctx *c, int64_t *out64) {
 }
 extern "C" int32_t omk_debug_get_buffer(omk_ctx *c, int32_t which, float *out, int64_t count) {
     CK(cudaSetDevice(c->device));
-    if (which == 8 || which == 9) {  // fp16-split buffers, reconstructed as hi + lo: 8 = tower output, 9 = fc0 output
+    if (which >= 8 && which <= 10) {  // fp16-split buffers, reconstructed as hi + lo: 8 = tower, 9 = fc0, 10 = fc1 output
         if (!out || count < 0) return fail(OMK_ERR_INVALID, "bad buffer");
+        const __half *hi = which == 8 ? c->ws.act0_h16 : which == 9 ? c->ws.act1_h16 : c->ws.act2_h16;
+        const __half *lo = which == 8 ? c->ws.act0_l16 : which == 9 ? c->ws.act1_l16 : c->ws.act2_l16;
+        if (!hi || !lo) return fail(OMK_ERR_STATE, "the tensor-core activation buffers do not exist yet (no network call so far)");
         float *tmp = nullptr;
-        CK(cudaMalloc(&tmp, sizeof(float) * (size_t)(count > 0 ? count : 1)));
-        launch_split16_to_f32(c, which == 8 ? c->ws.act0_h16 : c->ws.act1_h16, which == 8 ? c->ws.act0_l16 : c->ws.act1_l16, tmp, count);
+        SCRATCH(0, (size_t)(count > 0 ? count : 1), tmp);
+        launch_split16_to_f32(c, hi, lo, tmp, count);
         CK(cudaMemcpyAsync(out, tmp, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        cudaFree(tmp);
         return OMK_OK;
     }
     const float *src = which == 0 ? c->ws.act0 : which == 1 ? c->ws.act1 : which == 2 ? c->ws.act2 : which == 3 ? c->ws.logits : nullptr;
@@ -470,16 +515,15 @@ extern "C" int32_t omk_env_step(omk_ctx *c, const int32_t *ids, const uint8_t *a
     uint8_t *d_act = nullptr;
     int8_t *d_st = nullptr;
     uint32_t *d_legal = nullptr;
-    CK(cudaMalloc(&d_act, (size_t)n));
-    CK(cudaMalloc(&d_st, (size_t)n));
-    if (out_legal) CK(cudaMalloc(&d_legal, sizeof(uint32_t) * 3 * (size_t)n));
+    SCRATCH(0, (size_t)n, d_act);
+    SCRATCH(1, (size_t)n, d_st);
+    if (out_legal) SCRATCH(2, 3 * (size_t)n, d_legal);
     CK(cudaMemcpyAsync(d_act, actions, (size_t)n, cudaMemcpyHostToDevice, c->stream));
     launch_env_step(c, d_ids, d_act, n, d_st, d_legal);
     if (out_status) CK(cudaMemcpyAsync(out_status, d_st, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (out_legal) CK(cudaMemcpyAsync(out_legal, d_legal, sizeof(uint32_t) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
-    cudaFree(d_act); cudaFree(d_st); cudaFree(d_legal);
     return OMK_OK;
 }
 
@@ -499,15 +543,14 @@ extern "C" int32_t omk_env_get(omk_ctx *c, const int32_t *ids, int32_t n, uint8_
     if (n == 0) return OMK_OK;
     uint8_t *d_b = nullptr, *d_t = nullptr;
     uint16_t *d_l = nullptr;
-    CK(cudaMalloc(&d_b, (size_t)n * kCells));
-    CK(cudaMalloc(&d_t, (size_t)n));
-    CK(cudaMalloc(&d_l, sizeof(uint16_t) * (size_t)n));
+    SCRATCH(0, (size_t)n * kCells, d_b);
+    SCRATCH(1, (size_t)n, d_t);
+    SCRATCH(2, (size_t)n, d_l);
     launch_env_get(c, d_ids, n, d_b, d_t, d_l);
     if (out_boards) CK(cudaMemcpyAsync(out_boards, d_b, (size_t)n * kCells, cudaMemcpyDeviceToHost, c->stream));
     if (out_turns) CK(cudaMemcpyAsync(out_turns, d_t, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (out_legal_counts) CK(cudaMemcpyAsync(out_legal_counts, d_l, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_b); cudaFree(d_t); cudaFree(d_l);
     return OMK_OK;
 }
 
@@ -519,13 +562,12 @@ extern "C" int32_t omk_env_set(omk_ctx *c, const int32_t *ids, int32_t n, const 
     if (rc) return rc;
     if (n == 0) return OMK_OK;
     uint8_t *d_b = nullptr, *d_t = nullptr;
-    CK(cudaMalloc(&d_b, (size_t)n * kCells));
-    CK(cudaMalloc(&d_t, (size_t)n));
+    SCRATCH(0, (size_t)n * kCells, d_b);
+    SCRATCH(1, (size_t)n, d_t);
     CK(cudaMemcpyAsync(d_b, boards, (size_t)n * kCells, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_t, turns, (size_t)n, cudaMemcpyHostToDevice, c->stream));
     launch_env_set(c, d_ids, n, d_b, d_t);
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_b); cudaFree(d_t);
     return OMK_OK;
 }
 
@@ -538,11 +580,10 @@ extern "C" int32_t omk_env_encode(omk_ctx *c, const int32_t *ids, int32_t n, int
     if (rc) return rc;
     if (n == 0) return OMK_OK;
     float *d_o = nullptr;
-    CK(cudaMalloc(&d_o, sizeof(float) * 243 * (size_t)n));
+    SCRATCH(0, 243 * (size_t)n, d_o);
     launch_env_encode(c, d_ids, n, mode, d_o);
     CK(cudaMemcpyAsync(out, d_o, sizeof(float) * 243 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_o);
     return OMK_OK;
 }
 
@@ -553,14 +594,13 @@ extern "C" int32_t omk_env_random_playout(omk_ctx *c, int32_t n, int32_t plies, 
     uint8_t *d_a = nullptr;
     int8_t *d_s = nullptr;
     const size_t tot = (size_t)n * (size_t)plies;
-    if (out_actions) CK(cudaMalloc(&d_a, tot));
-    if (out_status) CK(cudaMalloc(&d_s, tot));
+    if (out_actions) SCRATCH(0, tot, d_a);
+    if (out_status) SCRATCH(1, tot, d_s);
     launch_env_playout(c, n, plies, d_a, d_s);
     if (out_actions) CK(cudaMemcpyAsync(out_actions, d_a, tot, cudaMemcpyDeviceToHost, c->stream));
     if (out_status) CK(cudaMemcpyAsync(out_status, d_s, tot, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
-    cudaFree(d_a); cudaFree(d_s);
     return OMK_OK;
 }
 
@@ -582,7 +622,7 @@ extern "C" int32_t omk_pool_new_games(omk_ctx *c, const int32_t *ids, int32_t n,
     }
     launch_reset_requests(c);
     launch_new_games(c, d_ids, n, d_streams, nullptr, nullptr);
-    run_evaluator(c, evaluator, n);
+    RUN_EVAL(c, evaluator, n);
     launch_apply(c, d_ids, n, kApplyNewGame);
     return check_device_error(c);
 }
@@ -616,7 +656,7 @@ extern "C" int32_t omk_pool_search(omk_ctx *c, const int32_t *ids, int32_t n, in
             if (r == 0) launch_root_noise(c, ids_l, lane_n[l], epsilon, alpha);
             launch_reset_requests(c);
             launch_select_expand(c, ids_l, lane_n[l], batch_size);
-            run_evaluator(c, evaluator, lane_n[l] * batch_size);
+            RUN_EVAL(c, evaluator, lane_n[l] * batch_size);
             launch_apply(c, ids_l, lane_n[l], kApplySearch);
         }
     }
@@ -680,7 +720,7 @@ extern "C" int32_t omk_pool_ensure_action(omk_ctx *c, const int32_t *ids, const 
     CK(cudaMemcpyAsync(c->ws.actions, actions, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     launch_reset_requests(c);
     launch_ensure_prepare(c, d_ids, c->ws.actions, n);
-    run_evaluator(c, evaluator, n);
+    RUN_EVAL(c, evaluator, n);
     launch_apply(c, d_ids, n, kApplyEnsure);
     return check_device_error(c);
 }
@@ -713,12 +753,11 @@ static int32_t dump_root(omk_ctx *c, int32_t id, RootDump *host) {
     CK(cudaSetDevice(c->device));
     if (id < 0 || id >= c->cap_trees) return fail(OMK_ERR_INVALID, "tree id out of range");
     RootDump *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(RootDump)));
+    SCRATCH(0, 1, d);
     launch_root_children(c, id, d->actions, d->n, d->w, d->p, &d->len, d->policy, d->misc);
     CK(cudaMemcpyAsync(host, d, sizeof(RootDump), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
-    cudaFree(d);
     return OMK_OK;
 }
 
@@ -773,6 +812,27 @@ extern "C" int32_t omk_pool_get_env(omk_ctx *c, int32_t id, uint8_t *out_board, 
     return OMK_OK;
 }
 
+extern "C" int32_t omk_pool_get_envs(omk_ctx *c, const int32_t *ids, int32_t n, uint8_t *out_boards, uint8_t *out_turns,
+                                     uint16_t *out_legal_counts, int8_t *out_status) {
+    CK(cudaSetDevice(c->device));
+    const int32_t *d_ids;
+    int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_trees);
+    if (rc) return rc;
+    if (n == 0) return OMK_OK;
+    // one scratch block: [boards n*81 | turns n | status n | legal n u16]
+    uint8_t *blk = nullptr;
+    const size_t nn = (size_t)n, off_t = nn * kCells, off_s = off_t + nn, off_l = (off_s + nn + 1) & ~(size_t)1;
+    SCRATCH(0, off_l + 2 * nn, blk);
+    launch_pool_get_envs(c, d_ids, n, blk, blk + off_t, reinterpret_cast<uint16_t *>(blk + off_l), reinterpret_cast<int8_t *>(blk + off_s));
+    if (out_boards) CK(cudaMemcpyAsync(out_boards, blk, nn * kCells, cudaMemcpyDeviceToHost, c->stream));
+    if (out_turns) CK(cudaMemcpyAsync(out_turns, blk + off_t, nn, cudaMemcpyDeviceToHost, c->stream));
+    if (out_status) CK(cudaMemcpyAsync(out_status, blk + off_s, nn, cudaMemcpyDeviceToHost, c->stream));
+    if (out_legal_counts) CK(cudaMemcpyAsync(out_legal_counts, blk + off_l, 2 * nn, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return OMK_OK;
+}
+
 // ------------------------------------------------------------------ self-play driver
 struct SpLayout {
     int32_t *mover, *other, *actions;
@@ -814,6 +874,23 @@ static SpLayout sp_layout(omk_ctx *c, int n) {
     L.bytes = off;
     return L;
 }
+// Restarted games install a cached raw prior of the empty board instead of evaluating it again (Agent::new, agent.rs:16-25,
+// evaluates with the CURRENT weights).  The cache therefore follows every weight change: omk_net_load_params and
+// omk_net_init_random call this while a self-play driver is active (trainer step -> sync weights -> next self-play phase).
+static int32_t sp_refresh_root_policy(omk_ctx *c) {
+    if (!c->sp_active || c->sp_cfg.evaluator != OMK_EVAL_NET) return OMK_OK;
+    int32_t rc = ensure_workspace(c, 1);
+    if (rc) return rc;
+    const SpLayout L = sp_layout(c, c->sp_cfg.n_games);
+    const uint32_t one = 1;
+    CK(cudaMemsetAsync(c->ws.nn_in, 0, sizeof(NNIn), c->stream));  // empty board, Black to move, EnvTurnMode::Player (== k_new_games' request)
+    CK(cudaMemcpyAsync(c->ws.n_req, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
+    if (!net_forward(c, nullptr, 1)) return fail(OMK_ERR_CUDA, "re-evaluating the empty board after a weight change failed");
+    CK(cudaMemcpyAsync(L.root_policy, c->ws.P, sizeof(float) * kCells, cudaMemcpyDeviceToDevice, c->stream));
+    launch_reset_requests(c);
+    return check_device_error(c);
+}
+
 extern "C" int32_t omk_selfplay_begin(omk_ctx *c, const omk_selfplay_config *cfg) {
     CK(cudaSetDevice(c->device));
     if (!cfg) return fail(OMK_ERR_INVALID, "cfg is NULL");
@@ -859,7 +936,7 @@ extern "C" int32_t omk_selfplay_begin(omk_ctx *c, const omk_selfplay_config *cfg
     // evaluating the empty board is deterministic, so reusing it is bit-identical to evaluating it again
     launch_reset_requests(c);
     launch_new_games(c, nullptr, 2 * n, nullptr, nullptr, nullptr);
-    run_evaluator(c, cfg->evaluator, 2 * n);
+    RUN_EVAL(c, cfg->evaluator, 2 * n);
     launch_apply(c, nullptr, 2 * n, kApplyNewGame);
     CK(cudaMemcpyAsync(M.root_policy, c->tree_nodes + kOffPolicy, sizeof(float) * kCells, cudaMemcpyDeviceToDevice, c->stream));
     c->sp_active = true;
@@ -950,7 +1027,7 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
                 launch_reset_requests(c);
                 launch_select_expand(c, mover + g0, nl, cfg.batch_size);
                 span_end(sp);
-                run_evaluator(c, cfg.evaluator, nl * cfg.batch_size);
+                RUN_EVAL(c, cfg.evaluator, nl * cfg.batch_size);
                 sp = span_begin(OMK_K_APPLY);
                 launch_apply(c, mover + g0, nl, kApplySearch);
                 span_end(sp);
@@ -968,7 +1045,7 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
             launch_reset_requests(c);
             launch_ensure_prepare(c, other + g0, actions + g0, nl);
             span_end(sp);
-            run_evaluator(c, cfg.evaluator, nl);
+            RUN_EVAL(c, cfg.evaluator, nl);
             sp = span_begin(OMK_K_MOVE);
             launch_apply(c, other + g0, nl, kApplyEnsure);
             launch_play(c, other + g0, actions + g0, nl, status2 + g0);

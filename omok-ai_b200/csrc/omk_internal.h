@@ -84,6 +84,10 @@ struct omk_ctx {
     omk::Workspace lane1_ws;
     cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
     int lane_min_trees = 768;       // searches over fewer trees stay on one lane: each lane should still fill an fc0 wave (env OMK_LANE_MIN_TREES; 0 disables lanes)
+    // grow-only device scratch of the granular host-buffer calls (env_step, env_get, net_eval, ...): no cudaMalloc /
+    // cudaFree (an implicit device synchronisation each) per call, nothing to leak on an error return
+    struct Scratch { void *p = nullptr; size_t cap = 0; } scratch[3];
+    std::vector<uint8_t> id_seen;   // host scratch of stage_ids: duplicate detection over an id list
     int id_base = 0;                // first tree id of the lane in use when the id list is the identity
 
     omk::EnvRec *envs = nullptr;
@@ -149,6 +153,8 @@ void launch_play(omk_ctx *c, const int32_t *ids_dev, const int32_t *actions_dev,
 void launch_root_children(omk_ctx *c, int tree, int32_t *actions_dev, unsigned long long *n_dev, float *w_dev,
                           float *p_dev, int32_t *len_dev, float *policy_dev, uint32_t *misc_dev);
 void launch_eval_hash(omk_ctx *c, int rows_bound);
+void launch_pool_get_envs(omk_ctx *c, const int32_t *ids_dev, int n, uint8_t *boards_dev, uint8_t *turns_dev,
+                          uint16_t *legal_dev, int8_t *status_dev);
 void launch_reset_requests(omk_ctx *c);
 void launch_sp_prepare(omk_ctx *c, int g0, int n, int32_t *mover, int32_t *other, uint8_t *modes, float *temps);
 void launch_sp_record(omk_ctx *c, int n, const int32_t *mover, const int32_t *actions, const float *policy_in,
@@ -160,7 +166,7 @@ bool prof_begin(omk_ctx *c, int kind, int min_level);
 void prof_end(omk_ctx *c, bool opened);
 
 // net_kernels.cu
-void net_forward(omk_ctx *c, const float *images_dev /* or nullptr: use ws.nn_in */, int max_rows);
+bool net_forward(omk_ctx *c, const float *images_dev /* or nullptr: use ws.nn_in */, int max_rows);  // false: nothing usable in ws.P / ws.V
 void net_pack_heads(omk_ctx *c);
 void launch_net_init_random(omk_ctx *c, uint64_t seed);
 

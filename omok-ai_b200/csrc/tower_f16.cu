@@ -229,7 +229,13 @@ __device__ __forceinline__ uint32_t t16_req_combo(const T16Req &r, const T16ReqS
 }
 #define T16_HALF(call_0, call_1) do { if (half == 0) { call_0; } else { call_1; } } while (0)
 
-template <bool STAMPS>
+// BOARDS: the hot path (packed request rows).  Block 0's conv0 + epilogue 1 are then a TABLE as well: the stem output of a
+// pixel is one of 8 rows, so conv0(stem row) + b0, lrelu is one of 8 rows of 32 channels.  Each CTA computes those 8 rows
+// once, at kernel start, THROUGH THE SAME MMA CHAIN AND EPILOGUE ARITHMETIC as the general path (TMEM lanes 0..7 = the 8
+// packed stem rows; a row of D depends only on its own row of A), so the boards path stays bit-identical to the float-image
+// path (tested).  Per iteration that removes the stem's 128-channel operand store, block 0's conv0 MMA round trip and the
+// arithmetic of its epilogue 1.
+template <bool STAMPS, bool BOARDS>
 __global__ void __launch_bounds__(T16_THREADS, 2)
     k_tower16(const uint8_t *__restrict__ wimg, const __grid_constant__ Tower16Params P, const NNIn *__restrict__ nn_in,
               const float *__restrict__ images, const uint32_t *n_req, int max_rows, const __grid_constant__ CUtensorMap map_hi,
@@ -257,6 +263,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     float *H0 = reinterpret_cast<float *>(sm + S16_H);
     float *T32 = reinterpret_cast<float *>(sm + S16_TAB);
     float *IMG = reinterpret_cast<float *>(sm + S16_IMG);
+    float *T0 = IMG;  // boards path: block 0's conv0 table, 8 rows x T16_HSTRIDE floats (the image buffer is unused there)
     uint32_t *TW = reinterpret_cast<uint32_t *>(sm + S16_TAB + 8 * T16_TABSTRIDE * 4);
     const uint32_t bar_w0 = sbase + S16_BAR, bar_mma = sbase + S16_BAR + 16, bar_band = sbase + S16_BAR + 24,
                    bar_free = sbase + S16_BAR + 32, tmem_slot = sbase + S16_BAR + 40;
@@ -310,10 +317,69 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     };
     if (t == 0) issue_weights(0);
 
+    if constexpr (BOARDS) {
+        // ---- block 0's conv0 table: the 8 packed stem rows through conv0's MMA chain and epilogue 1, once per CTA ----
+        if (warp == 0) {  // TMEM lanes 0..7 <- packed rows (lanes >= 8 repeat row 7: their accumulator rows are never read)
+            const uint4 *tw = reinterpret_cast<const uint4 *>(TW + min(lane, 7) * T16_TABSTRIDE);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t w[16];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4 v = tw[c * 4 + k];
+                    w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+                }
+                tmem_st16(tlane + TC_X + (uint32_t)(c * 16), w);
+            }
+            tmem_wait_st();
+        }
+        fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            if (elect_one()) {
+                fence_after();
+                mbar_wait(bar_w0, 0u);
+                const uint32_t wb0 = sbase + S16_W;
+                const uint64_t bhi = desc_sw128(wb0 + W16_W0HI), blo = desc_sw128(wb0 + W16_W0LO);
+                const uint32_t dcol = tmem_base + TC_ACC;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {  // the same chain as conv0 in the loop below
+                    const uint64_t off = (uint64_t)(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
+                    const uint32_t ahi = tmem_base + TC_X + 16u * kk;
+                    umma_f16_ts(dcol, ahi + 8u, bhi + off, T16_IDESC_N32, kk != 0);
+                    umma_f16_ts(dcol, ahi, blo + off, T16_IDESC_N32, 1u);
+                    umma_f16_ts(dcol, ahi, bhi + off, T16_IDESC_N32, 1u);
+                }
+                umma_commit(bar_mma);
+            }
+        } else if (lane == 0) {
+            fence_after();
+            umma_commit(bar_mma);
+        }
+        T16_WAIT(bar_mma, mma_uses & 1u);
+        ++mma_uses;
+        fence_after();
+        if (warp == 0) {
+            float d[32], o[32];
+            tmem_ld16(tlane + TC_ACC, d);
+            tmem_ld16(tlane + TC_ACC + 16, d + 16);
+            tmem_wait_ld();
+            t16_bias_lrelu16<0>(P.blk[0].b0, P.blk[0].inv[0], d, o);
+            t16_bias_lrelu16<1>(P.blk[0].b0, P.blk[0].inv[0], d + 16, o + 16);
+            if (lane < 8) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4)
+                    *reinterpret_cast<float4 *>(T0 + lane * T16_HSTRIDE + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+            }
+        }
+        fence_before();
+        __syncthreads();  // the table is visible; TMEM lanes 0..7 are free again
+    }
+
     // boards path: a thread needs only the request row of ITS position (prefetched one iteration ahead)
     const T16ReqSpec spec = t16_req_spec(in_tile ? p : 0);
     T16Req cur{};
-    if (!images) cur = t16_req_load(nn_in + min(pair * 3 + j, rows - 1), spec);
+    if constexpr (BOARDS) cur = t16_req_load(nn_in + min(pair * 3 + j, rows - 1), spec);
     int pos_iter = 0;
     for (int tr = pair; tr < n_triples; tr += n_pairs, ++pos_iter) {
         [[maybe_unused]] const bool dbg_on = blockIdx.x == 0 && pos_iter == 1;
@@ -321,7 +387,8 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
         const bool real = in_tile && row < rows;     // 13 padding lanes per pair; the last triple may be partial
         T16_STAMP(0);
         float x[64];
-        if (images) {
+        [[maybe_unused]] uint32_t combo = 0;
+        if constexpr (!BOARDS) {
             // ---- general float images (AgentModel::evaluate_pv takes any tensor): the reference's 243-float slot read as [81][3] ----
             if (t < 243) {
                 IMG[t] = images[(size_t)min(tr * 3 + 0, rows - 1) * 243 + t];
@@ -337,28 +404,19 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             for (int c = 0; c < 4; ++c) t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c * 16), x + c * 16);
         } else {
             // ---- packed boards: the stem of this pixel is a table row ----
-            const uint32_t combo = t16_req_combo(cur, spec);
+            // (block 0's conv0 is a table too, so the packed operand words of the stem row are not needed here: only the
+            // fp32 residual row)
+            combo = t16_req_combo(cur, spec);
             // prefetch the next triple's request row: its global-load latency hides behind this whole iteration
             if (tr + n_pairs < n_triples) cur = t16_req_load(nn_in + min((tr + n_pairs) * 3 + j, rows - 1), spec);
-            const uint4 *tw = reinterpret_cast<const uint4 *>(TW + combo * T16_TABSTRIDE + half * 64);
             const float4 *tx = reinterpret_cast<const float4 *>(T32 + combo * T16_TABSTRIDE + half * 64);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const float4 v = tx[c];
                 x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t w[16];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint4 v = tw[c * 4 + k];
-                    w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-                }
-                tmem_st16(tlane + TC_X + (uint32_t)(half * 64 + c * 16), w);
-            }
         }
-        tmem_wait_st();
+        if constexpr (!BOARDS) tmem_wait_st();
         T16_STAMP(1);
 
         // (rolled on purpose: unrolled three times the constant-bank offsets become immediates, but 9.4k instructions of code run no faster)
@@ -370,40 +428,57 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             if (r == 0 && lane == 0) bulk_wait_read0();  // the write-out's TMA stores have read their staging tiles: the weight prefetch below may overwrite them
             fence_before();
             __syncthreads();
-            if (warp == 0) {
-                if (elect_one()) {
-                    fence_after();
-                    mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
-                    const uint64_t bhi = desc_sw128(wb + W16_W0HI), blo = desc_sw128(wb + W16_W0LO);
-                    const uint32_t dcol = tmem_base + TC_ACC;
+            const bool table0 = BOARDS && r == 0;  // conv0 + epilogue 1 of this block are a table row
+            if (table0) {
+                if (warp == 3 && lane == 0) {
+                    issue_weights(g + 1);
+                    mbar_expect_tx(bar_band, T16_BAND_BYTES);
+                }
+            } else {
+                if (warp == 0) {
+                    if (elect_one()) {
+                        fence_after();
+                        mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+                        const uint64_t bhi = desc_sw128(wb + W16_W0HI), blo = desc_sw128(wb + W16_W0LO);
+                        const uint32_t dcol = tmem_base + TC_ACC;
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const uint64_t off = (uint64_t)(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
-                        const uint32_t ahi = tmem_base + TC_X + 16u * kk;
-                        umma_f16_ts(dcol, ahi + 8u, bhi + off, T16_IDESC_N32, kk != 0);
-                        umma_f16_ts(dcol, ahi, blo + off, T16_IDESC_N32, 1u);
-                        umma_f16_ts(dcol, ahi, bhi + off, T16_IDESC_N32, 1u);
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint64_t off = (uint64_t)(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
+                            const uint32_t ahi = tmem_base + TC_X + 16u * kk;
+                            umma_f16_ts(dcol, ahi + 8u, bhi + off, T16_IDESC_N32, kk != 0);
+                            umma_f16_ts(dcol, ahi, blo + off, T16_IDESC_N32, 1u);
+                            umma_f16_ts(dcol, ahi, bhi + off, T16_IDESC_N32, 1u);
+                        }
+                        umma_commit(bar_mma);
+                    }
+                } else if (lane == 0) {
+                    fence_after();
+                    if (warp == 3) {
+                        issue_weights(g + 1);  // the other buffer's last reader (block g-1, or the write-out) has completed
+                        mbar_expect_tx(bar_band, T16_BAND_BYTES);  // arm this block's band phase
                     }
                     umma_commit(bar_mma);
                 }
-            } else if (lane == 0) {
+                T16_WAIT(bar_mma, mma_uses & 1u);
+                ++mma_uses;
                 fence_after();
-                if (warp == 3) {
-                    issue_weights(g + 1);  // the other buffer's last reader (block g-1, or the write-out) has completed
-                    mbar_expect_tx(bar_band, T16_BAND_BYTES);  // arm this block's band phase
-                }
-                umma_commit(bar_mma);
             }
-            T16_WAIT(bar_mma, mma_uses & 1u);
-            ++mma_uses;
-            fence_after();
             T16_STAMP(2 + r * 8 + 0);
             // epilogue 1: + b0, lrelu -> fp32 tile for the depthwise stencil (this thread: 16 channels of its pixel)
             {
                 float d[16], o[16];
-                tmem_ld16(tlane + TC_ACC + half * 16, d);
-                tmem_wait_ld();
-                T16_HALF(t16_bias_lrelu16<0>(B.b0, B.inv[0], d, o), t16_bias_lrelu16<1>(B.b0, B.inv[0], d, o));
+                if (table0) {
+                    const float4 *t0 = reinterpret_cast<const float4 *>(T0 + combo * T16_HSTRIDE + half * 16);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = t0[c];
+                        o[4 * c + 0] = v.x; o[4 * c + 1] = v.y; o[4 * c + 2] = v.z; o[4 * c + 3] = v.w;
+                    }
+                } else {
+                    tmem_ld16(tlane + TC_ACC + half * 16, d);
+                    tmem_wait_ld();
+                    T16_HALF(t16_bias_lrelu16<0>(B.b0, B.inv[0], d, o), t16_bias_lrelu16<1>(B.b0, B.inv[0], d, o));
+                }
                 if (in_tile) {
                     float *hrow = H0 + (slot * kCells + p) * T16_HSTRIDE + half * 16;
 #pragma unroll
@@ -440,6 +515,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             if (warp == 0) {
                 if (elect_one()) {
                     fence_after();
+                    if constexpr (BOARDS) mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);  // block 0 skipped conv0's wait
                     const uint64_t bhi = desc_sw128(wb + W16_PW), blo = bhi + 4u;
                     const uint32_t dcol = tmem_base + TC_ACC;
 #pragma unroll
@@ -648,12 +724,12 @@ static int tower16_max_pairs(omk_ctx *c) {
     // n_sms pairs instead of n_sms / 2), so the grid is sized from the SM count; surplus CTAs would simply queue.
     int n = c->n_sms;
     int api = 0;
-    if (cudaOccupancyMaxActiveClusters(&api, k_tower16<false>, &cfg) != cudaSuccess) cudaGetLastError();
+    if (cudaOccupancyMaxActiveClusters(&api, k_tower16<false, true>, &cfg) != cudaSuccess) cudaGetLastError();
     if (getenv("OMK_DEBUG")) {
         int per_sm = -1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tower16<false>, T16_THREADS, T16_SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tower16<false, true>, T16_THREADS, T16_SMEM_BYTES);
         cudaFuncAttributes fa{};
-        cudaFuncGetAttributes(&fa, k_tower16<false>);
+        cudaFuncGetAttributes(&fa, k_tower16<false, true>);
         fprintf(stderr, "omok_b200: k_tower16 CTA pairs: %d (%d SMs); occupancy API: %d clusters, %d blocks/SM; regs %d, static smem %zu, max dyn smem %d, carveout %d\n",
                 n, c->n_sms, api, per_sm, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
     }
@@ -664,7 +740,8 @@ static int tower16_max_pairs(omk_ctx *c) {
 
 bool launch_tower_f16(omk_ctx *c, const float *images_dev, int rows_bound) {
     static const bool stamps = getenv("OMK_TOWER_STAMPS") && atoi(getenv("OMK_TOWER_STAMPS")) != 0;
-    auto kern = stamps ? k_tower16<true> : k_tower16<false>;
+    const bool boards = images_dev == nullptr;
+    auto kern = stamps ? (boards ? k_tower16<true, true> : k_tower16<true, false>) : (boards ? k_tower16<false, true> : k_tower16<false, false>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T16_SMEM_BYTES);
     // two 107 KB CTAs per SM need the full shared-memory carve-out; the default heuristic sizes it for one block
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -220,13 +220,28 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
     uint32_t sims = 0;
     int nreq = 0;
 
+    // The descent is REUSED inside a round.  The reference re-runs select_leaf for each of a round's `batch` simulations,
+    // but it has no virtual loss and applies the network results only after the round (:222-265), so between two
+    // simulations the statistics on the path change only through a terminal backup (:92-97, :177-181), and the leaf stops
+    // being a leaf only when the expansion just made fills it (node.rs:45-51).  Otherwise the next select_leaf returns the
+    // same leaf by the same path (measured: 49 of 50 rounds of a search return one leaf 16 times), so the state of the
+    // walk (x, depth, cur_n, h, path) is kept: after a backup the walk restarts at the root, after a filling expansion
+    // it continues downwards from the leaf.  Same results bit for bit, ~1/16 of the PUCT scans.
+    bool restart = true;
+    uint32_t x = 0;
+    uint32_t cur_n = root_n;
+    int depth = 0;
+    NodeHdr h{};
     for (int it = 0; it < batch && !err; ++it) {
         ++sims;
         // ---- select_leaf (node.rs:39-59) with the PUCT selector (:81-90, :277-286) ----
-        uint32_t x = 0;
-        uint32_t cur_n = root_n;
-        int depth = 0;
-        NodeHdr h = load_hdr(tn);
+        if (restart) {
+            x = 0;
+            cur_n = root_n;
+            depth = 0;
+            h = load_hdr(tn);
+            restart = false;
+        }
         for (;;) {
             const int nch = popc81(h.cmask);
             if (nch != (int)h.legal || nch == 0) break;
@@ -284,6 +299,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
             root_n = __shfl_sync(kFull, root_n, 0);
             root_w = __shfl_sync(kFull, root_w, 0);
             __syncwarp();
+            restart = true;  // statistics along the path changed
             continue;
         }
 
@@ -330,7 +346,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
                 req[nreq] = (uint16_t)id;  // :182-187 queue for the evaluator
             }
         }
-        if (c.status == kInProgress) ++nreq;
+        if (c.status == kInProgress) ++nreq; else restart = true;  // a terminal child was backed up along the path
+        set81(h.cmask, action);  // the kept copy of the leaf's header follows the one in memory
         root_n = __shfl_sync(kFull, root_n, 0);
         root_w = __shfl_sync(kFull, root_w, 0);
         __syncwarp();
@@ -858,6 +875,21 @@ __global__ void k_root_children(TreeArgs a, int tree, int32_t *out_actions, unsi
         out_policy[c] = h.has_policy ? node_policy(tn)[c] : dummy_prior(h, c);
 }
 
+// Agent.env of many trees at once (the root node's board, turn, legal_move_count and status)
+__global__ void k_pool_get_envs(TreeArgs a, uint8_t *boards, uint8_t *turns, uint16_t *legal, int8_t *status) {
+    const int slot = blockIdx.x;
+    if (slot >= a.n) return;
+    const NodeHdr h = load_hdr(tree_nodes_of(a, tree_of(a, slot)));
+    if (boards)
+        for (int c = threadIdx.x; c < kCells; c += blockDim.x)
+            boards[(size_t)slot * kCells + c] = bit81(h.black, c) ? 1 : (bit81(h.white, c) ? 2 : 0);
+    if (threadIdx.x == 0) {
+        if (turns) turns[slot] = (uint8_t)h.turn;
+        if (legal) legal[slot] = (uint16_t)h.legal;
+        if (status) status[slot] = (int8_t)h.status;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // OMK_EVAL_HASH: exact fake evaluator over the pending request rows
 // ---------------------------------------------------------------------------------------
@@ -1004,6 +1036,12 @@ void launch_root_children(omk_ctx *c, int tree, int32_t *actions_dev, unsigned l
                           float *p_dev, int32_t *len_dev, float *policy_dev, uint32_t *misc_dev) {
     k_root_children<<<1, 96, 0, c->stream>>>(make_args(c, nullptr, 1), tree, actions_dev, n_dev, w_dev, p_dev, len_dev,
                                               policy_dev, misc_dev);
+    c->launches++;
+}
+void launch_pool_get_envs(omk_ctx *c, const int32_t *ids_dev, int n, uint8_t *boards_dev, uint8_t *turns_dev,
+                          uint16_t *legal_dev, int8_t *status_dev) {
+    if (n <= 0) return;
+    k_pool_get_envs<<<n, 96, 0, c->stream>>>(make_args(c, ids_dev, n), boards_dev, turns_dev, legal_dev, status_dev);
     c->launches++;
 }
 void launch_eval_hash(omk_ctx *c, int rows_bound) {

@@ -180,6 +180,36 @@ def forward(params: list[np.ndarray], images: np.ndarray, dtype=torch.float32):
     return pol.float().numpy(), v.float().numpy(), logits.float().numpy()
 
 
+def forward_layers(params: list[np.ndarray], images: np.ndarray, dtype=torch.float64) -> dict[str, np.ndarray]:
+    """The same graph as `forward`, returning every layer the CUDA path can be inspected at, in `dtype` precision (no
+    cast to fp32): tower [B,81,128] (the NHWC flatten fc0 reads), fc0 [B,512], fc1 [B,512], logits [B,81], vlogit [B],
+    P [B,81], V [B].  Used by the per-layer error study (tools/net_error_study.py, tests/test_net_gpu.py)."""
+    p = {name: torch.from_numpy(np.asarray(a)).to(dtype) for (name, _), a in zip(PARAM_SPECS, params)}
+    x = torch.from_numpy(np.asarray(images, dtype=np.float32)).to(dtype)
+    B = x.shape[0]
+    x = x.reshape(B, BOARD, BOARD, 3).permute(0, 3, 1, 2)
+
+    def conv1x1(t, w, b):
+        return F.conv2d(t, w[0, 0].t().reshape(w.shape[3], w.shape[2], 1, 1), b)
+
+    x = F.leaky_relu(conv1x1(x, p["conv_w"], p["conv_b"]), LRELU)
+    for i in range(NRES):
+        h = F.leaky_relu(conv1x1(x, p[f"res{i}_w0"], p[f"res{i}_b0"]), LRELU)
+        dw = p[f"res{i}_dw"]
+        h = F.conv2d(h, dw[:, :, :, 0].permute(2, 0, 1).unsqueeze(1), None, padding=1, groups=MID)
+        h = F.leaky_relu(conv1x1(h, p[f"res{i}_pw"], p[f"res{i}_b1"]), LRELU)
+        h = conv1x1(h, p[f"res{i}_w2"], p[f"res{i}_b2"])
+        x = F.leaky_relu(h + x, LRELU)
+    tower = x.permute(0, 2, 3, 1).reshape(B, CELLS, CH)
+    fc0 = F.leaky_relu(tower.reshape(B, CELLS * CH) @ p["fc0_w"] + p["fc0_b"], LRELU)
+    fc1 = F.leaky_relu(fc0 @ p["fc1_w"] + p["fc1_b"], LRELU)
+    vlogit = (fc1 @ p["v_w"] + p["v_b"]).reshape(B)
+    logits = fc1 @ p["p_w"] + p["p_b"]
+    out = {"tower": tower, "fc0": fc0, "fc1": fc1, "logits": logits, "vlogit": vlogit,
+           "P": torch.softmax(logits, dim=1), "V": torch.tanh(vlogit)}
+    return {k: v.numpy() for k, v in out.items()}
+
+
 def forward_boards(params, boards: np.ndarray, turns: np.ndarray, opponent_mode: bool = False, dtype=torch.float32):
     imgs = np.stack([encode_image(b, int(t), opponent_mode) for b, t in zip(boards, turns)])
     return forward(params, imgs, dtype)

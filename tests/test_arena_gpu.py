@@ -46,3 +46,126 @@ def test_batched_evaluation_play_accounts_for_every_game(omk, arena):
     assert lw + rw + dr == games
     for c in (ctx, left, right):
         c.close()
+
+
+def _oracle_naive_move(orc, env, rng):
+    """trainer.rs:506-537 restated on the oracle's environment: the first legal action (ascending) that ends the game for
+    the mover, or that would end it for the opponent; otherwise a uniformly random legal move."""
+    import ctypes as C
+
+    def clone(flip_turn):
+        e = orc.Environment()
+        C.memmove(C.byref(e.e), C.byref(env), C.sizeof(env))
+        if flip_turn:
+            e.e.turn = 1 - e.e.turn
+        return e
+
+    legal = [a for a in range(81) if env.board[a] == 0]
+    for a in legal:
+        if clone(False).place_stone(a) != 0 or clone(True).place_stone(a) != 0:  # GameStatus::is_terminal
+            return a
+    return legal[rng.integers(0, len(legal))]
+
+
+def test_play_against_naive_player_matches_oracle_loop(omk, orc, arena):
+    """The whole evaluation loop (src/trainer.rs:487-603) against the oracle: same W/L/D and the same move lists, game by
+    game, with the exact hash evaluator and the same generator for the naive player's random moves."""
+    games, count, batch, eps, alpha, seed, rseed = 10, 64, 16, 0.25, 0.03, 11, 5
+    ctx = omk.Context(device=0, capacity_envs=162 * games, capacity_trees=games, capacity_nodes=2048, seed=seed)
+    moves = []
+    got = arena.play_against_naive_player(ctx, episode_count=games, count=count, batch_size=batch, epsilon=eps, alpha=alpha,
+                                          evaluator=omk.EVAL_HASH, seed=rseed, moves_out=moves)
+    ctx.close()
+    ev = orc.NativeHashEvaluator()
+    rng = np.random.default_rng(rseed)
+    agents = {g: orc.Agent(ev, seed, g) for g in range(games)}
+    want_moves = [[] for _ in range(games)]
+    tally = {1: 0, 2: 0, 3: 0}
+    live = list(range(games))
+    while live:
+        nxt = []
+        for g in live:
+            a = _oracle_naive_move(orc, agents[g].env, rng)
+            want_moves[g].append(a)
+            agents[g].ensure_action_exists(a, ev)
+            st = agents[g].play_action(a)
+            if st == 0:
+                nxt.append(g)
+            else:
+                tally[st] += 1
+        live = nxt
+        if not live:
+            break
+        orc.execute([agents[g] for g in live], count, batch, eps, alpha, ev)
+        nxt = []
+        for g in live:
+            a, _ = agents[g].sample_action(0)
+            want_moves[g].append(a)
+            st = agents[g].play_action(a)
+            if st == 0:
+                nxt.append(g)
+            else:
+                tally[st] += 1
+        live = nxt
+    assert moves == want_moves
+    assert got == (tally[2], tally[3], tally[1])
+
+
+def test_play_match_matches_oracle_loop(omk, orc, arena):
+    """benchmark/src/main.rs:14-108 against the oracle: two agents per game (one per model), MCTSExecutor::run(count, batch,
+    eps 0, alpha 1) + Best for the mover, ensure_action_exists + play_action for the other; move lists and result."""
+    games, count, batch = 6, 48, 8
+    half = games // 2
+    seeds = (21, 22)
+    left = omk.Context(device=0, capacity_envs=1, capacity_trees=half, capacity_nodes=2048, seed=seeds[0])
+    right = omk.Context(device=0, capacity_envs=1, capacity_trees=half, capacity_nodes=2048, seed=seeds[1])
+    moves = []
+    got = arena.play_match(left, right, game_count=games, count=count, batch_size=batch, evaluator=omk.EVAL_HASH, moves_out=moves)
+    left.close()
+    right.close()
+    ev = orc.NativeHashEvaluator()
+    want_moves = []
+    wins = {0: 0, 1: 0, "draw": 0}  # 0 = left, 1 = right
+    for leg in range(2):
+        first, second = (0, 1) if leg == 0 else (1, 0)
+        ag = {side: [orc.Agent(ev, seeds[side], g) for g in range(half)] for side in (0, 1)}
+        logs = [[] for _ in range(half)]
+        live = list(range(half))
+        mover, other = first, second
+        while live:
+            orc.execute([ag[mover][g] for g in live], count, batch, 0.0, 1.0, ev)
+            nxt = []
+            for g in live:
+                a, _ = ag[mover][g].sample_action(0)
+                logs[g].append(a)
+                st = ag[mover][g].play_action(a)
+                if st >= 2:
+                    wins[mover] += 1
+                elif st == 1:
+                    wins["draw"] += 1
+                else:
+                    ag[other][g].ensure_action_exists(a, ev)
+                    assert ag[other][g].play_action(a) == 0
+                    nxt.append(g)
+            live = nxt
+            mover, other = other, mover
+        want_moves += logs
+    assert moves == want_moves
+    assert got == (wins[0], wins[1], wins["draw"])
+
+
+def test_pool_get_envs_matches_single_tree_reads(omk):
+    ctx = omk.Context(device=0, capacity_envs=1, capacity_trees=16, capacity_nodes=256, seed=3)
+    ctx.pool_new_games(n=16, evaluator=omk.EVAL_HASH)
+    ctx.pool_search(n=16, count=32, batch_size=8, epsilon=0.0, alpha=1.0, evaluator=omk.EVAL_HASH)
+    acts, _ = ctx.pool_sample(n=16, modes=np.zeros(16, np.uint8))
+    ctx.pool_play(acts)
+    ids = np.array([5, 0, 15, 7], np.int32)
+    boards, turns, legal, status = ctx.pool_get_envs(ids=ids)
+    for k, t in enumerate(ids):
+        b, tu, lg = ctx.pool_get_env(int(t))
+        assert np.array_equal(boards[k], b) and turns[k] == tu and legal[k] == lg and status[k] == 0
+        assert b[acts[t]] == 1 and lg == 80
+    with pytest.raises(omk.OmkError):
+        ctx.pool_get_envs(ids=[1, 1])  # ids of one call must be unique
+    ctx.close()
