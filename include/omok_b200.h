@@ -100,6 +100,34 @@ OMK_API int32_t omk_net_eval(omk_ctx *ctx, const uint8_t *boards, const uint8_t 
  * (alpha-zero/src/encoder.rs:10-46; any float values, not only {0,1}).          */
 OMK_API int32_t omk_net_eval_images(omk_ctx *ctx, const float *images, int32_t n, float *out_p, float *out_v);
 
+/* ---------------------------------------------------------------- trainer step
+ * Replaces AgentModel::train (alpha-zero/src/agent_model.rs:136-168) and the training half of AgentModel::new's graph
+ * (:26-103; network.rs:249-253): loss = mean((z - v)^2) + mean(softmax_cross_entropy_with_logits(logits, pi)),
+ * tensorflow AdadeltaOptimizer with learning rate 0.01 (:24), rho 0.95, epsilon 1e-8 (the crate's defaults; the two
+ * accumulators live in the context and, as in the reference, are never saved), one minimize step, then a SECOND forward
+ * that reports the losses.  images[n*243] = encode_nn_input's tensor, pi[n*81] = encode_nn_targets' policy target,
+ * z[n] = its value target (alpha-zero/src/encoder.rs:10-68); out_losses[3] = {p_loss, v_loss, loss} after the update.
+ * The updated weights are live for omk_net_eval / the searches when the call returns (a running self-play driver's
+ * cached root prior is refreshed too).  fp32 CUDA kernels; correctness path, not the self-play hot path.             */
+OMK_API int32_t omk_train_step(omk_ctx *ctx, const float *images, const float *pi, const float *z, int32_t n, float *out_losses);
+/* The same step in two halves, for callers that average the gradient themselves (data parallelism, BASELINE config 5):
+ * omk_train_backward leaves the gradient of the local minibatch's mean loss in one flat DEVICE buffer (*out_count =
+ * 5 643 250 floats, the 31 tensors in checkpoint order) and returns with the stream idle; omk_train_apply runs the
+ * all-reduce of an attached communicator (below), Adadelta, the weight re-pack and the reporting forward.             */
+OMK_API int32_t omk_train_backward(omk_ctx *ctx, const float *images, const float *pi, const float *z, int32_t n,
+                           void **out_grads_device, int64_t *out_count);
+OMK_API int32_t omk_train_apply(omk_ctx *ctx, float *out_losses);
+/* host copy of the last gradient, per tensor in checkpoint order (tests); zero the Adadelta accumulators */
+OMK_API int32_t omk_train_get_grads(omk_ctx *ctx, float *const *tensors, const int64_t *lens);
+OMK_API int32_t omk_train_reset_optimizer(omk_ctx *ctx);
+/* Optional NCCL communicator for the gradient all-reduce (one rank per context / GPU; NVLink 5 / NVSwitch on a B200
+ * box).  libnccl.so.2 is loaded with dlopen on first use (env OMK_NCCL_LIB overrides the name): rank 0 calls
+ * omk_train_comm_unique_id and distributes the 128 bytes, every rank calls omk_train_comm_init; from then on
+ * omk_train_apply / omk_train_step sum the gradients (and the reported losses) over the ranks and divide by nranks.   */
+OMK_API int32_t omk_train_comm_unique_id(omk_ctx *ctx, uint8_t *out_id);
+OMK_API int32_t omk_train_comm_init(omk_ctx *ctx, const uint8_t *id, int32_t nranks, int32_t rank);
+OMK_API int32_t omk_train_comm_destroy(omk_ctx *ctx);
+
 /* ---------------------------------------------------------------- diagnostics (tests / A-B runs)
  * Kernel choice for fc0 + fc1 + heads, and for the tower: 1 = the tcgen05 kernels (3-pass fp16 hi/lo split; the product
  * path and the default), 0 = the fp32 CUDA-core kernels kept in the library as an A/B check of each layer (env

@@ -103,6 +103,14 @@ def load_library():
     L.omk_net_init_random.argtypes = [vp, u64]
     L.omk_net_eval.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.omk_net_eval_images.argtypes = [vp, vp, i32, vp, vp]
+    L.omk_train_step.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.omk_train_backward.argtypes = [vp, vp, vp, vp, i32, P(vp), P(i64)]
+    L.omk_train_apply.argtypes = [vp, vp]
+    L.omk_train_get_grads.argtypes = [vp, P(vp), P(i64)]
+    L.omk_train_reset_optimizer.argtypes = [vp]
+    L.omk_train_comm_unique_id.argtypes = [vp, vp]
+    L.omk_train_comm_init.argtypes = [vp, vp, i32, i32]
+    L.omk_train_comm_destroy.argtypes = [vp]
     L.omk_debug_set_fc0_mode.argtypes = [vp, i32]
     L.omk_debug_set_tower_mode.argtypes = [vp, i32]
     L.omk_debug_set_lane_min_trees.argtypes = [vp, i32]
@@ -216,6 +224,56 @@ class Context:
         v = np.zeros(n, dtype=np.float32) if want_v else None
         self._check(self.L.omk_net_eval_images(self.h, _ptr(images), n, _ptr(p), _ptr(v)))
         return p, v
+
+    # ---- trainer step (AgentModel::train) ----
+    @staticmethod
+    def _batch(images, pi, z):
+        images = np.ascontiguousarray(images, dtype=np.float32).reshape(-1, 243)
+        n = images.shape[0]
+        pi = np.ascontiguousarray(pi, dtype=np.float32).reshape(n, CELLS)
+        z = np.ascontiguousarray(z, dtype=np.float32).reshape(n)
+        return images, pi, z, n
+
+    def train_step(self, images, pi, z):
+        """One Adadelta step + the reporting forward: (p_loss, v_loss, loss) after the update."""
+        images, pi, z, n = self._batch(images, pi, z)
+        out = np.zeros(3, dtype=np.float32)
+        self._check(self.L.omk_train_step(self.h, _ptr(images), _ptr(pi), _ptr(z), n, _ptr(out)))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def train_backward(self, images, pi, z):
+        """Gradient of the local minibatch's mean loss: (device pointer of the flat buffer, element count)."""
+        images, pi, z, n = self._batch(images, pi, z)
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        self._check(self.L.omk_train_backward(self.h, _ptr(images), _ptr(pi), _ptr(z), n, C.byref(ptr), C.byref(cnt)))
+        return int(ptr.value or 0), int(cnt.value)
+
+    def train_apply(self):
+        out = np.zeros(3, dtype=np.float32)
+        self._check(self.L.omk_train_apply(self.h, _ptr(out)))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def train_get_grads(self):
+        arrs = [np.zeros(n, dtype=np.float32) for n in NET_LENS]
+        ptrs = (C.c_void_p * 31)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_int64 * 31)(*NET_LENS)
+        self._check(self.L.omk_train_get_grads(self.h, ptrs, lens))
+        return [a.reshape(s) for a, s in zip(arrs, NET_SHAPES)]
+
+    def train_reset_optimizer(self):
+        self._check(self.L.omk_train_reset_optimizer(self.h))
+
+    def train_comm_unique_id(self) -> bytes:
+        buf = np.zeros(128, dtype=np.uint8)
+        self._check(self.L.omk_train_comm_unique_id(self.h, _ptr(buf)))
+        return buf.tobytes()
+
+    def train_comm_init(self, unique_id: bytes, nranks: int, rank: int):
+        buf = np.frombuffer(unique_id, dtype=np.uint8).copy()
+        self._check(self.L.omk_train_comm_init(self.h, _ptr(buf), nranks, rank))
+
+    def train_comm_destroy(self):
+        self._check(self.L.omk_train_comm_destroy(self.h))
 
     def debug_set_fc0_mode(self, mode: int):
         self._check(self.L.omk_debug_set_fc0_mode(self.h, mode))

@@ -326,6 +326,7 @@ extern "C" int32_t omk_ctx_destroy(omk_ctx *c) {
                     c->net.fc1_wt_h16, c->net.fc1_wt_l16, c->net.fc_inv_scale, c->net.fc_absmax, c->net.tower16_wimg,
                     c->net.tower16_pimg, c->net.tower16_absmax};
     fc16_free(c);
+    train_free(c);
     for (omk_ctx::Scratch &sc : c->scratch) cudaFree(sc.p);
     free(c->tower16_params_host);
     if (c->lane1_stream) {
@@ -448,6 +449,91 @@ extern "C" int32_t omk_net_eval_images(omk_ctx *c, const float *images, int32_t 
     const uint32_t nn = (uint32_t)n;
     CK(cudaMemcpyAsync(c->ws.n_req, &nn, sizeof nn, cudaMemcpyHostToDevice, c->stream));
     return net_eval_common(c, n, d_img, out_p, out_v);
+}
+
+// ------------------------------------------------------------------ trainer step (AgentModel::train)
+// after the optimizer changed the fp32 tensors: re-pack the heads, re-split the tensor-core operands, refresh the
+// self-play driver's cached root prior -- exactly what omk_net_load_params does after its copies
+static int32_t weights_changed(omk_ctx *c) {
+    net_pack_heads(c);
+    if (!fc16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split fc weight preparation failed");
+    if (!tower16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split tower weight preparation failed");
+    CK(cudaStreamSynchronize(c->stream));
+    return sp_refresh_root_policy(c);
+}
+
+extern "C" int32_t omk_train_backward(omk_ctx *c, const float *images, const float *pi, const float *z, int32_t n,
+                                      void **out_grads_device, int64_t *out_count) {
+    CK(cudaSetDevice(c->device));
+    if (!c->net.loaded) return fail(OMK_ERR_STATE, "network weights not loaded");
+    if (n < 1 || !images || !pi || !z) return fail(OMK_ERR_INVALID, "bad arguments");
+    float *g = nullptr;
+    c->train_n = 0;
+    if (const char *e = train_backward_step(c, images, pi, z, n, &g)) return fail(OMK_ERR_CUDA, std::string("omk_train_backward: ") + e);
+    CK(cudaStreamSynchronize(c->stream));  // the caller may all-reduce the gradient buffer on its own stream
+    CK(cudaGetLastError());
+    c->train_n = n;
+    if (out_grads_device) *out_grads_device = g;
+    if (out_count) *out_count = 5643250;
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_train_apply(omk_ctx *c, float *out_losses) {
+    CK(cudaSetDevice(c->device));
+    if (c->train_n < 1) return fail(OMK_ERR_STATE, "omk_train_backward has not produced a gradient");
+    if (const char *e = train_apply_step(c)) return fail(OMK_ERR_CUDA, std::string("omk_train_apply: ") + e);
+    int32_t rc = weights_changed(c);
+    if (rc) return rc;
+    float l[3] = {0, 0, 0};
+    if (const char *e = train_report_losses(c, c->train_n, l)) return fail(OMK_ERR_CUDA, std::string("omk_train_apply: ") + e);
+    c->train_n = 0;  // one gradient, one update
+    if (!(l[2] == l[2]) || l[2] > 3.0e38f) return fail(OMK_ERR_NUMERIC, "the training loss is not finite");
+    if (out_losses) memcpy(out_losses, l, sizeof l);
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_train_step(omk_ctx *c, const float *images, const float *pi, const float *z, int32_t n, float *out_losses) {
+    int32_t rc = omk_train_backward(c, images, pi, z, n, nullptr, nullptr);
+    if (rc) return rc;
+    return omk_train_apply(c, out_losses);
+}
+
+extern "C" int32_t omk_train_get_grads(omk_ctx *c, float *const *tensors, const int64_t *lens) {
+    CK(cudaSetDevice(c->device));
+    const float *g = train_grad_buffer(c);
+    if (!g) return fail(OMK_ERR_STATE, "omk_train_backward has not run");
+    long long off = 0;
+    for (int i = 0; i < kNetTensors; ++i) {
+        if (!tensors[i] || lens[i] != kLens[i]) return fail(OMK_ERR_INVALID, "bad tensor length");
+        CK(cudaMemcpyAsync(tensors[i], g + off, sizeof(float) * (size_t)kLens[i], cudaMemcpyDeviceToHost, c->stream));
+        off += kLens[i];
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_train_reset_optimizer(omk_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    train_reset_optimizer(c);
+    CK(cudaStreamSynchronize(c->stream));
+    return OMK_OK;
+}
+
+extern "C" int32_t omk_train_comm_unique_id(omk_ctx *c, uint8_t *out_id) {
+    if (!out_id) return fail(OMK_ERR_INVALID, "out_id is NULL");
+    if (const char *e = train_comm_unique_id(c, out_id)) return fail(OMK_ERR_STATE, std::string("NCCL: ") + e);
+    return OMK_OK;
+}
+extern "C" int32_t omk_train_comm_init(omk_ctx *c, const uint8_t *id, int32_t nranks, int32_t rank) {
+    CK(cudaSetDevice(c->device));
+    if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(OMK_ERR_INVALID, "bad communicator arguments");
+    if (const char *e = train_comm_init(c, id, nranks, rank)) return fail(OMK_ERR_STATE, std::string("NCCL: ") + e);
+    return OMK_OK;
+}
+extern "C" int32_t omk_train_comm_destroy(omk_ctx *c) {
+    CK(cudaSetDevice(c->device));
+    train_comm_destroy(c);
+    return OMK_OK;
 }
 
 // ------------------------------------------------------------------ diagnostics

@@ -103,6 +103,8 @@ struct omk_ctx {
     void *fc16_state = nullptr;     // tensor maps of the fp16-split path (fc_f16.cu)
     int tower16_pairs = 0;          // resident CTA pairs of k_tower16 (0 = not queried yet)
     void *tower16_params_host = nullptr;  // host copy of the tower's fp32 parameter image (kernel argument of k_tower16)
+    void *train_state = nullptr;    // trainer step workspace, Adadelta slots, optional NCCL communicator (train_kernels.cu)
+    int train_n = 0;                // positions of the minibatch currently on the device (omk_train_backward)
     int tower_mode = 1;             // tower: 1 = tcgen05 3xFP16 k_tower16 (the product path), 0 = fp32 CUDA-core k_tower (A/B check only)
 
     // self-play driver state
@@ -183,6 +185,17 @@ void fc16_free(omk_ctx *c);
 bool fc16_tower_store_maps(omk_ctx *c, const void **map_hi, const void **map_lo);
 void launch_f32_to_split16(omk_ctx *c, const float *x, __half *hi, __half *lo, long long n);
 void launch_split16_to_f32(omk_ctx *c, const __half *hi, const __half *lo, float *x, long long n);
+
+// train_kernels.cu: every function returns nullptr on success or a message
+const char *train_backward_step(omk_ctx *c, const float *images, const float *pi, const float *z, int n, float **grads_dev);
+const char *train_apply_step(omk_ctx *c);
+const char *train_report_losses(omk_ctx *c, int n, float *out3);
+float *train_grad_buffer(omk_ctx *c);
+void train_reset_optimizer(omk_ctx *c);
+void train_free(omk_ctx *c);
+const char *train_comm_unique_id(omk_ctx *c, uint8_t *out128);
+const char *train_comm_init(omk_ctx *c, const uint8_t *id128, int nranks, int rank);
+const char *train_comm_destroy(omk_ctx *c);
 
 // tower_f16.cu
 bool tower16_prepare_weights(omk_ctx *c);

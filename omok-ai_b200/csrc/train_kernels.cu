@@ -1,0 +1,604 @@
+// train_kernels.cu -- the trainer's gradient step behind the C ABI (omk_train_step): AgentModel::train of the reference
+// (alpha-zero/src/agent_model.rs:26-103,136-168) as plain fp32 CUDA kernels.
+//
+//   loss   = mean((z - v)^2) over axes [0,1]  +  mean(softmax_cross_entropy_with_logits(logits, pi)) over axis 0
+//            (agent_model.rs:60-73, network.rs:249-253)
+//   update = tensorflow::train::AdadeltaOptimizer, learning rate 0.01 (agent_model.rs:24,75-83), rho 0.95 and
+//            epsilon 1e-8 (the crate's defaults) == the ApplyAdadelta op:
+//                accum        = rho * accum + (1 - rho) * g^2
+//                update       = sqrt(accum_update + eps) / sqrt(accum + eps) * g
+//                var         -= lr * update
+//                accum_update = rho * accum_update + (1 - rho) * update^2
+//   train() = one minimize step, then a SECOND forward that reports (p_loss, v_loss, loss) (agent_model.rs:150-167).
+//
+// This is NOT the self-play hot path: an iteration runs 600 steps of 128 positions against ~10^8 network evaluations
+// of self-play, so the kernels here are written for correctness and determinism (fp32 everywhere, fixed summation
+// orders, no atomics), not for the tensor cores: one generic tiled GEMM with transposes and fused epilogues, the
+// depthwise forward / data-gradient / weight-gradient kernels, column sums, the loss, and the optimizer.
+// Data parallelism (BASELINE config 5): the flat gradient (5 643 250 floats, 22.6 MB) is all-reduced over NCCL when a
+// communicator is attached (omk_train_comm_init; libnccl is loaded with dlopen, the library has no link dependency on
+// it) or handed to the caller between omk_train_backward and omk_train_apply.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+
+#include "omk_internal.h"
+
+namespace omk {
+
+constexpr int kTP = 128, kTM = 32, kTF = 512, kTFlat = kCells * kTP;  // channels, bottleneck width, fc width, 10368
+constexpr float kTLrelu = 0.2f;  // TensorFlow LeakyRelu default alpha
+
+static const long long kTLen[kNetTensors] = {
+    384, 128,
+    4096, 32, 288, 1024, 32, 4096, 128,
+    4096, 32, 288, 1024, 32, 4096, 128,
+    4096, 32, 288, 1024, 32, 4096, 128,
+    (long long)kTFlat * kTF, kTF, kTF * kTF, kTF, kTF, 1, kTF * kCells, kCells};
+constexpr long long kTParams = 5643250;
+
+// ---------------------------------------------------------------------------------------------------------------
+// C[M,N] = epilogue( op(A) . op(B) ), fp32, 64x64x16 tiles, 256 threads, 4x4 outputs per thread.
+//   TA: A is stored [K,M] (row-major) and read transposed; TB: B is stored [N,K].
+//   epilogue: (+ bias[n]) (+ res[m,n]) (lrelu if act) (* lrelu'(gate[m,n]) if gate) (+ C if accumulate)
+// K is walked in order by one CTA per output tile: the summation order of an output element is fixed.
+// ---------------------------------------------------------------------------------------------------------------
+struct GemmEpi {
+    const float *bias = nullptr;  // [N]
+    const float *res = nullptr;   // [M,N], leading dimension ldc
+    const float *gate = nullptr;  // [M,N], leading dimension ldc: multiply by (gate > 0 ? 1 : 0.2)
+    int act = 0;                  // lrelu on the result
+    int accumulate = 0;           // C += result
+};
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+    k_tgemm(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C, int M, int N, int K, int lda, int ldb,
+            int ldc, GemmEpi e) {
+    __shared__ float As[16][64 + 1];
+    __shared__ float Bs[16][64 + 1];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        // stage a 64 x 16 slice of op(A) and a 16 x 64 slice of op(B); out-of-range elements are zeros
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = t + 256 * i;  // 0..1023
+            int m, k;
+            if (TA) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.0f;
+            if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            As[k][m] = v;
+            int n, kb;
+            if (TB) { kb = idx & 15; n = idx >> 4; } else { n = idx & 63; kb = idx >> 6; }
+            const int gn = n0 + n, gkb = k0 + kb;
+            float w = 0.0f;
+            if (gn < N && gkb < K) w = TB ? B[(size_t)gn * ldb + gkb] : B[(size_t)gkb * ldb + gn];
+            Bs[kb][n] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            const size_t o = (size_t)m * ldc + n;
+            if (e.bias) v += e.bias[n];
+            if (e.res) v += e.res[o];
+            if (e.act) v = v > 0.0f ? v : kTLrelu * v;
+            if (e.gate) v *= e.gate[o] > 0.0f ? 1.0f : kTLrelu;
+            if (e.accumulate) v += C[o];
+            C[o] = v;
+        }
+    }
+}
+
+template <bool TA, bool TB>
+static void tgemm(cudaStream_t s, const float *A, const float *B, float *C, int M, int N, int K, int lda, int ldb, int ldc,
+                  const GemmEpi &e) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    k_tgemm<TA, TB><<<grid, 256, 0, s>>>(A, B, C, M, N, K, lda, ldb, ldc, e);
+}
+
+// out[n] = sum over m of X[m, n] in a fixed order: one block per 32 columns, 8 row groups, sequential within a group,
+// groups added in order
+__global__ void k_colsum(const float *__restrict__ X, int M, int N, int ld, float *__restrict__ out) {
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+    float s = 0.0f;
+    if (c < N)
+        for (int m = g; m < M; m += 8) s += X[(size_t)m * ld + c];
+    part[g][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (g == 0 && c < N) {
+        float tot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += part[i][threadIdx.x & 31];
+        out[c] = tot;
+    }
+}
+
+// depthwise 3x3, SAME zero padding, stride 1, no bias (network-utils lib.rs:204-216) on [n][81][32]; dw is [3][3][32]
+// forward: out[p][c] = sum_tap in[p + tap][c] * dw[tap][c]
+// data gradient (flip = 1): din[q][c] = sum_tap dout[q - tap][c] * dw[tap][c]
+__global__ void k_dw(const float *__restrict__ in, const float *__restrict__ dw, float *__restrict__ out, int n, int flip,
+                     const float *__restrict__ gate) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n * kCells * kTM;
+    if (idx >= total) return;
+    const int c = (int)(idx & 31);
+    const int p = (int)((idx >> 5) % kCells);
+    const long long b = (idx >> 5) / kCells;
+    const int y = p / kSide, x = p % kSide;
+    const float *src = in + b * kCells * kTM;
+    float acc = 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int yy = flip ? y - (ky - 1) : y + (ky - 1), xx = flip ? x - (kx - 1) : x + (kx - 1);
+            if (yy < 0 || yy >= kSide || xx < 0 || xx >= kSide) continue;
+            acc = fmaf(src[(yy * kSide + xx) * kTM + c], dw[(ky * 3 + kx) * kTM + c], acc);
+        }
+    }
+    if (gate) acc *= gate[idx] > 0.0f ? 1.0f : kTLrelu;
+    out[idx] = acc;
+}
+// weight gradient: ddw[tap][c] = sum over positions b and pixels p of in[b][p + tap][c] * dout[b][p][c]
+// one block per tap (9), 32 channels x 8 position groups; groups added in order
+__global__ void k_dw_wgrad(const float *__restrict__ in, const float *__restrict__ dout, float *__restrict__ ddw, int n) {
+    __shared__ float part[8][33];
+    const int tap = blockIdx.x, ky = tap / 3, kx = tap % 3;
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    float s = 0.0f;
+    for (int b = g; b < n; b += 8) {
+        const float *ip = in + (size_t)b * kCells * kTM, *dp = dout + (size_t)b * kCells * kTM;
+        for (int p = 0; p < kCells; ++p) {
+            const int y = p / kSide + ky - 1, x = p % kSide + kx - 1;
+            if (y < 0 || y >= kSide || x < 0 || x >= kSide) continue;
+            s = fmaf(ip[(y * kSide + x) * kTM + c], dp[p * kTM + c], s);
+        }
+    }
+    part[g][c] = s;
+    __syncthreads();
+    if (g == 0) {
+        float tot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += part[i][c];
+        ddw[tap * kTM + c] = tot;
+    }
+}
+
+// elementwise: y = x * lrelu'(gate)
+__global__ void k_lrelu_bwd(const float *__restrict__ x, const float *__restrict__ gate, float *__restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = x[i] * (gate[i] > 0.0f ? 1.0f : kTLrelu);
+}
+
+// per position: softmax cross entropy with the visit policy, squared value error, and their logit gradients for the
+// MEAN losses (1/n folded in).  row_loss[2*i] = policy term, [2*i+1] = value term.
+__global__ void k_loss(const float *__restrict__ logits /*[n][81]*/, const float *__restrict__ vlogit /*[n]*/, const float *__restrict__ pi,
+                       const float *__restrict__ z, int n, float *__restrict__ dlogits, float *__restrict__ dvlogit,
+                       float *__restrict__ row_loss) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float *l = logits + (size_t)row * kCells, *t = pi + (size_t)row * kCells;
+    float v[3], tv[3], mx = -INFINITY, tsum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int c = lane + 32 * j;
+        v[j] = c < kCells ? l[c] : -INFINITY;
+        tv[j] = c < kCells ? t[c] : 0.0f;
+        mx = fmaxf(mx, v[j]);
+        tsum += tv[j];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        tsum += __shfl_xor_sync(0xffffffffu, tsum, off);
+    }
+    float ex[3], s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        ex[j] = (lane + 32 * j) < kCells ? expf(v[j] - mx) : 0.0f;
+        s += ex[j];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float lse = mx + logf(s), inv = 1.0f / s, invn = 1.0f / (float)n;
+    float pl = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int c = lane + 32 * j;
+        if (c < kCells) {
+            pl -= tv[j] * (v[j] - lse);
+            if (dlogits) dlogits[(size_t)row * kCells + c] = (ex[j] * inv * tsum - tv[j]) * invn;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) pl += __shfl_xor_sync(0xffffffffu, pl, off);
+    if (lane == 0) {
+        const float val = tanhf(vlogit[row]), d = val - z[row];
+        row_loss[2 * row] = pl;
+        row_loss[2 * row + 1] = d * d;
+        if (dvlogit) dvlogit[row] = 2.0f * d * (1.0f - val * val) * invn;
+    }
+}
+// (p_loss, v_loss, loss) = means over the rows, summed in row order by one thread per term (n is a minibatch)
+__global__ void k_loss_reduce(const float *__restrict__ row_loss, int n, float *__restrict__ out3) {
+    if (threadIdx.x < 2) {
+        float s = 0.0f;
+        for (int i = 0; i < n; ++i) s += row_loss[2 * i + threadIdx.x];
+        out3[threadIdx.x] = s / (float)n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out3[2] = out3[0] + out3[1];
+}
+
+__global__ void k_scale(float *x, long long n, float f) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= f;
+}
+
+// tensorflow ApplyAdadelta (see the header of this file)
+__global__ void k_adadelta(float *__restrict__ var, float *__restrict__ accum, float *__restrict__ accum_update, const float *__restrict__ g,
+                           long long n, float lr, float rho, float eps) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i];
+    const float a = rho * accum[i] + (1.0f - rho) * gi * gi;
+    const float upd = sqrtf(accum_update[i] + eps) * (1.0f / sqrtf(a + eps)) * gi;
+    accum[i] = a;
+    var[i] -= lr * upd;
+    accum_update[i] = rho * accum_update[i] + (1.0f - rho) * upd * upd;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct TrainState {
+    int cap_n = 0;  // positions the workspace is sized for
+    float *img = nullptr, *pi = nullptr, *z = nullptr;
+    float *x[4] = {};                      // residual stream after the stem and after each block: [n*81][128]
+    float *h0[3] = {}, *hd[3] = {}, *h1[3] = {};  // per block: conv0 out, depthwise out, pointwise out: [n*81][32]
+    float *a0 = nullptr, *a1 = nullptr;    // fc0 / fc1 outputs [n][512]
+    float *logits = nullptr, *vlogit = nullptr;
+    float *dx = nullptr, *dy = nullptr;    // [n*81][128] gradient of the residual stream / of a block's pre-activation sum
+    float *d32a = nullptr, *d32b = nullptr;  // [n*81][32]
+    float *da0 = nullptr, *da1 = nullptr, *dlogits = nullptr, *dvlogit = nullptr, *row_loss = nullptr;
+    float *losses = nullptr;               // [3] device
+    float *grads = nullptr;                // flat [kTParams] in checkpoint order
+    float *accum = nullptr, *accum_update = nullptr;  // Adadelta slots, flat
+    long long off[kNetTensors + 1] = {};
+    long long steps = 0;
+    // NCCL (optional, loaded with dlopen)
+    void *nccl_lib = nullptr, *comm = nullptr;
+    int world = 1, rank = 0;
+    int (*p_allreduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*p_comm_init_rank)(void **, int, const void * /* ncclUniqueId by value: 128 bytes */, int) = nullptr;
+    int (*p_comm_destroy)(void *) = nullptr;
+    const char *(*p_err)(int) = nullptr;
+};
+struct NcclUniqueId { char internal[128]; };
+
+static TrainState *train_state(omk_ctx *c) {
+    if (!c->train_state) {
+        TrainState *t = new TrainState();
+        long long o = 0;
+        for (int i = 0; i < kNetTensors; ++i) {
+            t->off[i] = o;
+            o += kTLen[i];
+        }
+        t->off[kNetTensors] = o;
+        c->train_state = t;
+    }
+    return reinterpret_cast<TrainState *>(c->train_state);
+}
+
+static bool talloc(float **p, size_t count) {
+    cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc(p, sizeof(float) * (count ? count : 1)) == cudaSuccess;
+}
+
+static bool train_ensure(omk_ctx *c, TrainState *t, int n) {
+    if (!t->grads) {
+        if (!talloc(&t->grads, kTParams) || !talloc(&t->accum, kTParams) || !talloc(&t->accum_update, kTParams) || !talloc(&t->losses, 4))
+            return false;
+        cudaMemsetAsync(t->accum, 0, sizeof(float) * kTParams, c->stream);
+        cudaMemsetAsync(t->accum_update, 0, sizeof(float) * kTParams, c->stream);
+    }
+    if (n <= t->cap_n) return true;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+    const size_t N = (size_t)n, M = N * kCells;
+    bool ok = talloc(&t->img, N * 243) && talloc(&t->pi, N * kCells) && talloc(&t->z, N);
+    for (int i = 0; i < 4; ++i) ok = ok && talloc(&t->x[i], M * kTP);
+    for (int r = 0; r < 3; ++r) ok = ok && talloc(&t->h0[r], M * kTM) && talloc(&t->hd[r], M * kTM) && talloc(&t->h1[r], M * kTM);
+    ok = ok && talloc(&t->a0, N * kTF) && talloc(&t->a1, N * kTF) && talloc(&t->logits, N * kCells) && talloc(&t->vlogit, N) &&
+         talloc(&t->dx, M * kTP) && talloc(&t->dy, M * kTP) && talloc(&t->d32a, M * kTM) && talloc(&t->d32b, M * kTM) &&
+         talloc(&t->da0, N * kTF) && talloc(&t->da1, N * kTF) && talloc(&t->dlogits, N * kCells) && talloc(&t->dvlogit, N) &&
+         talloc(&t->row_loss, 2 * N);
+    t->cap_n = ok ? n : 0;
+    return ok;
+}
+
+void train_free(omk_ctx *c) {
+    if (!c->train_state) return;
+    TrainState *t = reinterpret_cast<TrainState *>(c->train_state);
+    if (t->comm && t->p_comm_destroy) t->p_comm_destroy(t->comm);
+    float *all[] = {t->img, t->pi, t->z, t->x[0], t->x[1], t->x[2], t->x[3], t->h0[0], t->h0[1], t->h0[2], t->hd[0], t->hd[1], t->hd[2],
+                    t->h1[0], t->h1[1], t->h1[2], t->a0, t->a1, t->logits, t->vlogit, t->dx, t->dy, t->d32a, t->d32b, t->da0, t->da1,
+                    t->dlogits, t->dvlogit, t->row_loss, t->losses, t->grads, t->accum, t->accum_update};
+    for (float *p : all) cudaFree(p);
+    if (t->nccl_lib) dlclose(t->nccl_lib);
+    delete t;
+    c->train_state = nullptr;
+}
+
+// tensor indices in checkpoint order
+enum { T_CONV_W = 0, T_CONV_B = 1, T_BLK0 = 2, T_FC0_W = 23, T_FC0_B = 24, T_FC1_W = 25, T_FC1_B = 26, T_V_W = 27, T_V_B = 28, T_P_W = 29, T_P_B = 30 };
+enum { B_W0 = 0, B_B0 = 1, B_DW = 2, B_PW = 3, B_B1 = 4, B_W2 = 5, B_B2 = 6 };
+
+// the reference network in fp32, keeping every layer the backward pass needs (network.rs:51-262)
+static void train_forward(omk_ctx *c, TrainState *t, int n) {
+    cudaStream_t s = c->stream;
+    float *const *W = c->net.t;
+    const int M = n * kCells;
+    GemmEpi e;
+    e.bias = W[T_CONV_B];
+    e.act = 1;
+    tgemm<false, false>(s, t->img, W[T_CONV_W], t->x[0], M, kTP, 3, 3, kTP, kTP, e);  // stem: the 243-float slot read as [81][3]
+    for (int r = 0; r < 3; ++r) {
+        float *const *B = W + T_BLK0 + 7 * r;
+        GemmEpi e0;
+        e0.bias = B[B_B0];
+        e0.act = 1;
+        tgemm<false, false>(s, t->x[r], B[B_W0], t->h0[r], M, kTM, kTP, kTP, kTM, kTM, e0);
+        const long long tot = (long long)M * kTM;
+        k_dw<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(t->h0[r], B[B_DW], t->hd[r], n, 0, nullptr);
+        GemmEpi e1;
+        e1.bias = B[B_B1];
+        e1.act = 1;
+        tgemm<false, false>(s, t->hd[r], B[B_PW], t->h1[r], M, kTM, kTM, kTM, kTM, kTM, e1);
+        GemmEpi e2;
+        e2.bias = B[B_B2];
+        e2.res = t->x[r];
+        e2.act = 1;
+        tgemm<false, false>(s, t->h1[r], B[B_W2], t->x[r + 1], M, kTP, kTM, kTM, kTP, kTP, e2);
+    }
+    GemmEpi f0;
+    f0.bias = W[T_FC0_B];
+    f0.act = 1;
+    tgemm<false, false>(s, t->x[3], W[T_FC0_W], t->a0, n, kTF, kTFlat, kTFlat, kTF, kTF, f0);  // NHWC flatten == the row itself
+    GemmEpi f1;
+    f1.bias = W[T_FC1_B];
+    f1.act = 1;
+    tgemm<false, false>(s, t->a0, W[T_FC1_W], t->a1, n, kTF, kTF, kTF, kTF, kTF, f1);
+    GemmEpi hp;
+    hp.bias = W[T_P_B];
+    tgemm<false, false>(s, t->a1, W[T_P_W], t->logits, n, kCells, kTF, kTF, kCells, kCells, hp);
+    GemmEpi hv;
+    hv.bias = W[T_V_B];
+    tgemm<false, false>(s, t->a1, W[T_V_W], t->vlogit, n, 1, kTF, kTF, 1, 1, hv);
+    c->launches += 5 + 3 * 4;
+}
+
+static void train_losses(omk_ctx *c, TrainState *t, int n, bool with_grads) {
+    k_loss<<<(n + 7) / 8, 256, 0, c->stream>>>(t->logits, t->vlogit, t->pi, t->z, n, with_grads ? t->dlogits : nullptr,
+                                                with_grads ? t->dvlogit : nullptr, t->row_loss);
+    k_loss_reduce<<<1, 32, 0, c->stream>>>(t->row_loss, n, t->losses);
+    c->launches += 2;
+}
+
+static void colsum(omk_ctx *c, const float *X, int M, int N, float *out) {
+    k_colsum<<<(N + 31) / 32, 256, 0, c->stream>>>(X, M, N, N, out);
+    c->launches++;
+}
+
+// gradients of the mean loss with respect to all 31 tensors, into t->grads (checkpoint order)
+static void train_backward(omk_ctx *c, TrainState *t, int n) {
+    cudaStream_t s = c->stream;
+    float *const *W = c->net.t;
+    const int M = n * kCells;
+    auto G = [&](int tensor) { return t->grads + t->off[tensor]; };
+    GemmEpi none;
+    // heads
+    tgemm<true, false>(s, t->a1, t->dlogits, G(T_P_W), kTF, kCells, n, kTF, kCells, kCells, none);   // a1^T . dlogits
+    colsum(c, t->dlogits, n, kCells, G(T_P_B));
+    tgemm<true, false>(s, t->a1, t->dvlogit, G(T_V_W), kTF, 1, n, kTF, 1, 1, none);
+    colsum(c, t->dvlogit, n, 1, G(T_V_B));
+    tgemm<false, true>(s, t->dlogits, W[T_P_W], t->da1, n, kTF, kCells, kCells, kCells, kTF, none);  // dlogits . Pw^T
+    {   // da1 = (dlogits . Pw^T + dvlogit . Vw^T) * lrelu'(a1): second product accumulates, then the gate
+        GemmEpi e;
+        e.accumulate = 1;
+        tgemm<false, true>(s, t->dvlogit, W[T_V_W], t->da1, n, kTF, 1, 1, 1, kTF, e);
+        const long long tot = (long long)n * kTF;
+        k_lrelu_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(t->da1, t->a1, t->da1, tot);
+    }
+    // fc1
+    tgemm<true, false>(s, t->a0, t->da1, G(T_FC1_W), kTF, kTF, n, kTF, kTF, kTF, none);
+    colsum(c, t->da1, n, kTF, G(T_FC1_B));
+    GemmEpi g0;
+    g0.gate = t->a0;
+    tgemm<false, true>(s, t->da1, W[T_FC1_W], t->da0, n, kTF, kTF, kTF, kTF, kTF, g0);
+    // fc0
+    tgemm<true, false>(s, t->x[3], t->da0, G(T_FC0_W), kTFlat, kTF, n, kTFlat, kTF, kTF, none);
+    colsum(c, t->da0, n, kTF, G(T_FC0_B));
+    tgemm<false, true>(s, t->da0, W[T_FC0_W], t->dx, n, kTFlat, kTF, kTF, kTF, kTFlat, none);  // d(flat) == d(x3) as [M][128]
+    c->launches += 10;
+    // residual blocks, last to first (network-utils lib.rs:386-461; network.rs:108-111)
+    for (int r = 2; r >= 0; --r) {
+        float *const *B = W + T_BLK0 + 7 * r;
+        const int gb = T_BLK0 + 7 * r;
+        const long long tot128 = (long long)M * kTP, tot32 = (long long)M * kTM;
+        k_lrelu_bwd<<<(unsigned)((tot128 + 255) / 256), 256, 0, s>>>(t->dx, t->x[r + 1], t->dy, tot128);  // through the block's last lrelu
+        tgemm<true, false>(s, t->h1[r], t->dy, G(gb + B_W2), kTM, kTP, M, kTM, kTP, kTP, none);
+        colsum(c, t->dy, M, kTP, G(gb + B_B2));
+        GemmEpi g1;
+        g1.gate = t->h1[r];
+        tgemm<false, true>(s, t->dy, B[B_W2], t->d32a, M, kTM, kTP, kTP, kTP, kTM, g1);  // d(pointwise pre-activation)
+        tgemm<true, false>(s, t->hd[r], t->d32a, G(gb + B_PW), kTM, kTM, M, kTM, kTM, kTM, none);
+        colsum(c, t->d32a, M, kTM, G(gb + B_B1));
+        tgemm<false, true>(s, t->d32a, B[B_PW], t->d32b, M, kTM, kTM, kTM, kTM, kTM, none);  // d(depthwise output)
+        k_dw_wgrad<<<9, 256, 0, s>>>(t->h0[r], t->d32b, G(gb + B_DW), n);
+        k_dw<<<(unsigned)((tot32 + 255) / 256), 256, 0, s>>>(t->d32b, B[B_DW], t->d32a, n, 1, t->h0[r]);  // d(conv0 pre-activation)
+        tgemm<true, false>(s, t->x[r], t->d32a, G(gb + B_W0), kTP, kTM, M, kTP, kTM, kTM, none);
+        colsum(c, t->d32a, M, kTM, G(gb + B_B0));
+        GemmEpi skip;  // dx_r = dy (the skip connection) + d(conv0 pre-activation) . W0^T
+        skip.res = t->dy;
+        tgemm<false, true>(s, t->d32a, B[B_W0], t->dx, M, kTP, kTM, kTM, kTM, kTP, skip);
+        c->launches += 9;
+    }
+    // stem
+    const long long tot128 = (long long)M * kTP;
+    k_lrelu_bwd<<<(unsigned)((tot128 + 255) / 256), 256, 0, s>>>(t->dx, t->x[0], t->dy, tot128);
+    tgemm<true, false>(s, t->img, t->dy, G(T_CONV_W), 3, kTP, M, 3, kTP, kTP, none);
+    colsum(c, t->dy, M, kTP, G(T_CONV_B));
+    c->launches += 2;
+}
+
+static bool train_upload(omk_ctx *c, TrainState *t, const float *images, const float *pi, const float *z, int n) {
+    return cudaMemcpyAsync(t->img, images, sizeof(float) * (size_t)n * 243, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+           cudaMemcpyAsync(t->pi, pi, sizeof(float) * (size_t)n * kCells, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+           cudaMemcpyAsync(t->z, z, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+}
+
+// ---- entry points used by omk_api.cu ----
+// forward + losses + backward on the local minibatch: the flat gradient of the MEAN loss is left in the gradient buffer
+const char *train_backward_step(omk_ctx *c, const float *images, const float *pi, const float *z, int n, float **grads_dev) {
+    TrainState *t = train_state(c);
+    if (!train_ensure(c, t, n)) return "training workspace allocation failed";
+    if (!train_upload(c, t, images, pi, z, n)) return "copying the minibatch to the device failed";
+    train_forward(c, t, n);
+    train_losses(c, t, n, true);
+    train_backward(c, t, n);
+    if (grads_dev) *grads_dev = t->grads;
+    return cudaPeekAtLastError() == cudaSuccess ? nullptr : cudaGetErrorString(cudaGetLastError());
+}
+
+// all-reduce (when a communicator is attached) + Adadelta on every tensor.  The caller re-packs the tensor-core weights.
+const char *train_apply_step(omk_ctx *c) {
+    TrainState *t = train_state(c);
+    if (!t->grads) return "omk_train_backward has not run";
+    if (t->comm && t->world > 1) {
+        const int rc = t->p_allreduce(t->grads, t->grads, (size_t)kTParams, 7 /* ncclFloat32 */, 0 /* ncclSum */, t->comm, c->stream);
+        if (rc != 0) return t->p_err ? t->p_err(rc) : "ncclAllReduce failed";
+        k_scale<<<(unsigned)((kTParams + 255) / 256), 256, 0, c->stream>>>(t->grads, kTParams, 1.0f / (float)t->world);
+        c->launches++;
+    }
+    for (int i = 0; i < kNetTensors; ++i) {
+        const long long len = kTLen[i];
+        k_adadelta<<<(unsigned)((len + 255) / 256), 256, 0, c->stream>>>(c->net.t[i], t->accum + t->off[i], t->accum_update + t->off[i],
+                                                                         t->grads + t->off[i], len, 0.01f, 0.95f, 1e-8f);
+    }
+    c->launches += kNetTensors;
+    t->steps++;
+    return cudaPeekAtLastError() == cudaSuccess ? nullptr : cudaGetErrorString(cudaGetLastError());
+}
+
+// the reference's second forward: (p_loss, v_loss, loss) of the minibatch uploaded by train_backward_step, with the
+// CURRENT weights; averaged over the ranks when a communicator is attached
+const char *train_report_losses(omk_ctx *c, int n, float *out3) {
+    TrainState *t = train_state(c);
+    if (n > t->cap_n || n <= 0) return "no minibatch on the device";
+    train_forward(c, t, n);
+    train_losses(c, t, n, false);
+    if (t->comm && t->world > 1) {
+        const int rc = t->p_allreduce(t->losses, t->losses, 3, 7, 0, t->comm, c->stream);
+        if (rc != 0) return t->p_err ? t->p_err(rc) : "ncclAllReduce failed";
+        k_scale<<<1, 32, 0, c->stream>>>(t->losses, 3, 1.0f / (float)t->world);
+        c->launches++;
+    }
+    if (cudaMemcpyAsync(out3, t->losses, sizeof(float) * 3, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return "loss copy failed";
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return "stream synchronisation failed";
+    return cudaPeekAtLastError() == cudaSuccess ? nullptr : cudaGetErrorString(cudaGetLastError());
+}
+
+float *train_grad_buffer(omk_ctx *c) { return train_state(c)->grads; }
+long long train_steps(omk_ctx *c) { return c->train_state ? train_state(c)->steps : 0; }
+void train_reset_optimizer(omk_ctx *c) {
+    TrainState *t = train_state(c);
+    if (t->accum) {
+        cudaMemsetAsync(t->accum, 0, sizeof(float) * kTParams, c->stream);
+        cudaMemsetAsync(t->accum_update, 0, sizeof(float) * kTParams, c->stream);
+    }
+    t->steps = 0;
+}
+
+// ---- NCCL through dlopen ----
+static const char *nccl_load(TrainState *t) {
+    if (t->nccl_lib) return nullptr;
+    const char *names[] = {getenv("OMK_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        if (!nm || !*nm) continue;
+        t->nccl_lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (t->nccl_lib) break;
+    }
+    if (!t->nccl_lib) return "libnccl.so.2 not found (set OMK_NCCL_LIB to its path)";
+    t->p_allreduce = reinterpret_cast<decltype(t->p_allreduce)>(dlsym(t->nccl_lib, "ncclAllReduce"));
+    t->p_comm_destroy = reinterpret_cast<decltype(t->p_comm_destroy)>(dlsym(t->nccl_lib, "ncclCommDestroy"));
+    t->p_err = reinterpret_cast<decltype(t->p_err)>(dlsym(t->nccl_lib, "ncclGetErrorString"));
+    if (!t->p_allreduce || !dlsym(t->nccl_lib, "ncclCommInitRank") || !dlsym(t->nccl_lib, "ncclGetUniqueId")) return "libnccl lacks the expected symbols";
+    return nullptr;
+}
+const char *train_comm_unique_id(omk_ctx *c, uint8_t *out128) {
+    TrainState *t = train_state(c);
+    if (const char *e = nccl_load(t)) return e;
+    auto fn = reinterpret_cast<int (*)(NcclUniqueId *)>(dlsym(t->nccl_lib, "ncclGetUniqueId"));
+    NcclUniqueId id;
+    const int rc = fn(&id);
+    if (rc != 0) return t->p_err ? t->p_err(rc) : "ncclGetUniqueId failed";
+    memcpy(out128, id.internal, 128);
+    return nullptr;
+}
+const char *train_comm_init(omk_ctx *c, const uint8_t *id128, int nranks, int rank) {
+    TrainState *t = train_state(c);
+    if (const char *e = nccl_load(t)) return e;
+    if (t->comm && t->p_comm_destroy) {
+        t->p_comm_destroy(t->comm);
+        t->comm = nullptr;
+    }
+    auto fn = reinterpret_cast<int (*)(void **, int, NcclUniqueId, int)>(dlsym(t->nccl_lib, "ncclCommInitRank"));
+    NcclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    const int rc = fn(&t->comm, nranks, id, rank);
+    if (rc != 0) return t->p_err ? t->p_err(rc) : "ncclCommInitRank failed";
+    t->world = nranks;
+    t->rank = rank;
+    return nullptr;
+}
+const char *train_comm_destroy(omk_ctx *c) {
+    TrainState *t = train_state(c);
+    if (t->comm && t->p_comm_destroy) t->p_comm_destroy(t->comm);
+    t->comm = nullptr;
+    t->world = 1;
+    t->rank = 0;
+    return nullptr;
+}
+
+}  // namespace omk

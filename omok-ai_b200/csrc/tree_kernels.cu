@@ -348,6 +348,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
         }
         if (c.status == kInProgress) ++nreq; else restart = true;  // a terminal child was backed up along the path
         set81(h.cmask, action);  // the kept copy of the leaf's header follows the one in memory
+#ifdef OMK_NO_DESCENT_REUSE
+        restart = true;  // A/B build: the first version's behaviour, a full descent per simulation
+#endif
         root_n = __shfl_sync(kFull, root_n, 0);
         root_w = __shfl_sync(kFull, root_w, 0);
         __syncwarp();

@@ -12,9 +12,11 @@ does between two self-play phases, fed by this library's self-play driver.
                                             GPUs, gloo in the CPU tests); every rank then applies the same update
 
 The self-play hot path is the hand-written CUDA of csrc/.  The gradient step is not on that path (600 steps of 128
-positions per iteration against ~10^8 network evaluations of self-play); it runs on PyTorch autograd over tensors in the
-reference's own variable layout, and `TrainStep.sync_to(ctx)` hands the updated weights to the CUDA kernels
-(omk_net_load_params re-splits / re-packs them).
+positions per iteration against ~10^8 network evaluations of self-play).  On a GPU it is `AbiTrainStep`: the C ABI's
+omk_train_step (csrc/train_kernels.cu: fp32 forward / backward / Adadelta kernels, NCCL all-reduce of the flat gradient
+through an attached communicator) -- the call the Rust `AgentModel::train` shim makes.  `TrainStep` is the same step on
+PyTorch autograd over tensors in the reference's variable layout; it runs anywhere (the CPU tests check it against a float64 restatement and check the
+data-parallel logic over gloo) and hands weights to the kernels with `sync_to`.
 """
 from __future__ import annotations
 
@@ -119,8 +121,12 @@ def split_episodes(boards: np.ndarray, policy: np.ndarray, status: np.ndarray, c
 
     boards [P,G,81], policy [P,G,81], status [P,G] (status AFTER the move; a finished game restarts on the next ply).
     Returns (episodes, carry): episodes = list of (boards[T,81], policies[T,81], final_z); `carry` holds the unfinished
-    tails, pass it to the next call."""
+    tails, pass it to the next call (the reference trains on finished episodes only, trainer.rs:206-215).
+    A status outside {InProgress, Draw, BlackWin, WhiteWin} -- Option::None of a refused move -- is an error, not an
+    end of game."""
     P, G = status.shape
+    if status.size and (int(status.min()) < 0 or int(status.max()) > 3):
+        raise ValueError("self-play produced a status outside 0..3 (a refused move): the transition stream is corrupt")
     carry = carry if carry is not None else [([], []) for _ in range(G)]
     episodes = []
     for g in range(G):
@@ -246,3 +252,31 @@ class TrainStep:
     def sync_to(self, ctx) -> None:
         """Hand the current weights to the CUDA self-play kernels of `ctx` (omk_net_load_params)."""
         ctx.net_load_params(self.numpy_params())
+
+
+class AbiTrainStep:
+    """`AgentModel::train` through the C ABI (omk_train_step): weights, Adadelta slots and the gradient live in the
+    context `ctx`; after every step the self-play kernels of the same context see the new weights (no `sync_to`).
+    With `world > 1` a NCCL communicator is attached to the context: `unique_id` comes from rank 0's
+    `ctx.train_comm_unique_id()` and reaches the other ranks by any side channel (tools/iteration.py broadcasts it with
+    torch.distributed); every step then all-reduces the 22.6 MB gradient once."""
+
+    LEARNING_RATE = 0.01
+
+    def __init__(self, ctx, world: int = 1, rank: int = 0, unique_id: bytes | None = None):
+        self.ctx, self.world, self.steps = ctx, world, 0
+        if world > 1:
+            if unique_id is None:
+                raise ValueError("data-parallel training needs rank 0's NCCL unique id")
+            ctx.train_comm_init(unique_id, world, rank)
+
+    def train(self, images, pi, z):
+        self.steps += 1
+        return self.ctx.train_step(images, pi, z)
+
+    def numpy_params(self):
+        return self.ctx.net_get_params()
+
+    def sync_to(self, ctx) -> None:
+        if ctx is not self.ctx:
+            ctx.net_load_params(self.numpy_params())

@@ -180,6 +180,41 @@ def forward(params: list[np.ndarray], images: np.ndarray, dtype=torch.float32):
     return pol.float().numpy(), v.float().numpy(), logits.float().numpy()
 
 
+def loss_and_grads(params: list[np.ndarray], images: np.ndarray, pi: np.ndarray, z: np.ndarray, dtype=torch.float64):
+    """The reference's training loss (alpha-zero/src/agent_model.rs:60-73, network.rs:249-253) and its gradient with
+    respect to the 31 tensors, by autograd over the same graph as `forward` in `dtype`:
+    loss = mean((z - v)^2) + mean_i(-sum_j pi_ij log_softmax(logits)_ij).  Returns ((p_loss, v_loss, loss), grads)."""
+    p = {name: torch.from_numpy(np.asarray(a)).to(dtype).requires_grad_(True) for (name, _), a in zip(PARAM_SPECS, params)}
+    x = torch.from_numpy(np.asarray(images, dtype=np.float32)).to(dtype)
+    B = x.shape[0]
+    x = x.reshape(B, BOARD, BOARD, 3).permute(0, 3, 1, 2)
+
+    def conv1x1(t, w, b):
+        return F.conv2d(t, w[0, 0].t().reshape(w.shape[3], w.shape[2], 1, 1), b)
+
+    x = F.leaky_relu(conv1x1(x, p["conv_w"], p["conv_b"]), LRELU)
+    for i in range(NRES):
+        h = F.leaky_relu(conv1x1(x, p[f"res{i}_w0"], p[f"res{i}_b0"]), LRELU)
+        dw = p[f"res{i}_dw"]
+        h = F.conv2d(h, dw[:, :, :, 0].permute(2, 0, 1).unsqueeze(1), None, padding=1, groups=MID)
+        h = F.leaky_relu(conv1x1(h, p[f"res{i}_pw"], p[f"res{i}_b1"]), LRELU)
+        h = conv1x1(h, p[f"res{i}_w2"], p[f"res{i}_b2"])
+        x = F.leaky_relu(h + x, LRELU)
+    flat = x.permute(0, 2, 3, 1).reshape(B, CELLS * CH)
+    h = F.leaky_relu(flat @ p["fc0_w"] + p["fc0_b"], LRELU)
+    h = F.leaky_relu(h @ p["fc1_w"] + p["fc1_b"], LRELU)
+    v = torch.tanh(h @ p["v_w"] + p["v_b"])
+    logits = h @ p["p_w"] + p["p_b"]
+    zt = torch.from_numpy(np.asarray(z, dtype=np.float32)).to(dtype).reshape(B, 1)
+    pt = torch.from_numpy(np.asarray(pi, dtype=np.float32)).to(dtype).reshape(B, CELLS)
+    v_loss = torch.mean((zt - v) ** 2)
+    p_loss = torch.mean(-(pt * F.log_softmax(logits, dim=1)).sum(dim=1))
+    loss = v_loss + p_loss
+    loss.backward()
+    grads = [p[name].grad.detach().numpy() for name, _ in PARAM_SPECS]
+    return (float(p_loss), float(v_loss), float(loss)), grads
+
+
 def forward_layers(params: list[np.ndarray], images: np.ndarray, dtype=torch.float64) -> dict[str, np.ndarray]:
     """The same graph as `forward`, returning every layer the CUDA path can be inspected at, in `dtype` precision (no
     cast to fp32): tower [B,81,128] (the NHWC flatten fc0 reads), fc0 [B,512], fc1 [B,512], logits [B,81], vlogit [B],

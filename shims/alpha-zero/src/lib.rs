@@ -175,11 +175,20 @@ impl AgentModel {
         self.evaluate(&input, true)
     }
 
-    /// reference: agent_model.rs:136-168.  The gradient step is a trainer-side row: this repository
-    /// implements it in omok-ai_b200/trainer.py (loss, Adadelta, data-parallel all-reduce) and hands the weights back
-    /// through omk_net_load_params; the C ABI has no training entry point, so the shim says so instead of pretending.
-    pub fn train(&self, _session: &Session, _input: Tensor<f32>, _policy_target: Tensor<f32>, _value_target: Tensor<f32>) -> Result<(f32, f32, f32), Status> {
-        Err(Status::from_message("AgentModel::train is not part of libomok_b200's C ABI: run the trainer step of omok-ai_b200/trainer.py and load the weights with ModelIO::load"))
+    /// reference: agent_model.rs:136-168 -- one Adadelta step on the minibatch, then the second forward that reports
+    /// `(p_loss, v_loss, loss)`.  `input` is encode_nn_input's `[n,9,9,3]` tensor, `policy_target` `[n,9,9]`,
+    /// `value_target` `[n,1]` (encoder.rs:48-68).  Forwards to omk_train_step; the optimizer slots live in the context.
+    pub fn train(&self, _session: &Session, input: Tensor<f32>, policy_target: Tensor<f32>, value_target: Tensor<f32>) -> Result<(f32, f32, f32), Status> {
+        let n = input.len() / (CELLS * 3);
+        debug_assert_eq!(policy_target.len(), n * CELLS);
+        debug_assert_eq!(value_target.len(), n);
+        let mut losses = [0f32; 3];
+        sys::with(|c| {
+            call(unsafe {
+                sys::omk_train_step(c.raw(), input.as_ptr(), policy_target.as_ptr(), value_target.as_ptr(), n as i32, losses.as_mut_ptr())
+            })
+        })?;
+        Ok((losses[0], losses[1], losses[2]))
     }
 }
 

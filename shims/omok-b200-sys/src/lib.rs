@@ -68,6 +68,15 @@ extern "C" {
     pub fn omk_net_get_params(ctx: *mut omk_ctx, tensors: *const *mut f32, lens: *const i64) -> i32;
     pub fn omk_net_init_random(ctx: *mut omk_ctx, seed: u64) -> i32;
     pub fn omk_net_eval(ctx: *mut omk_ctx, boards: *const u8, turns: *const u8, n: i32, mode: i32, out_p: *mut f32, out_v: *mut f32) -> i32;
+    // trainer step (alpha-zero/src/agent_model.rs:136-168)
+    pub fn omk_train_step(ctx: *mut omk_ctx, images: *const f32, pi: *const f32, z: *const f32, n: i32, out_losses: *mut f32) -> i32;
+    pub fn omk_train_backward(ctx: *mut omk_ctx, images: *const f32, pi: *const f32, z: *const f32, n: i32, out_grads_device: *mut *mut c_void, out_count: *mut i64) -> i32;
+    pub fn omk_train_apply(ctx: *mut omk_ctx, out_losses: *mut f32) -> i32;
+    pub fn omk_train_get_grads(ctx: *mut omk_ctx, tensors: *const *mut f32, lens: *const i64) -> i32;
+    pub fn omk_train_reset_optimizer(ctx: *mut omk_ctx) -> i32;
+    pub fn omk_train_comm_unique_id(ctx: *mut omk_ctx, out_id: *mut u8) -> i32;
+    pub fn omk_train_comm_init(ctx: *mut omk_ctx, id: *const u8, nranks: i32, rank: i32) -> i32;
+    pub fn omk_train_comm_destroy(ctx: *mut omk_ctx) -> i32;
     pub fn omk_net_eval_images(ctx: *mut omk_ctx, images: *const f32, n: i32, out_p: *mut f32, out_v: *mut f32) -> i32;
     // diagnostics
     pub fn omk_debug_set_fc0_mode(ctx: *mut omk_ctx, mode: i32) -> i32;
@@ -91,6 +100,7 @@ extern "C" {
     pub fn omk_pool_ensure_action(ctx: *mut omk_ctx, ids: *const i32, actions: *const i32, n: i32, evaluator: i32) -> i32;
     pub fn omk_pool_play(ctx: *mut omk_ctx, ids: *const i32, actions: *const i32, n: i32, out_status: *mut i8) -> i32;
     pub fn omk_pool_get_env(ctx: *mut omk_ctx, id: i32, out_board: *mut u8, out_turn: *mut u8, out_legal_count: *mut u16) -> i32;
+    pub fn omk_pool_get_envs(ctx: *mut omk_ctx, ids: *const i32, n: i32, out_boards: *mut u8, out_turns: *mut u8, out_legal_counts: *mut u16, out_status: *mut i8) -> i32;
     pub fn omk_pool_root_stats(ctx: *mut omk_ctx, id: i32, out_n: *mut u64, out_w: *mut f32, out_p: *mut f32, out_status: *mut i32, out_policy: *mut f32) -> i32;
     pub fn omk_pool_root_children(ctx: *mut omk_ctx, id: i32, out_actions: *mut i32, out_n: *mut u64, out_w: *mut f32, out_p: *mut f32, out_len: *mut i32) -> i32;
     pub fn omk_pool_tree_info(ctx: *mut omk_ctx, id: i32, out_nodes: *mut i32, out_rng_counter: *mut u32) -> i32;

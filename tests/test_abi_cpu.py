@@ -61,3 +61,33 @@ def test_rust_sys_crate_declares_every_entry_point_with_the_same_arity(omk):
         c_args = [a for a in c.group(1).split(",") if a.strip() and a.strip() != "void"]
         r_args = [a for a in r.group(1).split(",") if a.strip()]
         assert len(c_args) == len(r_args), (name, c_args, r_args)
+        # ... and the same parameter TYPES, position by position
+        for ca, ra in zip(c_args, r_args):
+            assert _c_type_as_rust(ca) == ra.split(":", 1)[1].strip(), (name, ca, ra)
+
+
+_SCALARS = {"int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64", "uint8_t": "u8", "int8_t": "i8",
+            "uint16_t": "u16", "float": "f32", "void": "c_void", "omk_ctx": "omk_ctx", "omk_selfplay_config": "omk_selfplay_config",
+            "omk_selfplay_stats": "omk_selfplay_stats"}
+
+
+def _c_type_as_rust(decl: str) -> str:
+    """`const float *const *tensors` -> `*const *const f32` (the parameter name is dropped)."""
+    import re
+
+    toks = re.findall(r"[A-Za-z_]\w*|\*", decl)
+    toks = toks[:-1]  # parameter name
+    base = [t for t in toks if t in _SCALARS]
+    assert len(base) == 1, decl
+    # walk the declarator left to right: qualifiers before a `*` say whether THAT pointer's pointee is const
+    out, const_pending, seen_base = _SCALARS[base[0]], False, False
+    for t in toks:
+        if t == "const":
+            const_pending = True
+        elif t in _SCALARS:
+            seen_base = True
+        elif t == "*":
+            assert seen_base, decl
+            out = ("*const " if const_pending else "*mut ") + out
+            const_pending = False
+    return out

@@ -48,10 +48,11 @@ def test_trained_weights_reach_the_cuda_network(omk):
 
 
 def test_one_small_iteration_end_to_end():
-    it = importlib.import_module("tools.iteration") if False else None
+    """self-play (transitions streamed to the host) -> episodes -> replay with the 6x augmentation -> omk_train_step x 3
+    -> the refreshed weights answer omk_net_eval_images, on one GPU."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     iteration = importlib.import_module("iteration")
-    out = iteration.run(games=16, plies=30, count=32, batch=16, steps=3, minibatch=32, quiet=True)
-    assert out["replay_transitions"] >= 6 * 16 * 30 * 0 + 6 * 16  # every game contributes, finished or not
+    out = iteration.run(games_per_gpu=16, plies=30, count=32, batch=16, steps=3, minibatch=32, quiet=True)
+    assert out["replay_transitions"] >= 32 and out["d2h_bytes"] == 16 * 30 * (81 + 81 * 4 + 4 + 1)
     assert out["policy_sums_to_one"] and np.isfinite(out["last_loss"]) and out["train_step_ms"] > 0
-    assert out["selfplay_sims_per_s"] > 0
+    assert out["selfplay_sims_per_s"] > 0 and out["train_step"].startswith("omk_train_step")

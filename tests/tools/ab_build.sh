@@ -12,8 +12,8 @@ extra=""
 [ "$base" = tree_kernels ] && extra="-fmad=false"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden $extra "$@" -c "$file" -o ../_build/variants/$name.$base.o
 objs=""
-for o in env_kernels tree_kernels net_kernels fc_f16 tower_f16 omk_api; do
+for o in env_kernels tree_kernels net_kernels fc_f16 tower_f16 train_kernels omk_api; do
   if [ "$o" = "$base" ]; then objs="$objs ../_build/variants/$name.$base.o"; else objs="$objs ../_build/$o.o"; fi
 done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../_build/variants/$name.so $objs -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../_build/variants/$name.so $objs -lcudart -ldl
 echo built ../_build/variants/$name.so
