@@ -11,9 +11,11 @@ One "step" = one ply on every game = 1024 positions = 1024 x 800 simulations.
 N > 1 is launched by torchrun: one process per GPU, per-GPU game pools, NO data-path collective
 (games are independent units -> weak scaling); only the timing barrier / max-over-ranks uses NCCL.
 
-The line's `value` is device-resident throughput (omk_selfplay_run, CUDA events); `e2e` drives the same
-ply through the granular C-ABI calls a Rust `alpha-zero` shim would make (host id/action buffers in,
-actions/policies/status out, every call synchronising) -- that is the headline against the reference arm.
+The line's `value` is device-resident throughput (omk_selfplay_run, CUDA events) WITH the transition stream on: every
+ply's positions (board, visit policy, action, status: 410 B each) leave for the host replay buffer through the pinned
+ring inside the timed region (BASELINE configs[3]); `e2e` drives the same ply through the granular C-ABI calls a Rust
+`alpha-zero` shim would make (host id/action buffers in, actions/policies/status out, every call synchronising) -- that
+is the headline against the reference arm; its byte counts are the library's own transfer counters.
 `--impl reference` times the CPU oracle (C restatement, all host cores) with the PyTorch-CPU fp32 network
 standing in for TensorFlow-CPU, on a bounded sample of the same workload.
 """
@@ -53,11 +55,13 @@ def read_peaks():
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the network kernels, from the committed
     `ncu --set full` capture of this same workload (profiles/r01_ncu_traffic.json; tools/ncu_summary.py wrote it)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    try:
-        return {k: v["dram_bytes_per_launch"] for k, v in json.load(open(path)).items()}
-    except Exception:
-        return {}
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            return {k: v["dram_bytes_per_launch"] for k, v in json.load(open(path)).items()}
+        except Exception:
+            continue
+    return {}
 
 
 class ClockSampler:
@@ -170,7 +174,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    warm = min(args.warmup, 1)
+    warm = max(0, args.warmup)  # the same W untimed plies as the repo arm is asked for
     r = cpu_selfplay_sample(steps, warm)
     value = r["sims"] / r["seconds"]
     line = {
@@ -179,7 +183,7 @@ def run_reference(args, rank, world):
         "positions_per_sec": r["positions"] / r["seconds"],
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * r["seconds"] / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": reference_config(args.gpus, r["trees"]),
         "cpu_baseline": {"value": value, "unit": "simulations/s", "cores": r["cores"], "kind": "port",
                          "sample": f"{r['trees']} concurrent trees x {steps} plies x {COUNT} sims/move (rounds of {BATCH}); "
                                    "C oracle on all host cores + PyTorch-CPU fp32 network in place of TensorFlow-CPU"},
@@ -189,12 +193,27 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def reference_config(n_gpus, trees):
+    """The reference arm runs a BOUNDED SAMPLE of the workload: `trees` concurrent games instead of 1024 per GPU (one
+    ply of 1024 games is ~50 s of CPU work on 16 cores), everything else identical; its NN batches are trees x 16 rows."""
+    cfg = workload_config(n_gpus)
+    cfg["workload"] = (f"bounded sample of BASELINE configs[2] on the host CPU: {trees} concurrent games (of {GAMES_PER_GPU}) x {COUNT} "
+                       f"sims/move, rounds of {BATCH}, eps {EPS}, alpha {ALPHA}, the same random-init network in PyTorch-CPU fp32; "
+                       "trainer-shaped self-play (2 trees per game, ensure_action_exists + re-root each ply); C restatement of the "
+                       "reference's Rust on all host cores (the Rust/TensorFlow binary cannot be built here)")
+    # the structured keys keep naming the workload both arms are quoted on; what this arm actually ran is in `sample_*`
+    cfg["sample_games"], cfg["sample_trees"], cfg["sample_nn_rows_per_call"] = trees, 2 * trees, trees * BATCH
+    cfg["sample_parallelism"] = "one process, pthreads over trees (rayon stand-in) + PyTorch intra-op threads; rank 0 only"
+    return cfg
+
+
 def workload_config(n_gpus, games=GAMES_PER_GPU):
     which = "BASELINE configs[2]" if games == GAMES_PER_GPU else f"BASELINE configs[2] shape at {games} games per GPU"
     lanes = f"two search lanes (streams) of {games // 2} games each" if games >= 768 else "one search lane"
     return {"workload": f"{which}: batched MCTS, {games} concurrent trees per GPU x {COUNT} sims/move, "
                         f"rounds of {BATCH}, eps {EPS}, alpha {ALPHA}, random-init residual policy/value net; "
-                        "trainer-shaped self-play (2 trees per game, ensure_action_exists + re-root each ply)",
+                        "trainer-shaped self-play (2 trees per game, ensure_action_exists + re-root each ply); every ply's "
+                        "transitions (board, visit policy, action, status) stream to the host replay buffer inside the timed region",
             "games_per_gpu": games, "trees_per_gpu": 2 * games, "sims_per_move": COUNT,
             "nn_batch_per_tree": BATCH, "capacity_nodes": CAP_NODES,
             "parallelism": f"games sharded x{n_gpus}, no collective; per GPU {lanes}",
@@ -249,14 +268,17 @@ def main():
     # ---- device-resident arm: `value` ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ctx.selfplay_run(warm, profile=0, want_transitions=False)
+    ctx.selfplay_run(warm, profile=0, want_transitions=True)
     launches0 = ctx.launch_count
     barrier()
     sampler.mark_start()
-    stats, *_ = ctx.selfplay_run(steps, profile=0, want_transitions=False)
+    # BASELINE configs[3]: "positions streamed to host replay buffer" -- the pinned transition ring is ON in the timed region
+    stats, t_boards, t_policy, t_status, t_actions = ctx.selfplay_run(steps, profile=0, want_transitions=True)
     barrier()
     sampler.mark_end()
     launches = ctx.launch_count - launches0
+    assert t_boards.shape == (steps, games, 81) and int(stats.d2h_bytes) == steps * games * (81 + 81 * 4 + 4 + 1)
+    stream_d2h = int(stats.d2h_bytes)
     ctx.selfplay_run(1, profile=0, want_transitions=False)  # keeps the load on while the last samples arrive (untimed)
     barrier()
     clocks = sampler.stop()
@@ -276,8 +298,8 @@ def main():
     ids_b = np.arange(0, 2 * games, 2, dtype=np.int32)
     ids_w = ids_b + 1
     ctx.pool_new_games(n=2 * games, evaluator=omk.EVAL_NET)
-    h2d = d2h = 0
     barrier()
+    h2d0, d2h0 = ctx.transfer_bytes  # the library counts every host <-> device copy its entry points make
     t0 = time.perf_counter()
     e2e_sims = 0
     for p in range(e2e_steps):
@@ -289,16 +311,15 @@ def main():
         st = ctx.pool_play(acts, ids=mover)
         ctx.pool_ensure_action(acts, ids=other, evaluator=omk.EVAL_NET)
         ctx.pool_play(acts, ids=other)
-        h2d += mover.nbytes * 5 + modes.nbytes + games * 4 + acts.nbytes * 3
-        d2h += acts.nbytes + pol.nbytes + st.nbytes * 2 + 4 * 3
         assert (st == 0).all() or p >= 8, "a game ended implausibly early"
         done = np.nonzero(st != 0)[0]
         if len(done):  # a finished game starts over with two fresh agents, as the trainer's episode loop does (src/trainer.rs:101-121)
             fresh = np.concatenate([ids_b[done], ids_w[done]]).astype(np.int32)
             ctx.pool_new_games(ids=fresh, evaluator=omk.EVAL_NET)
-            h2d += fresh.nbytes
     barrier()
     e2e_s = time.perf_counter() - t0
+    h2d1, d2h1 = ctx.transfer_bytes
+    h2d, d2h = h2d1 - h2d0, d2h1 - d2h0
 
     # ---- aggregate over ranks: max time, summed work (the only cross-rank traffic of the whole run) ----
     times, work = sharding.reduce_measurements(
@@ -336,7 +357,8 @@ def main():
                     "peak_source": note,
                     "avg_launch_ms": fc0_ms / max(1, fc0_launches), "rows_per_launch": rows_per_launch,
                     "share_of_step": fc0_ms / float(kstats.gpu_ms) if kstats.gpu_ms else None,
-                    "measured": "second pass of the same workload, one search lane (see bench.py)",
+                    "measured": "NOT in the timed region: second pass of the same workload with one search lane, CUDA-event spans per kernel (in the two-lane timed region a span would include waits for the other lane); shares agree with the ncu launch list of the two-lane command under profiles/",
+                    "in_timed_region": False,
                     "traffic": traffic.get("k_fc16") if fc0_mode == "f16" else None}
         roof_tower = {"bound": "tensor", "kernel": tower_names.get(tower_mode, tower_mode),
                       "achieved": tower_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tower_tflops / peak,
@@ -344,7 +366,8 @@ def main():
                       "peak_source": note + "; this kernel is bound by its CUDA-core epilogues (issue slots), not by the tensor pipe",
                       "avg_launch_ms": tower_ms / max(1, tower_launches), "rows_per_launch": rows_per_launch,
                       "share_of_step": tower_ms / float(kstats.gpu_ms) if kstats.gpu_ms else None,
-                      "measured": "second pass of the same workload, one search lane (see bench.py)",
+                      "measured": "NOT in the timed region: second pass of the same workload with one search lane, CUDA-event spans per kernel (in the two-lane timed region a span would include waits for the other lane); shares agree with the ncu launch list of the two-lane command under profiles/",
+                    "in_timed_region": False,
                       "traffic": traffic.get("k_tower16") if tower_mode == "f16" else None}
         # K2 tree kernels of this workload (one-lane pass) and K1 environment step (measured here, 16 Mi boards = 512 MB of
         # records, far beyond L2) against the HBM roofline: SURVEY 8d byte models, 1672 B per simulation, 78 B per board-step
@@ -405,7 +428,11 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_sims / e2e_s, "unit": "simulations/s", "h2d_bytes_per_step": h2d // e2e_steps,
                     "d2h_bytes_per_step": d2h // e2e_steps,
-                    "path": "omk_pool_search/sample/play/ensure_action/play per ply with host id+action buffers"},
+                    "path": "omk_pool_search/sample/play/ensure_action/play per ply with host id+action buffers",
+                    "bytes_source": "omk_ctx_transfer_bytes (the library's own counters)"},
+            "transition_stream": {"in_timed_region": True, "d2h_bytes_per_step": stream_d2h // steps,
+                                  "bytes_per_position": 81 + 81 * 4 + 4 + 1,
+                                  "path": "omk_selfplay_run: four-slot device ring -> pinned host mirror on a copy stream -> caller's arrays"},
             "gpu_launches": launches,
             "roofline": dominant,
             "roofline_second": other,

@@ -79,6 +79,9 @@ OMK_API int32_t omk_ctx_synchronize(omk_ctx *ctx);
 OMK_API void *omk_ctx_stream(omk_ctx *ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 OMK_API int64_t omk_ctx_launch_count(omk_ctx *ctx);
+/* bytes the API layer has copied host->device / device->host for this context since creation (every entry point's
+ * argument and result copies, and the self-play driver's transition stream; bench.py's e2e byte counts) */
+OMK_API int32_t omk_ctx_transfer_bytes(omk_ctx *ctx, int64_t *out_h2d, int64_t *out_d2h);
 
 /* ---------------------------------------------------------------- network
  * Replaces AgentModel::{evaluate_p, evaluate_pv} (alpha-zero/src/agent_model.rs:105-134)
@@ -136,6 +139,10 @@ OMK_API int32_t omk_train_comm_destroy(omk_ctx *ctx);
  * 1 = fc0 output, 2 = fc1 output, 3 = head logits of the CUDA-core path.                                                                           */
 OMK_API int32_t omk_debug_set_fc0_mode(omk_ctx *ctx, int32_t mode);
 OMK_API int32_t omk_debug_set_tower_mode(omk_ctx *ctx, int32_t mode);
+/* k-blocks (of 64) fc0 accumulates in tensor memory between two drains into fp32 registers: 9 (default) or 3 -- the
+ * tensor-core accumulator truncates, so the shorter chunk is more accurate (max relative prior error 2.1e-4 -> 1.6e-4 on
+ * 20 000 positions) at +0.8 % fc0 time on large batches and slower small batches (env OMK_FC0_CHUNK=3).               */
+OMK_API int32_t omk_debug_set_fc0_chunk(omk_ctx *ctx, int32_t k_blocks);
 /* clock64 phase timestamps of one iteration inside k_tower16 (64 values; tests/tools/check_f16.py) */
 OMK_API int32_t omk_debug_tower_timing(omk_ctx *ctx, int64_t *out64);
 OMK_API int32_t omk_debug_get_buffer(omk_ctx *ctx, int32_t which, float *out, int64_t count);

@@ -98,6 +98,7 @@ def load_library():
     L.omk_ctx_stream.restype = vp
     L.omk_ctx_launch_count.argtypes = [vp]
     L.omk_ctx_launch_count.restype = i64
+    L.omk_ctx_transfer_bytes.argtypes = [vp, P(i64), P(i64)]
     L.omk_net_load_params.argtypes = [vp, P(vp), P(i64)]
     L.omk_net_get_params.argtypes = [vp, P(vp), P(i64)]
     L.omk_net_init_random.argtypes = [vp, u64]
@@ -113,6 +114,7 @@ def load_library():
     L.omk_train_comm_destroy.argtypes = [vp]
     L.omk_debug_set_fc0_mode.argtypes = [vp, i32]
     L.omk_debug_set_tower_mode.argtypes = [vp, i32]
+    L.omk_debug_set_fc0_chunk.argtypes = [vp, i32]
     L.omk_debug_set_lane_min_trees.argtypes = [vp, i32]
     L.omk_debug_get_buffer.argtypes = [vp, i32, vp, i64]
     L.omk_debug_tower_timing.argtypes = [vp, vp]
@@ -190,6 +192,13 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.L.omk_ctx_launch_count(self.h))
+
+    @property
+    def transfer_bytes(self) -> tuple[int, int]:
+        """(host->device, device->host) bytes the API layer has copied for this context since creation."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.L.omk_ctx_transfer_bytes(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     # ---- network ----
     def net_load_params(self, params):
@@ -280,6 +289,9 @@ class Context:
 
     def debug_set_tower_mode(self, mode: int):
         self._check(self.L.omk_debug_set_tower_mode(self.h, mode))
+
+    def debug_set_fc0_chunk(self, k_blocks: int):
+        self._check(self.L.omk_debug_set_fc0_chunk(self.h, k_blocks))
 
     def debug_set_lane_min_trees(self, min_trees: int):
         self._check(self.L.omk_debug_set_lane_min_trees(self.h, min_trees))

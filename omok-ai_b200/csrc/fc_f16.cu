@@ -36,18 +36,20 @@ constexpr int F_N = 512;
 constexpr int F_K0 = 10368, F_K1 = 512;
 constexpr int F_A_BYTES = F_BM * F_BK * 2;        // 16 KB
 // k-blocks accumulated in tensor memory between two drains into fp32 registers.  The tensor-core accumulator truncates,
-// so the error of a layer grows with the chunk length; profiles/r02_net_error_study.json has error and time per choice
-// (A/B builds: -DOMK_F_CHUNK0=.. -DOMK_F_CHUNK1=.. -DOMK_F_CHUNKH=..).
-#ifndef OMK_F_CHUNK0
-#define OMK_F_CHUNK0 9
-#endif
+// so a layer's error grows with the chunk length (profiles/r02_net_error_study.md: 20 000 positions, 3 weight seeds):
+//   fc1 / heads  8 -> 1 k-block: max relative prior error 4.6e-4 -> 2.1e-4, +0.001 ms per 16 k rows: the default;
+//   fc0          9 -> 3 k-blocks: 2.1e-4 -> 1.6e-4, fc0 +0.8 % on 16 k-row batches, but three times the partial sums of the
+//                split-K path (small batches: 8 rows 22 -> 31 us, 1024 rows 51 -> 96 us): OPT-IN at run time
+//                (omk_debug_set_fc0_chunk(ctx, 3) / env OMK_FC0_CHUNK=3); both chunkings keep a row's result independent
+//                of the batch size and of the path (pair / split-K) its batch takes.
 #ifndef OMK_F_CHUNK1
-#define OMK_F_CHUNK1 8
+#define OMK_F_CHUNK1 1
 #endif
 #ifndef OMK_F_CHUNKH
-#define OMK_F_CHUNKH 8
+#define OMK_F_CHUNKH 1
 #endif
-constexpr int F_CHUNK0 = OMK_F_CHUNK0;            // fc0: 162 k-blocks = 18 x 9
+constexpr int F_SPLITK_KB = 9;                    // k-blocks per CTA of the split-K fc0 (small batches)
+constexpr int F_CHUNK0 = 9, F_CHUNK0_FINE = 3;    // fc0: 162 k-blocks = 18 x 9 (default) or 54 x 3 (fc0_chunk == 3)
 constexpr int F_CHUNK1 = OMK_F_CHUNK1;            // fc1: 8 k-blocks
 constexpr int F_CHUNKH = OMK_F_CHUNKH;            // heads: 8 k-blocks
 constexpr int kSplitKMaxRows = 2048;              // fc0 batches up to here take the split-K path (36 CTAs per 128 rows): 95 vs 152 us at 2048 rows, 181 vs 158 us at 4096
@@ -67,7 +69,7 @@ struct FcCfg {
 
 // BN = 256: fc0 / fc1 tiles.  BN = 128 with HEADS: the policy/value heads (512 -> 81 | 1, padded to 128 columns): a drain
 // thread owns a whole row of logits, so tanh (value, network.rs:188-202) and softmax (policy, :227-247) finish in registers.
-// SPLITK (small batches): blockIdx.z selects ONE chunk of CHUNK k-blocks; the CTA writes that chunk's raw fp32 partial sums
+// SPLITK (small batches): blockIdx.z selects F_SPLITK_KB k-blocks; the CTA writes the raw fp32 partial sums of each of their chunks
 // to C[z][gridDim.y * 128 rows][512] and k_fc0_reduce adds the chunks in order -- the same partial sums in the same order as the
 // unsplit kernel, so a row's result stays bit-identical whatever the batch size (recorded-mode parity).
 template <int K, int CHUNK, bool PAIR, int BN = 256, bool HEADS = false, bool SPLITK = false>
@@ -82,9 +84,11 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
     constexpr int CG = PAIR ? 2 : 1;
     static_assert(K % F_BK == 0 && (K / F_BK) % CHUNK == 0, "chunking must tile K");
     static_assert(!SPLITK || (!PAIR && !HEADS), "split-K is the one-CTA fc0 variant");
-    constexpr int NKB = SPLITK ? CHUNK : K / F_BK;      // k-blocks this CTA walks
+    // split-K: one CTA walks F_SPLITK_KB k-blocks = several chunks, and stores every chunk's partial sums separately
+    constexpr int NKB = SPLITK ? F_SPLITK_KB : K / F_BK;      // k-blocks this CTA walks
+    static_assert(!SPLITK || (F_SPLITK_KB % CHUNK == 0 && (K / F_BK) % F_SPLITK_KB == 0), "split-K groups must tile K");
     constexpr int NCHUNK = NKB / CHUNK;
-    const int kb_base = SPLITK ? (int)blockIdx.z * CHUNK : 0;
+    const int kb_base = SPLITK ? (int)blockIdx.z * F_SPLITK_KB : 0;
     extern __shared__ uint8_t smem_raw[];
     const int rows = (int)min(*n_req, (uint32_t)max_rows);
     uint32_t rank = 0;
@@ -209,17 +213,23 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
             if (lane == 0) {
                 if constexpr (PAIR) mbar_arrive_cluster(mapa(tmem_empty0 + 8 * buf, 0)); else mbar_arrive(tmem_empty0 + 8 * buf);
             }
+            if constexpr (SPLITK) {  // raw partial sums of THIS chunk: C[chunk index][row in tile][512]; the accumulator restarts
+                const int prow = m0 + q * 32 + lane;
+                if (prow < rows) {
+                    float *dst = C + ((size_t)((int)blockIdx.z * NCHUNK + ch) * ((size_t)gridDim.y * F_BM) + (size_t)prow) * F_N + n0 + half * 128;
+#pragma unroll
+                    for (int j = 0; j < 128; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                }
+#pragma unroll
+                for (int j = 0; j < 128; ++j) acc[j] = 0.0f;
+            }
         }
         const int row = m0 + q * 32 + lane;
         const size_t coff = (size_t)row * F_N + n0 + half * 128;
         const float *brow = bias + n0 + half * 128;
         const float inv_scale = *inv_scale_p;  // undo the power-of-two weight scaling (exact)
         if constexpr (SPLITK) {
-            if (row < rows) {  // raw partial sums of this chunk: C[z][row in tile][512]
-                float *dst = C + ((size_t)blockIdx.z * ((size_t)gridDim.y * F_BM) + (size_t)row) * F_N + n0 + half * 128;
-#pragma unroll
-                for (int j = 0; j < 128; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            }
+            // (the chunks' partial sums were stored in the drain loop)
         } else if constexpr (HEADS) {
             if (row < rows) {
                 // logits: columns 0..80 policy, 81 value (k_pack_heads); same softmax / tanh arithmetic as k_heads
@@ -412,8 +422,8 @@ struct ActMaps {  // tensor maps over one workspace's activation buffers (each s
     CUtensorMap tower_st_hi, tower_st_lo;  // k_tower16's write-out into act0
     const __half *key[6] = {};  // the six buffers the maps were encoded for (a reallocation may reuse only some addresses)
     int a_rows = 0;
-    float *splitk_partial = nullptr;  // [18 chunks][splitk_rows][512] fp32 partial sums of this workspace's split-K fc0
-    int splitk_rows = 0;
+    float *splitk_partial = nullptr;  // [splitk_chunks][splitk_rows][512] fp32 partial sums of this workspace's split-K fc0
+    int splitk_rows = 0, splitk_chunks = 0;
 };
 struct Fc16State {
     CUtensorMap map0_b_hi, map0_b_lo;  // fc0 (B boxes of 128 rows: the pair kernel loads half tiles)
@@ -518,24 +528,28 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     Fc16State *s = state16_of(c);
     ActMaps *am = s->weights_ready ? refresh_maps16(c, s) : nullptr;
     if (!am) return false;
-    static const int splitk_max = getenv("OMK_FC0_SPLITK_MAX") ? atoi(getenv("OMK_FC0_SPLITK_MAX")) : kSplitKMaxRows;
+    const bool fine = c->fc0_chunk == F_CHUNK0_FINE;
+    static const int splitk_env = getenv("OMK_FC0_SPLITK_MAX") ? atoi(getenv("OMK_FC0_SPLITK_MAX")) : -1;
+    // the fine chunking writes three times the partial sums: its split-K path pays up to 1024 rows only (measured)
+    const int splitk_max = splitk_env >= 0 ? splitk_env : (fine ? 1024 : kSplitKMaxRows);
     if (rows_bound <= splitk_max) {
         // Small and medium batches (a single game's rounds of 8, Agent::new, an arena of 100 games, ...): the pair kernel
         // would stream all of K through a handful of CTA pairs (0.18 ms however few tiles there are); instead every
         // (128-row tile, N half, chunk) is one CTA and k_fc0_reduce adds the chunks in order.
-        constexpr int kChunks = F_K0 / F_BK / F_CHUNK0;
+        const int kChunks = F_K0 / F_BK / (fine ? F_CHUNK0_FINE : F_CHUNK0);
         const int mt = (rows_bound + F_BM - 1) / F_BM, ws_rows = mt * F_BM;
-        if (am->splitk_rows < ws_rows) {  // per workspace: two search lanes may run this path at the same time
+        if (am->splitk_rows < ws_rows || am->splitk_chunks < kChunks) {  // per workspace: two search lanes may run this path at the same time
             cudaFree(am->splitk_partial);
             am->splitk_partial = nullptr;
             am->splitk_rows = 0;
             if (cudaMalloc(&am->splitk_partial, sizeof(float) * (size_t)kChunks * ws_rows * F_N) != cudaSuccess) return false;
             am->splitk_rows = ws_rows;
+            am->splitk_chunks = kChunks;
         }
         using Cfg = FcCfg<false, 256>;
-        auto sk = k_fc16<F_K0, F_CHUNK0, false, 256, false, true>;
+        auto sk = fine ? k_fc16<F_K0, F_CHUNK0_FINE, false, 256, false, true> : k_fc16<F_K0, F_CHUNK0, false, 256, false, true>;
         cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-        sk<<<dim3(F_N / F_BN, mt, kChunks), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+        sk<<<dim3(F_N / F_BN, mt, F_K0 / F_BK / F_SPLITK_KB), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
             am->map0_a_hi, am->map0_a_lo, s->map0s_b_hi, s->map0s_b_lo, c->net.t[24], c->net.fc_inv_scale, am->splitk_partial, nullptr,
             nullptr, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr);
         k_fc0_reduce<<<(rows_bound * 64 + 255) / 256, 256, 0, c->stream>>>(am->splitk_partial, kChunks, ws_rows, c->net.t[24],
@@ -544,7 +558,7 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
         c->launches += 2;
         return check_launch("fc0 (fp16 split, split-K)");
     }
-    auto kern = k_fc16<F_K0, F_CHUNK0, true>;
+    auto kern = fine ? k_fc16<F_K0, F_CHUNK0_FINE, true> : k_fc16<F_K0, F_CHUNK0, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FcCfg<true, 256>::kSmemBytes);
     const int pairs = (rows_bound + 255) / 256;
     cudaLaunchConfig_t cfg{};

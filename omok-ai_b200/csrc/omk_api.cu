@@ -37,6 +37,17 @@ static const long long kLens[kNetTensors] = {
     4096, 32, 288, 1024, 32, 4096, 128,
     10368LL * 512, 512, 512 * 512, 512, 512, 1, 512 * 81, 81};
 
+
+// every host <-> device copy of the API layer is counted in the context (omk_ctx_transfer_bytes; bench.py's e2e bytes)
+static inline cudaError_t copy_h2d(omk_ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    c->h2d_bytes += (int64_t)bytes;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+}
+static inline cudaError_t copy_d2h(omk_ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    c->d2h_bytes += (int64_t)bytes;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+}
+
 extern "C" const char *omk_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t omk_version(void) { return 100; }
 
@@ -167,12 +178,12 @@ static void lanes_join(omk_ctx *c) {  // the main stream continues after lane 1 
 
 static int32_t check_device_error(omk_ctx *c) {
     uint32_t e = 0;
-    CK(cudaMemcpyAsync(&e, c->dev_error, sizeof e, cudaMemcpyDeviceToHost, c->stream));
+    CK(copy_d2h(c, &e, c->dev_error, sizeof e, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     if (e) {
         uint32_t z = 0;
-        cudaMemcpyAsync(c->dev_error, &z, sizeof z, cudaMemcpyHostToDevice, c->stream);
+        copy_h2d(c, c->dev_error, &z, sizeof z, c->stream);
     }
     if (e & 1u) return fail(OMK_ERR_CAPACITY, "a tree ran out of node slots (capacity_nodes=" + std::to_string(c->cap_nodes) + ")");
     if (e & 2u)
@@ -201,7 +212,7 @@ static int32_t stage_ids(omk_ctx *c, const int32_t *ids, int n, const int32_t **
         if (ids[i] >= 0 && ids[i] < limit) c->id_seen[(size_t)ids[i]] = 0;
     if (bad) return fail(OMK_ERR_INVALID, "id out of range");
     if (dup) return fail(OMK_ERR_INVALID, "duplicate id in the id list (ids must be unique within one call)");
-    CK(cudaMemcpyAsync(c->ws.ids, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(copy_h2d(c, c->ws.ids, ids, sizeof(int32_t) * (size_t)n, c->stream));
     *out = c->ws.ids;
     return OMK_OK;
 }
@@ -279,6 +290,7 @@ extern "C" int32_t omk_ctx_create(int32_t device, int32_t capacity_envs, int32_t
     if (const char *m = getenv("OMK_FC0")) c->fc0_mode = parse_mode(m);
     if (const char *m = getenv("OMK_TOWER")) c->tower_mode = parse_mode(m);
     if (const char *m = getenv("OMK_LANE_MIN_TREES")) c->lane_min_trees = atoi(m);
+    if (const char *m = getenv("OMK_FC0_CHUNK")) c->fc0_chunk = atoi(m) == 3 ? 3 : 9;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -368,6 +380,11 @@ extern "C" int32_t omk_ctx_synchronize(omk_ctx *c) {
 }
 extern "C" void *omk_ctx_stream(omk_ctx *c) { return (void *)c->stream; }
 extern "C" int64_t omk_ctx_launch_count(omk_ctx *c) { return c->launches; }
+extern "C" int32_t omk_ctx_transfer_bytes(omk_ctx *c, int64_t *out_h2d, int64_t *out_d2h) {
+    if (out_h2d) *out_h2d = c->h2d_bytes;
+    if (out_d2h) *out_d2h = c->d2h_bytes;
+    return OMK_OK;
+}
 
 // ------------------------------------------------------------------ network
 static int32_t sp_refresh_root_policy(omk_ctx *c);  // self-play driver: re-evaluate the cached empty-board prior
@@ -378,7 +395,7 @@ extern "C" int32_t omk_net_load_params(omk_ctx *c, const float *const *tensors, 
         if (!tensors[i] || lens[i] != kLens[i])
             return fail(OMK_ERR_INVALID, "tensor " + std::to_string(i) + ": expected " + std::to_string(kLens[i]) + " elements");
     for (int i = 0; i < kNetTensors; ++i)
-        CK(cudaMemcpyAsync(c->net.t[i], tensors[i], sizeof(float) * (size_t)kLens[i], cudaMemcpyHostToDevice, c->stream));
+        CK(copy_h2d(c, c->net.t[i], tensors[i], sizeof(float) * (size_t)kLens[i], c->stream));
     net_pack_heads(c);
     if (!fc16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split fc weight preparation failed");
     if (!tower16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split tower weight preparation failed");
@@ -392,7 +409,7 @@ extern "C" int32_t omk_net_get_params(omk_ctx *c, float *const *tensors, const i
     for (int i = 0; i < kNetTensors; ++i)
         if (!tensors[i] || lens[i] != kLens[i]) return fail(OMK_ERR_INVALID, "bad tensor length");
     for (int i = 0; i < kNetTensors; ++i)
-        CK(cudaMemcpyAsync(tensors[i], c->net.t[i], sizeof(float) * (size_t)kLens[i], cudaMemcpyDeviceToHost, c->stream));
+        CK(copy_d2h(c, tensors[i], c->net.t[i], sizeof(float) * (size_t)kLens[i], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return OMK_OK;
 }
@@ -413,7 +430,8 @@ static int32_t net_eval_common(omk_ctx *c, int n, const float *images_dev, float
     // P rows are padded to 96 floats on the device; compact on the way out
     CK(cudaMemcpy2DAsync(out_p, sizeof(float) * kCells, c->ws.P, sizeof(float) * kRow, sizeof(float) * kCells, (size_t)n,
                          cudaMemcpyDeviceToHost, c->stream));
-    if (out_v) CK(cudaMemcpyAsync(out_v, c->ws.V, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    c->d2h_bytes += (int64_t)sizeof(float) * kCells * n;
+    if (out_v) CK(copy_d2h(c, out_v, c->ws.V, sizeof(float) * (size_t)n, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return check_device_error(c);  // OMK_ERR_NUMERIC when the network produced a non-finite output
@@ -430,8 +448,8 @@ extern "C" int32_t omk_net_eval(omk_ctx *c, const uint8_t *boards, const uint8_t
     uint8_t *d_boards = nullptr, *d_turns = nullptr;
     SCRATCH(0, (size_t)n * kCells, d_boards);
     SCRATCH(1, (size_t)n, d_turns);
-    CK(cudaMemcpyAsync(d_boards, boards, (size_t)n * kCells, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_turns, turns, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(copy_h2d(c, d_boards, boards, (size_t)n * kCells, c->stream));
+    CK(copy_h2d(c, d_turns, turns, (size_t)n, c->stream));
     launch_pack_boards(c, d_boards, d_turns, n, mode);
     return net_eval_common(c, n, nullptr, out_p, out_v);
 }
@@ -445,9 +463,9 @@ extern "C" int32_t omk_net_eval_images(omk_ctx *c, const float *images, int32_t 
     if (rc) return rc;
     float *d_img = nullptr;
     SCRATCH(0, (size_t)n * 243, d_img);
-    CK(cudaMemcpyAsync(d_img, images, sizeof(float) * (size_t)n * 243, cudaMemcpyHostToDevice, c->stream));
+    CK(copy_h2d(c, d_img, images, sizeof(float) * (size_t)n * 243, c->stream));
     const uint32_t nn = (uint32_t)n;
-    CK(cudaMemcpyAsync(c->ws.n_req, &nn, sizeof nn, cudaMemcpyHostToDevice, c->stream));
+    CK(copy_h2d(c, c->ws.n_req, &nn, sizeof nn, c->stream));
     return net_eval_common(c, n, d_img, out_p, out_v);
 }
 
@@ -505,7 +523,7 @@ extern "C" int32_t omk_train_get_grads(omk_ctx *c, float *const *tensors, const 
     long long off = 0;
     for (int i = 0; i < kNetTensors; ++i) {
         if (!tensors[i] || lens[i] != kLens[i]) return fail(OMK_ERR_INVALID, "bad tensor length");
-        CK(cudaMemcpyAsync(tensors[i], g + off, sizeof(float) * (size_t)kLens[i], cudaMemcpyDeviceToHost, c->stream));
+        CK(copy_d2h(c, tensors[i], g + off, sizeof(float) * (size_t)kLens[i], c->stream));
         off += kLens[i];
     }
     CK(cudaStreamSynchronize(c->stream));
@@ -547,6 +565,12 @@ extern "C" int32_t omk_debug_set_tower_mode(omk_ctx *c, int32_t mode) {
     c->tower_mode = mode;
     return OMK_OK;
 }
+extern "C" int32_t omk_debug_set_fc0_chunk(omk_ctx *c, int32_t k_blocks) {
+    if (k_blocks != 3 && k_blocks != 9) return fail(OMK_ERR_INVALID, "fc0 chunk must be 9 (default) or 3 (finer accumulation)");
+    CK(cudaStreamSynchronize(c->stream));
+    c->fc0_chunk = k_blocks;
+    return OMK_OK;
+}
 extern "C" int32_t omk_debug_set_lane_min_trees(omk_ctx *c, int32_t min_trees) {
     if (min_trees < 0) return fail(OMK_ERR_INVALID, "min_trees < 0");
     c->lane_min_trees = min_trees;
@@ -568,13 +592,13 @@ extern "C" int32_t omk_debug_get_buffer(omk_ctx *c, int32_t which, float *out, i
         float *tmp = nullptr;
         SCRATCH(0, (size_t)(count > 0 ? count : 1), tmp);
         launch_split16_to_f32(c, hi, lo, tmp, count);
-        CK(cudaMemcpyAsync(out, tmp, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+        CK(copy_d2h(c, out, tmp, sizeof(float) * (size_t)count, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return OMK_OK;
     }
     const float *src = which == 0 ? c->ws.act0 : which == 1 ? c->ws.act1 : which == 2 ? c->ws.act2 : which == 3 ? c->ws.logits : nullptr;
     if (!src || !out || count < 0) return fail(OMK_ERR_INVALID, "bad buffer id");
-    CK(cudaMemcpyAsync(out, src, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    CK(copy_d2h(c, out, src, sizeof(float) * (size_t)count, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return OMK_OK;
 }
@@ -604,10 +628,10 @@ extern "C" int32_t omk_env_step(omk_ctx *c, const int32_t *ids, const uint8_t *a
     SCRATCH(0, (size_t)n, d_act);
     SCRATCH(1, (size_t)n, d_st);
     if (out_legal) SCRATCH(2, 3 * (size_t)n, d_legal);
-    CK(cudaMemcpyAsync(d_act, actions, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(copy_h2d(c, d_act, actions, (size_t)n, c->stream));
     launch_env_step(c, d_ids, d_act, n, d_st, d_legal);
-    if (out_status) CK(cudaMemcpyAsync(out_status, d_st, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    if (out_legal) CK(cudaMemcpyAsync(out_legal, d_legal, sizeof(uint32_t) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_status) CK(copy_d2h(c, out_status, d_st, (size_t)n, c->stream));
+    if (out_legal) CK(copy_d2h(c, out_legal, d_legal, sizeof(uint32_t) * 3 * (size_t)n, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return OMK_OK;
@@ -633,9 +657,9 @@ extern "C" int32_t omk_env_get(omk_ctx *c, const int32_t *ids, int32_t n, uint8_
     SCRATCH(1, (size_t)n, d_t);
     SCRATCH(2, (size_t)n, d_l);
     launch_env_get(c, d_ids, n, d_b, d_t, d_l);
-    if (out_boards) CK(cudaMemcpyAsync(out_boards, d_b, (size_t)n * kCells, cudaMemcpyDeviceToHost, c->stream));
-    if (out_turns) CK(cudaMemcpyAsync(out_turns, d_t, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    if (out_legal_counts) CK(cudaMemcpyAsync(out_legal_counts, d_l, sizeof(uint16_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_boards) CK(copy_d2h(c, out_boards, d_b, (size_t)n * kCells, c->stream));
+    if (out_turns) CK(copy_d2h(c, out_turns, d_t, (size_t)n, c->stream));
+    if (out_legal_counts) CK(copy_d2h(c, out_legal_counts, d_l, sizeof(uint16_t) * (size_t)n, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return OMK_OK;
 }
@@ -650,8 +674,8 @@ extern "C" int32_t omk_env_set(omk_ctx *c, const int32_t *ids, int32_t n, const 
     uint8_t *d_b = nullptr, *d_t = nullptr;
     SCRATCH(0, (size_t)n * kCells, d_b);
     SCRATCH(1, (size_t)n, d_t);
-    CK(cudaMemcpyAsync(d_b, boards, (size_t)n * kCells, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_t, turns, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(copy_h2d(c, d_b, boards, (size_t)n * kCells, c->stream));
+    CK(copy_h2d(c, d_t, turns, (size_t)n, c->stream));
     launch_env_set(c, d_ids, n, d_b, d_t);
     CK(cudaStreamSynchronize(c->stream));
     return OMK_OK;
@@ -668,7 +692,7 @@ extern "C" int32_t omk_env_encode(omk_ctx *c, const int32_t *ids, int32_t n, int
     float *d_o = nullptr;
     SCRATCH(0, 243 * (size_t)n, d_o);
     launch_env_encode(c, d_ids, n, mode, d_o);
-    CK(cudaMemcpyAsync(out, d_o, sizeof(float) * 243 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(copy_d2h(c, out, d_o, sizeof(float) * 243 * (size_t)n, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return OMK_OK;
 }
@@ -683,8 +707,8 @@ extern "C" int32_t omk_env_random_playout(omk_ctx *c, int32_t n, int32_t plies, 
     if (out_actions) SCRATCH(0, tot, d_a);
     if (out_status) SCRATCH(1, tot, d_s);
     launch_env_playout(c, n, plies, d_a, d_s);
-    if (out_actions) CK(cudaMemcpyAsync(out_actions, d_a, tot, cudaMemcpyDeviceToHost, c->stream));
-    if (out_status) CK(cudaMemcpyAsync(out_status, d_s, tot, cudaMemcpyDeviceToHost, c->stream));
+    if (out_actions) CK(copy_d2h(c, out_actions, d_a, tot, c->stream));
+    if (out_status) CK(copy_d2h(c, out_status, d_s, tot, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return OMK_OK;
@@ -703,7 +727,7 @@ extern "C" int32_t omk_pool_new_games(omk_ctx *c, const int32_t *ids, int32_t n,
     if (rc) return rc;
     const uint32_t *d_streams = nullptr;
     if (streams) {
-        CK(cudaMemcpyAsync(c->ws.streams, streams, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        CK(copy_h2d(c, c->ws.streams, streams, sizeof(uint32_t) * (size_t)n, c->stream));
         d_streams = c->ws.streams;
     }
     launch_reset_requests(c);
@@ -763,16 +787,16 @@ extern "C" int32_t omk_pool_sample(omk_ctx *c, const int32_t *ids, int32_t n, co
         bool any_boltz = false;
         for (int i = 0; i < n; ++i) any_boltz |= modes[i] == OMK_SAMPLE_BOLTZMANN;
         if (any_boltz && !temperatures) return fail(OMK_ERR_INVALID, "Boltzmann sampling needs temperatures");
-        CK(cudaMemcpyAsync(c->ws.modes, modes, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        CK(copy_h2d(c, c->ws.modes, modes, (size_t)n, c->stream));
         d_modes = c->ws.modes;
         if (temperatures) {
-            CK(cudaMemcpyAsync(c->ws.temps, temperatures, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+            CK(copy_h2d(c, c->ws.temps, temperatures, sizeof(float) * (size_t)n, c->stream));
             d_temps = c->ws.temps;
         }
     }
     launch_sample(c, d_ids, n, d_modes, d_temps, c->ws.actions, c->ws.policy_out, nullptr);
-    if (out_actions) CK(cudaMemcpyAsync(out_actions, c->ws.actions, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    if (out_policy) CK(cudaMemcpyAsync(out_policy, c->ws.policy_out, sizeof(float) * kCells * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_actions) CK(copy_d2h(c, out_actions, c->ws.actions, sizeof(int32_t) * (size_t)n, c->stream));
+    if (out_policy) CK(copy_d2h(c, out_policy, c->ws.policy_out, sizeof(float) * kCells * (size_t)n, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return OMK_OK;
@@ -785,8 +809,8 @@ extern "C" int32_t omk_pool_policy(omk_ctx *c, const int32_t *ids, int32_t n, fl
     if (rc) return rc;
     if (n == 0) return OMK_OK;
     launch_sample(c, d_ids, n, nullptr, nullptr, nullptr, c->ws.policy_out, c->ws.modes);
-    if (out_policy) CK(cudaMemcpyAsync(out_policy, c->ws.policy_out, sizeof(float) * kCells * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    if (out_valid) CK(cudaMemcpyAsync(out_valid, c->ws.modes, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_policy) CK(copy_d2h(c, out_policy, c->ws.policy_out, sizeof(float) * kCells * (size_t)n, c->stream));
+    if (out_valid) CK(copy_d2h(c, out_valid, c->ws.modes, (size_t)n, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return OMK_OK;
@@ -803,7 +827,7 @@ extern "C" int32_t omk_pool_ensure_action(omk_ctx *c, const int32_t *ids, const 
     if (n == 0) return OMK_OK;
     rc = ensure_workspace(c, n);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(c->ws.actions, actions, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(copy_h2d(c, c->ws.actions, actions, sizeof(int32_t) * (size_t)n, c->stream));
     launch_reset_requests(c);
     launch_ensure_prepare(c, d_ids, c->ws.actions, n);
     RUN_EVAL(c, evaluator, n);
@@ -818,9 +842,9 @@ extern "C" int32_t omk_pool_play(omk_ctx *c, const int32_t *ids, const int32_t *
     int32_t rc = stage_ids(c, ids, n, &d_ids, c->cap_trees);
     if (rc) return rc;
     if (n == 0) return OMK_OK;
-    CK(cudaMemcpyAsync(c->ws.actions, actions, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(copy_h2d(c, c->ws.actions, actions, sizeof(int32_t) * (size_t)n, c->stream));
     launch_play(c, d_ids, c->ws.actions, n, c->ws.status);
-    if (out_status) CK(cudaMemcpyAsync(out_status, c->ws.status, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_status) CK(copy_d2h(c, out_status, c->ws.status, (size_t)n, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return OMK_OK;
@@ -841,7 +865,7 @@ static int32_t dump_root(omk_ctx *c, int32_t id, RootDump *host) {
     RootDump *d = nullptr;
     SCRATCH(0, 1, d);
     launch_root_children(c, id, d->actions, d->n, d->w, d->p, &d->len, d->policy, d->misc);
-    CK(cudaMemcpyAsync(host, d, sizeof(RootDump), cudaMemcpyDeviceToHost, c->stream));
+    CK(copy_d2h(c, host, d, sizeof(RootDump), c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return OMK_OK;
@@ -910,10 +934,10 @@ extern "C" int32_t omk_pool_get_envs(omk_ctx *c, const int32_t *ids, int32_t n, 
     const size_t nn = (size_t)n, off_t = nn * kCells, off_s = off_t + nn, off_l = (off_s + nn + 1) & ~(size_t)1;
     SCRATCH(0, off_l + 2 * nn, blk);
     launch_pool_get_envs(c, d_ids, n, blk, blk + off_t, reinterpret_cast<uint16_t *>(blk + off_l), reinterpret_cast<int8_t *>(blk + off_s));
-    if (out_boards) CK(cudaMemcpyAsync(out_boards, blk, nn * kCells, cudaMemcpyDeviceToHost, c->stream));
-    if (out_turns) CK(cudaMemcpyAsync(out_turns, blk + off_t, nn, cudaMemcpyDeviceToHost, c->stream));
-    if (out_status) CK(cudaMemcpyAsync(out_status, blk + off_s, nn, cudaMemcpyDeviceToHost, c->stream));
-    if (out_legal_counts) CK(cudaMemcpyAsync(out_legal_counts, blk + off_l, 2 * nn, cudaMemcpyDeviceToHost, c->stream));
+    if (out_boards) CK(copy_d2h(c, out_boards, blk, nn * kCells, c->stream));
+    if (out_turns) CK(copy_d2h(c, out_turns, blk + off_t, nn, c->stream));
+    if (out_status) CK(copy_d2h(c, out_status, blk + off_s, nn, c->stream));
+    if (out_legal_counts) CK(copy_d2h(c, out_legal_counts, blk + off_l, 2 * nn, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return OMK_OK;
@@ -970,7 +994,7 @@ static int32_t sp_refresh_root_policy(omk_ctx *c) {
     const SpLayout L = sp_layout(c, c->sp_cfg.n_games);
     const uint32_t one = 1;
     CK(cudaMemsetAsync(c->ws.nn_in, 0, sizeof(NNIn), c->stream));  // empty board, Black to move, EnvTurnMode::Player (== k_new_games' request)
-    CK(cudaMemcpyAsync(c->ws.n_req, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
+    CK(copy_h2d(c, c->ws.n_req, &one, sizeof one, c->stream));
     if (!net_forward(c, nullptr, 1)) return fail(OMK_ERR_CUDA, "re-evaluating the empty board after a weight change failed");
     CK(cudaMemcpyAsync(L.root_policy, c->ws.P, sizeof(float) * kCells, cudaMemcpyDeviceToDevice, c->stream));
     launch_reset_requests(c);
@@ -1067,8 +1091,8 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
         return OMK_OK;
     };
     unsigned long long h_before[2] = {0, 0}, h_after[2] = {0, 0}, h_fin0 = 0, h_fin1 = 0;
-    CK(cudaMemcpyAsync(h_before, c->dev_sims, sizeof h_before, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&h_fin0, counters, sizeof h_fin0, cudaMemcpyDeviceToHost, c->stream));
+    CK(copy_d2h(c, h_before, c->dev_sims, sizeof h_before, c->stream));
+    CK(copy_d2h(c, &h_fin0, counters, sizeof h_fin0, c->stream));
     CK(cudaStreamSynchronize(c->stream));
 
     c->prof_level = profile;
@@ -1146,10 +1170,10 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
         if (want_out) {  // this ply's slice -> pinned host mirror, behind both lanes' recording kernels
             for (int l = 0; l < lanes; ++l) CK(cudaStreamWaitEvent(c->sp_copy_stream, c->sp_ev_rec[ply % kRing][l], 0));
             uint8_t *hs = c->sp_ring_host + (size_t)(ply % kRing) * slot.bytes;
-            if (out_boards) { CK(cudaMemcpyAsync(hs + slot.off_boards, d_boards, (size_t)n * kCells, cudaMemcpyDeviceToHost, c->sp_copy_stream)); d2h += (size_t)n * kCells; }
-            if (out_policy) { CK(cudaMemcpyAsync(hs + slot.off_policy, d_policy, (size_t)n * kCells * sizeof(float), cudaMemcpyDeviceToHost, c->sp_copy_stream)); d2h += (size_t)n * kCells * 4; }
-            if (out_actions) { CK(cudaMemcpyAsync(hs + slot.off_actions, d_actions, (size_t)n * 4, cudaMemcpyDeviceToHost, c->sp_copy_stream)); d2h += (size_t)n * 4; }
-            if (out_status) { CK(cudaMemcpyAsync(hs + slot.off_status, d_status, (size_t)n, cudaMemcpyDeviceToHost, c->sp_copy_stream)); d2h += (size_t)n; }
+            if (out_boards) { CK(copy_d2h(c, hs + slot.off_boards, d_boards, (size_t)n * kCells, c->sp_copy_stream)); d2h += (size_t)n * kCells; }
+            if (out_policy) { CK(copy_d2h(c, hs + slot.off_policy, d_policy, (size_t)n * kCells * sizeof(float), c->sp_copy_stream)); d2h += (size_t)n * kCells * 4; }
+            if (out_actions) { CK(copy_d2h(c, hs + slot.off_actions, d_actions, (size_t)n * 4, c->sp_copy_stream)); d2h += (size_t)n * 4; }
+            if (out_status) { CK(copy_d2h(c, hs + slot.off_status, d_status, (size_t)n, c->sp_copy_stream)); d2h += (size_t)n; }
             CK(cudaEventRecord(c->sp_ev_copy[ply % kRing], c->sp_copy_stream));
             // the device slot is recorded into again kRing plies from now: by then the host has waited for this copy (drain)
         }
@@ -1166,8 +1190,8 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
             int32_t rc_d = drain(ply);
             if (rc_d) return rc_d;
         }
-    CK(cudaMemcpyAsync(h_after, c->dev_sims, sizeof h_after, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&h_fin1, counters, sizeof h_fin1, cudaMemcpyDeviceToHost, c->stream));
+    CK(copy_d2h(c, h_after, c->dev_sims, sizeof h_after, c->stream));
+    CK(copy_d2h(c, &h_fin1, counters, sizeof h_fin1, c->stream));
     int32_t rc = check_device_error(c);
     if (stats) {
         memset(stats, 0, sizeof *stats);

@@ -76,6 +76,7 @@ struct omk_ctx {
     uint64_t seed = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;  // host <-> device bytes copied by the API layer since creation
     // Second search lane: large searches split their trees into two halves that run as two independent chains of
     // kernels on two streams with two evaluator workspaces.  Trees never interact, so the split changes no result; the
     // latency-bound tree kernels of one half then overlap the (tensor-bound, register-light) fc0 of the other half.
@@ -99,6 +100,7 @@ struct omk_ctx {
 
     omk::NetWeights net;
     omk::Workspace ws;
+    int fc0_chunk = 9;              // k-blocks of fc0 accumulated in tensor memory per drain: 9 (default) or 3 (finer, more accurate; fc_f16.cu)
     int fc0_mode = 1;               // fc0 + fc1: 1 = tcgen05 3xFP16 k_fc16 (the product path), 0 = fp32 CUDA-core k_gemm (A/B check only)
     void *fc16_state = nullptr;     // tensor maps of the fp16-split path (fc_f16.cu)
     int tower16_pairs = 0;          // resident CTA pairs of k_tower16 (0 = not queried yet)

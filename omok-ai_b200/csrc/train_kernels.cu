@@ -243,10 +243,14 @@ __global__ void k_loss(const float *__restrict__ logits /*[n][81]*/, const float
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) pl += __shfl_xor_sync(0xffffffffu, pl, off);
     if (lane == 0) {
-        const float val = tanhf(vlogit[row]), d = val - z[row];
+        // tanh and its derivative from one exponential: 1 - tanh^2 = 4e / (1 + e)^2 with e = exp(-2|x|) keeps its relative
+        // accuracy where tanh saturates (value logits have a scale of ~20; 1 - v*v would cancel to a few bits there)
+        const float xl = vlogit[row], ex2 = expf(-2.0f * fabsf(xl)), den = 1.0f + ex2;
+        const float val = copysignf((1.0f - ex2) / den, xl), sech2 = 4.0f * ex2 / (den * den);
+        const float d = val - z[row];
         row_loss[2 * row] = pl;
         row_loss[2 * row + 1] = d * d;
-        if (dvlogit) dvlogit[row] = 2.0f * d * (1.0f - val * val) * invn;
+        if (dvlogit) dvlogit[row] = 2.0f * d * sech2 * invn;
     }
 }
 // (p_loss, v_loss, loss) = means over the rows, summed in row order by one thread per term (n is a minibatch)
@@ -483,6 +487,7 @@ static void train_backward(omk_ctx *c, TrainState *t, int n) {
 }
 
 static bool train_upload(omk_ctx *c, TrainState *t, const float *images, const float *pi, const float *z, int n) {
+    c->h2d_bytes += (int64_t)sizeof(float) * (int64_t)n * (243 + kCells + 1);
     return cudaMemcpyAsync(t->img, images, sizeof(float) * (size_t)n * 243, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
            cudaMemcpyAsync(t->pi, pi, sizeof(float) * (size_t)n * kCells, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
            cudaMemcpyAsync(t->z, z, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;

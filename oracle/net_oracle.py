@@ -212,7 +212,7 @@ def loss_and_grads(params: list[np.ndarray], images: np.ndarray, pi: np.ndarray,
     loss = v_loss + p_loss
     loss.backward()
     grads = [p[name].grad.detach().numpy() for name, _ in PARAM_SPECS]
-    return (float(p_loss), float(v_loss), float(loss)), grads
+    return (p_loss.item(), v_loss.item(), loss.item()), grads
 
 
 def forward_layers(params: list[np.ndarray], images: np.ndarray, dtype=torch.float64) -> dict[str, np.ndarray]:

@@ -63,6 +63,7 @@ extern "C" {
     pub fn omk_ctx_synchronize(ctx: *mut omk_ctx) -> i32;
     pub fn omk_ctx_stream(ctx: *mut omk_ctx) -> *mut c_void;
     pub fn omk_ctx_launch_count(ctx: *mut omk_ctx) -> i64;
+    pub fn omk_ctx_transfer_bytes(ctx: *mut omk_ctx, out_h2d: *mut i64, out_d2h: *mut i64) -> i32;
     // network (alpha-zero/src/agent_model.rs:105-134, network.rs:51-262)
     pub fn omk_net_load_params(ctx: *mut omk_ctx, tensors: *const *const f32, lens: *const i64) -> i32;
     pub fn omk_net_get_params(ctx: *mut omk_ctx, tensors: *const *mut f32, lens: *const i64) -> i32;
@@ -81,6 +82,7 @@ extern "C" {
     // diagnostics
     pub fn omk_debug_set_fc0_mode(ctx: *mut omk_ctx, mode: i32) -> i32;
     pub fn omk_debug_set_tower_mode(ctx: *mut omk_ctx, mode: i32) -> i32;
+    pub fn omk_debug_set_fc0_chunk(ctx: *mut omk_ctx, k_blocks: i32) -> i32;
     pub fn omk_debug_tower_timing(ctx: *mut omk_ctx, out64: *mut i64) -> i32;
     pub fn omk_debug_get_buffer(ctx: *mut omk_ctx, which: i32, out: *mut f32, count: i64) -> i32;
     pub fn omk_debug_set_lane_min_trees(ctx: *mut omk_ctx, min_trees: i32) -> i32;

@@ -249,3 +249,76 @@ def test_tensor_core_kernels_are_in_the_library(omk):
     sass = subprocess.run(["cuobjdump", "-sass", omk.lib_path()], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UBLKCP", "LDTM", "STTM"):
         assert mnemonic in sass, mnemonic
+
+
+def banded_positions(n, seed):
+    """Thirds of early (0-30 stones), middle (30-60) and late (60-80 stones) boards."""
+    rng = np.random.default_rng(seed)
+    boards = np.zeros((n, 81), np.uint8)
+    turns = np.zeros(n, np.uint8)
+    for b in range(n):
+        lo, hi = ((0, 31), (30, 61), (60, 81))[b % 3]
+        k = int(rng.integers(lo, hi))
+        cells = rng.permutation(81)[:k]
+        boards[b, cells[0::2]] = 1
+        boards[b, cells[1::2]] = 2
+        turns[b] = k % 2
+    return boards, turns
+
+
+@pytest.mark.parametrize("chunk,bar", [(9, 3.0e-4), (3, 2.4e-4)])
+def test_large_sample_error_margin(omk, chunk, bar):
+    """the margin to the 1e-3 bar on a LARGE sample -- 6 000 positions per weight seed including
+    60-80-stone boards, both EnvTurnMode encodings, two seeds (profiles/r02_net_error_study.md has 20 000 x 3 seeds + a
+    trained-scale set: max 2.1e-4 with the default chunking, 1.6e-4 with fc0_chunk = 3).  Priors: relative error
+    below `bar` (3.3x / 4.2x inside the north-star tolerance).  Values: tanh of a logit of scale ~20 -- near a zero crossing a
+    relative error is ill-conditioned for ANY fp32 forward, so values are held to 2e-4 absolute everywhere and to 1e-3
+    relative where |v| >= 0.1."""
+    import torch
+
+    from oracle import net_oracle as no
+
+    ctx = omk.Context(device=0, capacity_envs=1, capacity_trees=1, capacity_nodes=16, seed=0)
+    ctx.debug_set_fc0_chunk(chunk)
+    boards, turns = banded_positions(6000, 777)
+    modes = (np.arange(6000) // 3) % 2
+    worst = 0.0
+    for seed in (0, 5):
+        params = no.random_params(seed)
+        ctx.net_load_params(params)
+        for md in (0, 1):
+            idx = np.flatnonzero(modes == md)
+            p, v = ctx.net_eval(boards[idx], turns[idx], mode=md)
+            imgs = np.stack([no.encode_image(b, int(t), bool(md)) for b, t in zip(boards[idx], turns[idx])])
+            ref = no.forward_layers(params, imgs, torch.float64)
+            big = ref["P"] > 1e-12
+            rel = np.abs(p.astype(np.float64) - ref["P"])[big] / ref["P"][big]
+            worst = max(worst, float(rel.max()))
+            assert rel.max() < bar, f"seed {seed} mode {md}: max relative prior error {rel.max():.2e}"
+            dv = np.abs(v.astype(np.float64) - ref["V"])
+            assert dv.max() < 2e-4
+            far = np.abs(ref["V"]) >= 0.1
+            assert (dv[far] / np.abs(ref["V"][far])).max() < 1e-3
+    ctx.close()
+    print(f"fc0 chunk {chunk}: worst relative prior error {worst:.2e}")
+
+
+def test_fc0_fine_chunk_keeps_batch_invariance(omk):
+    """fc0_chunk = 3 (finer TMEM accumulation): rows stay bit-identical whatever the batch size and whichever fc0 path the
+    batch takes (split-K up to 1024 rows with this chunking, CTA pairs above), and differ from the default chunking only
+    in the last bits."""
+    from oracle import net_oracle
+
+    ctx = omk.Context(device=0, capacity_envs=1, capacity_trees=1, capacity_nodes=16, seed=0)
+    ctx.net_load_params(net_oracle.random_params(0))
+    boards, turns = random_positions(2600, 44)
+    p9, v9 = ctx.net_eval(boards, turns)
+    ctx.debug_set_fc0_chunk(3)
+    P, V = ctx.net_eval(boards, turns)  # 2600 rows: CTA-pair path
+    for lo, hi in ((0, 8), (3, 900), (1000, 2024), (1500, 2600), (2599, 2600)):  # split-K (<= 1024 rows) and pair sub-batches
+        q, w = ctx.net_eval(boards[lo:hi], turns[lo:hi])
+        assert q.tobytes() == P[lo:hi].tobytes() and w.tobytes() == V[lo:hi].tobytes()
+    assert np.max(np.abs(P - p9) / np.maximum(p9, 1e-12)) < 1e-3 and P.tobytes() != p9.tobytes()
+    with pytest.raises(omk.OmkError):
+        ctx.debug_set_fc0_chunk(5)
+    ctx.close()
