@@ -228,6 +228,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="N > 1: also merge every rank's streamed transitions on rank 0 (BASELINE configs[3]'s host replay buffer) and report the merge time")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,6 +280,17 @@ def main():
     launches = ctx.launch_count - launches0
     assert t_boards.shape == (steps, games, 81) and int(stats.d2h_bytes) == steps * games * (81 + 81 * 4 + 4 + 1)
     stream_d2h = int(stats.d2h_bytes)
+    merge = None
+    if args.gather and dist:  # the host replay buffer of configs[3]: all ranks' blocks of the timed region land on rank 0
+        barrier()
+        tm = time.perf_counter()
+        merged = sharding.gather_replay(torch.from_numpy(t_boards).cuda(), torch.from_numpy(t_policy).cuda(), torch.from_numpy(t_status).cuda())
+        host = [m.cpu() for m in merged] if merged is not None else None
+        barrier()
+        merge = {"seconds": time.perf_counter() - tm, "games_on_rank0": int(host[0].shape[1]) if host else None,
+                 "bytes_on_rank0": int(sum(h.numel() * h.element_size() for h in host)) if host else None,
+                 "path": "sharding.gather_replay: per-rank [plies, games, ...] blocks all-gathered over NCCL, concatenated along the game axis on rank 0, copied to host",
+                 "in_timed_region": False}
     ctx.selfplay_run(1, profile=0, want_transitions=False)  # keeps the load on while the last samples arrive (untimed)
     barrier()
     clocks = sampler.stop()
@@ -434,6 +446,7 @@ def main():
                                   "bytes_per_position": 81 + 81 * 4 + 4 + 1,
                                   "path": "omk_selfplay_run: four-slot device ring -> pinned host mirror on a copy stream -> caller's arrays"},
             "gpu_launches": launches,
+            "replay_merge": merge,
             "roofline": dominant,
             "roofline_second": other,
             "roofline_network": roof_net,

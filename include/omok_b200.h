@@ -220,10 +220,10 @@ OMK_API int32_t omk_pool_tree_info(omk_ctx *ctx, int32_t id, int32_t *out_nodes,
  * mover-view z placeholder, game id, ply) stream to a pinned host ring.          */
 /* kernel families for profiling spans */
 enum {
-    OMK_K_TOWER = 0,      /* k_tower: stem + 3 bottleneck blocks */
-    OMK_K_FC0 = 1,        /* k_gemm 10368 -> 512 (67 % of the network's flops) */
-    OMK_K_FC1 = 2,        /* k_gemm 512 -> 512 */
-    OMK_K_HEADS = 3,      /* k_gemm 512 -> 82 + k_heads (tanh / softmax) */
+    OMK_K_TOWER = 0,      /* k_tower16: stem + 3 bottleneck blocks (tcgen05 kind::f16, 3-pass fp16 hi/lo split) */
+    OMK_K_FC0 = 1,        /* k_fc16<10368>: fc0 10368 -> 512, CTA pairs / split-K + k_fc0_reduce (67 % of the network's flops) */
+    OMK_K_FC1 = 2,        /* k_fc16<512>: fc1 512 -> 512 */
+    OMK_K_HEADS = 3,      /* k_fc16<512, HEADS>: policy + value heads with tanh / softmax in the epilogue */
     OMK_K_HASH = 4,       /* k_eval_hash */
     OMK_K_SELECT = 5,     /* k_select_expand (+ request counter reset) */
     OMK_K_APPLY = 6,      /* k_apply */
