@@ -184,6 +184,13 @@ OMK_API int32_t omk_pool_new_games(omk_ctx *ctx, const int32_t *ids, int32_t n, 
  * {batch selections+expansions per tree, one NN batch over all trees, apply+backup}. */
 OMK_API int32_t omk_pool_search(omk_ctx *ctx, const int32_t *ids, int32_t n, int32_t count, int32_t batch_size,
                         float epsilon, float alpha, int32_t evaluator);
+/* OPT-IN, NOT the reference's search: virtual loss inside a round (north_star's "PUCT selection with virtual loss").
+ * The reference reads the statistics as they are (parallel_mcts_executor.rs:80-90), so a round's `batch_size`
+ * selections of a tree usually return the same leaf; with this switch on, every pending evaluation counts as one visit
+ * of value -1 along its path until its network result replaces it, which spreads a round over different lines.  Visit
+ * counts then differ from the reference's by design: default OFF (env OMK_SEARCH_VIRTUAL_LOSS=1 turns it on at context
+ * creation), and searches with the parity evaluator (OMK_EVAL_HASH) are refused while it is on.                       */
+OMK_API int32_t omk_search_set_virtual_loss(omk_ctx *ctx, int32_t enabled);
 /* Agent::sample_action: modes[n] (OMK_SAMPLE_*), temperatures[n] (Boltzmann only);
  * out_actions[n] (OMK_NONE if the policy is empty), out_policy[n*81] un-heated pi.  */
 OMK_API int32_t omk_pool_sample(omk_ctx *ctx, const int32_t *ids, int32_t n, const uint8_t *modes,

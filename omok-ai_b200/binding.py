@@ -127,6 +127,7 @@ def load_library():
     L.omk_env_random_playout.argtypes = [vp, i32, i32, vp, vp]
     L.omk_pool_new_games.argtypes = [vp, vp, i32, vp, i32]
     L.omk_pool_search.argtypes = [vp, vp, i32, i32, i32, f32, f32, i32]
+    L.omk_search_set_virtual_loss.argtypes = [vp, i32]
     L.omk_pool_sample.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.omk_pool_policy.argtypes = [vp, vp, i32, vp, vp]
     L.omk_pool_ensure_action.argtypes = [vp, vp, vp, i32, i32]
@@ -363,6 +364,10 @@ class Context:
         ids = _ids(ids)
         n = len(ids) if ids is not None else n
         self._check(self.L.omk_pool_search(self.h, _ptr(ids), n, count, batch_size, epsilon, alpha, evaluator))
+
+    def search_set_virtual_loss(self, enabled: bool):
+        """Opt-in, non-reference search mode (see include/omok_b200.h); refused with EVAL_HASH while on."""
+        self._check(self.L.omk_search_set_virtual_loss(self.h, 1 if enabled else 0))
 
     def pool_sample(self, ids=None, n=None, modes=None, temperatures=None):
         ids = _ids(ids)

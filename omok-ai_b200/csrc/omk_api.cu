@@ -258,6 +258,8 @@ static bool run_evaluator(omk_ctx *c, int evaluator, int rows_bound) {
 
 static int32_t check_evaluator(omk_ctx *c, int evaluator) {
     if (evaluator != OMK_EVAL_NET && evaluator != OMK_EVAL_HASH) return fail(OMK_ERR_INVALID, "unknown evaluator");
+    if (evaluator == OMK_EVAL_HASH && c->virtual_loss)
+        return fail(OMK_ERR_STATE, "virtual loss is a non-reference search mode: it is refused with the parity evaluator (OMK_EVAL_HASH)");
     if (evaluator == OMK_EVAL_NET && !c->net.loaded) return fail(OMK_ERR_STATE, "network weights not loaded");
     return OMK_OK;
 }
@@ -291,6 +293,7 @@ extern "C" int32_t omk_ctx_create(int32_t device, int32_t capacity_envs, int32_t
     if (const char *m = getenv("OMK_TOWER")) c->tower_mode = parse_mode(m);
     if (const char *m = getenv("OMK_LANE_MIN_TREES")) c->lane_min_trees = atoi(m);
     if (const char *m = getenv("OMK_FC0_CHUNK")) c->fc0_chunk = atoi(m) == 3 ? 3 : 9;
+    if (const char *m = getenv("OMK_SEARCH_VIRTUAL_LOSS")) c->virtual_loss = atoi(m) != 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
@@ -772,6 +775,12 @@ extern "C" int32_t omk_pool_search(omk_ctx *c, const int32_t *ids, int32_t n, in
     }
     if (lanes == 2) lanes_join(c);
     return check_device_error(c);
+}
+
+extern "C" int32_t omk_search_set_virtual_loss(omk_ctx *c, int32_t enabled) {
+    CK(cudaStreamSynchronize(c->stream));
+    c->virtual_loss = enabled != 0;
+    return OMK_OK;
 }
 
 extern "C" int32_t omk_pool_sample(omk_ctx *c, const int32_t *ids, int32_t n, const uint8_t *modes, const float *temperatures,

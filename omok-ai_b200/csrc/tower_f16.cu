@@ -23,7 +23,8 @@
 // TMEM columns: X/D3 [0,128)  16-channel group kk of x: hi [16kk,16kk+8) lo [16kk+8,16kk+16); the conv2 accumulator
 //                             D3 (fp32, 128 columns) aliases it: x's TMEM copy is dead once conv0 has read it
 //               H    [128,160) 16-channel group g of the block's hidden activations, same hi/lo packing
-//               ACC  [160,192) the conv0 / conv1 accumulator (fp32, 32 columns); [192,256) unused (allocations are powers of two)
+//               ACC  [160,192) the conv0 / conv1 accumulator (fp32, 32 columns)
+//               ONE  [192,200) constant A group of the bias MMA (k = 0, 1: 64.0; k = 2..15: 0); [200,256) unused (allocations are powers of two)
 #include <cstdio>
 #include <cstdlib>
 
@@ -36,11 +37,18 @@ using namespace tc;
 
 constexpr int T16_THREADS = 256;
 constexpr uint32_t T16_TMEM_COLS = 256;
-constexpr uint32_t TC_X = 0, TC_D3 = 0, TC_H = 128, TC_ACC = 160;
+constexpr uint32_t TC_X = 0, TC_D3 = 0, TC_H = 128, TC_ACC = 160, TC_ONE = 192;  // TC_ONE: 8 columns, the bias MMA's constant A group
 // per-block weight image (bytes).  W0^T [32 n][128 k]: hi and lo, each two k-atoms of [32 rows x 128 B];
 // PW^T [32 n][32 k] and W2^T [128 n][32 k]: hi in bytes [0,64) and lo in bytes [64,128) of each 128-byte row
 constexpr int W16_W0HI = 0, W16_W0LO = 8192, W16_PW = 16384, W16_W2 = 20480;
-constexpr int W16_BYTES = 36864;
+// conv2's bias b2 goes THROUGH THE MMA: one extra k-step whose A operand is a constant group of TMEM columns (k = 0, 1 hold
+// T16_BIAS_ONE, the rest zero) and whose B operand is this tile: [128 n][8 k] fp16, K-major WITHOUT swizzle (core matrices
+// of 8 rows x 16 bytes), k = 0 / 1 = hi / lo halves of b2[n] * 2^s / T16_BIAS_ONE.  The second k-chunk of the K = 16
+// instruction points (leading-byte-offset) at a block of zeros shared by both weight buffers.  Epilogue 3 then is
+// x = lrelu(d * 2^-s + x): per channel pair one FFMA2 instead of FFMA2 + FADD2 and no constant-bank load of the bias.
+constexpr int W16_B2T = 36864;
+constexpr int W16_BYTES = 36864 + 2048;
+constexpr float T16_BIAS_ONE = 64.0f;  // |b2| up to 65504 * 64 / 2^s stays finite in the fp16 tile
 // The small fp32 parameters travel as a KERNEL ARGUMENT (7.9 KB of the constant bank): every use is warp-uniform, so
 // biases, stem and depthwise weights become constant-bank operands of the FMAs instead of shared-memory loads.
 struct alignas(16) Tower16Block {
@@ -58,16 +66,22 @@ constexpr int P16_FLOATS = P16_BLK0 + 3 * P16_BLK;  // 1964
 static_assert(sizeof(Tower16Params) == P16_FLOATS * 4 && sizeof(Tower16Block) == P16_BLK * 4, "parameter image layout");
 constexpr int T16_HSTRIDE = 36;                     // fp32 depthwise tile row stride (floats): conflict-free float4 rows
 // shared memory map (bytes from the 1024-aligned base)
-constexpr int S16_W = 0;                                      // 2 x 36 KB weight images
-constexpr int S16_H = 2 * W16_BYTES;                          // 73728: [162 rows (two positions)][36] fp32
-constexpr int S16_IMG = S16_H + 162 * T16_HSTRIDE * 4;        // 97056: three 243-float input images
-constexpr int S16_TAB = S16_IMG + 736 * 4;                    // 100000: stem tables, 8 input combinations x 132 words, fp32 and packed hi/lo
+constexpr int S16_W = 0;                                      // 2 x 38 KB weight images
+constexpr int S16_ZERO = 2 * W16_BYTES;                       // 77824: 2 KB of zeros (second k-chunk of the bias MMA)
+constexpr int S16_H = S16_ZERO + 2048;                        // 79872: [162 rows (two positions)][36] fp32
+constexpr int S16_IMG = S16_H + 162 * T16_HSTRIDE * 4;        // three 243-float input images (boards path: block 0's conv0 table)
+constexpr int S16_TAB = S16_IMG + 736 * 4;                    // fp32 stem table, 8 input combinations x 132 words
 constexpr int T16_TABSTRIDE = 132;                            // words per combination: 128 + 4, so the 8 rows start 4 banks apart
-constexpr int S16_BAR = S16_TAB + 2 * 8 * T16_TABSTRIDE * 4;  // 108448
-constexpr int T16_SMEM_BYTES = S16_BAR + 64 + 1024;           // 109536: two CTAs per SM
+// (the PACKED hi/lo stem table is needed only once, for the conv0 table at kernel start: it borrows the depthwise tile)
+constexpr int S16_BAR = S16_TAB + 8 * T16_TABSTRIDE * 4;
+constexpr int T16_SMEM_BYTES = S16_BAR + 64 + 1024;           // 111 KB: two CTAs per SM (2 x (smem + 1 KB) <= 228 KB)
+// ... and stays clear of the rows the PEER may already mirror into this tile while the table is still being read: the peer's
+// band lands in rows >= 37 (rank 0 writes its pixels 37..80 of slot 0's position, rank 1 rows 81 + p)
+static_assert(8 * T16_TABSTRIDE * 4 <= 37 * T16_HSTRIDE * 4, "the packed stem table fits below the first mirrored band row of the tile it borrows");
+static_assert(2 * (T16_SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
 constexpr uint32_t T16_BAND_BYTES = 10 * 32 * 4;              // mirrored stencil band: 10 pixel rows x 32 channels fp32
 constexpr uint32_t T16_IDESC_N32 = idesc_f16(128, 32), T16_IDESC_N128 = idesc_f16(128, 128);
-static_assert(W16_BYTES == 8 * 4608, "the idle weight buffer doubles as eight per-warp staging tiles (4 KB used, 512-byte aligned)");
+static_assert(W16_BYTES >= 8 * 4608 && W16_BYTES % 64 == 0, "the idle weight buffer doubles as eight per-warp staging tiles (4 KB used, 512-byte aligned)");
 static_assert(S16_BAR % 8 == 0, "mbarriers are 8-byte aligned");
 
 __device__ long long g_t16_dbg[64];  // phase timestamps of CTA 0's second iteration (omk_debug_tower_timing)
@@ -185,13 +199,11 @@ __device__ __forceinline__ void t16_stencil(const Tower16Block &B, const float *
 // epilogue 3 arithmetic on 32 channels [c0, c0+32) of this thread's 64: x = lrelu(d * 2^-s + b2 + x)
 template <int HALF>
 __device__ __forceinline__ void t16_residual32(const Tower16Block &B, int c0, const float *d, float *x) {
-    const float inv = B.inv[2];
+    const float inv = B.inv[2];  // (the accumulator already holds (conv2 + b2) * 2^s: the bias went through the MMA)
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
         const int c = c0 + i;
-        const float2 s = __ffma2_rn(make_float2(d[i], d[i + 1]), make_float2(inv, inv),
-                                    make_float2(B.b2[HALF * 64 + c], B.b2[HALF * 64 + c + 1]));
-        const float2 tt = __fadd2_rn(s, make_float2(x[c], x[c + 1]));
+        const float2 tt = __ffma2_rn(make_float2(d[i], d[i + 1]), make_float2(inv, inv), make_float2(x[c], x[c + 1]));
         const float2 u = __fmul2_rn(tt, make_float2(0.2f, 0.2f));
         x[c + 0] = fmaxf(tt.x, u.x);
         x[c + 1] = fmaxf(tt.y, u.y);
@@ -264,7 +276,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     float *T32 = reinterpret_cast<float *>(sm + S16_TAB);
     float *IMG = reinterpret_cast<float *>(sm + S16_IMG);
     float *T0 = IMG;  // boards path: block 0's conv0 table, 8 rows x T16_HSTRIDE floats (the image buffer is unused there)
-    uint32_t *TW = reinterpret_cast<uint32_t *>(sm + S16_TAB + 8 * T16_TABSTRIDE * 4);
+    uint32_t *TW = reinterpret_cast<uint32_t *>(sm + S16_H);  // packed stem table: used once, before the tile is
     const uint32_t bar_w0 = sbase + S16_BAR, bar_mma = sbase + S16_BAR + 16, bar_band = sbase + S16_BAR + 24,
                    bar_free = sbase + S16_BAR + 32, tmem_slot = sbase + S16_BAR + 40;
     const uint32_t peer_h0 = mapa(sbase + S16_H, rank ^ 1u);
@@ -281,7 +293,9 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     // Stem tables.  A board's input pixel is one of 8 bit triples (encoder.rs:22-43 writes only 0.0 / 1.0), so the stem
     // 3 -> 128 convolution + lrelu of a pixel is one of 8 rows: each CTA computes them once, with the arithmetic of
     // t16_stem (bit-identical to the general float-image path), as fp32 and as packed fp16 hi / lo A-operand words.
-    for (int e = t; e < 8 * 64; e += T16_THREADS) {
+    for (int e = t; e < 2048 / 16; e += T16_THREADS) reinterpret_cast<uint4 *>(sm + S16_ZERO)[e] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's shared-memory reads (before the barriers below)
+    for (int e = BOARDS ? t : 8 * 64; e < 8 * 64; e += T16_THREADS) {
         const int combo = e >> 6, ch = (e & 63) * 2;
         const float v0 = (float)(combo & 1), v1 = (float)((combo >> 1) & 1), v2 = (float)(combo >> 2);
         float2 sv = __ffma2_rn(make_float2(v0, v0), make_float2(P.wstem[0][ch], P.wstem[0][ch + 1]),
@@ -306,6 +320,13 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);  // this warp's lane quadrant
 
+    {   // the bias MMA's constant A group: k = 0, 1 = T16_BIAS_ONE, k = 2 .. 15 = 0 (every lane; written once)
+        uint32_t one8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        const __half2 o2 = __floats2half2_rn(T16_BIAS_ONE, T16_BIAS_ONE);
+        one8[0] = *reinterpret_cast<const uint32_t *>(&o2);
+        tmem_st8(tlane + TC_ONE, one8);
+        tmem_wait_st();
+    }
     uint32_t g = 0;          // running block counter: weight buffer = g & 1, its phase parity = (g >> 1) & 1
     uint32_t mma_uses = 0;   // completed uses of bar_mma
     auto issue_weights = [&](uint32_t gg) {  // one thread
@@ -313,7 +334,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
         fence_proxy_async_smem();  // the buffer may have served as a staging tile (generic proxy)
         mbar_expect_tx(bar, (uint32_t)W16_BYTES);
         const uint8_t *src = wimg + (size_t)(gg % 3u) * W16_BYTES;
-        for (int c = 0; c < W16_BYTES; c += 9216) bulk_load(sbase + S16_W + buf * W16_BYTES + c, src + c, 9216, bar);
+        for (int c = 0; c < W16_BYTES; c += W16_BYTES / 4) bulk_load(sbase + S16_W + buf * W16_BYTES + c, src + c, W16_BYTES / 4, bar);
     };
     if (t == 0) issue_weights(0);
 
@@ -560,6 +581,9 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                         umma_f16_ts(tmem_base + TC_D3, ahi, blo, T16_IDESC_N128, 1u);
                         umma_f16_ts(tmem_base + TC_D3, ahi, bhi, T16_IDESC_N128, 1u);
                     }
+                    // + b2 * 2^s: constant A group x bias tile (k-chunk 0 = the tile, k-chunk 1 = the shared zero block)
+                    umma_f16_ts(tmem_base + TC_D3, tmem_base + TC_ONE, desc_nosw(wb + W16_B2T, sbase + S16_ZERO - (wb + W16_B2T), 128u),
+                                T16_IDESC_N128, 1u);
                     umma_commit(bar_mma);
                 }
             } else if (lane == 0) {
@@ -656,6 +680,10 @@ __global__ void k_tower16_pack(Tower16PackArgs a, const uint32_t *absmax, uint8_
         for (int i = tid; i < 32 * 128; i += nth) {  // W2[k][n]: k = cin 0..31, n = cout 0..127
             const int k = i >> 7, n = i & 127;
             put_split(img, W16_W2 + swz128b(n, k * 2), W16_W2 + swz128b(n, 64 + k * 2), a.w2[r][k * 128 + n] * s2);
+        }
+        for (int n = tid; n < 128; n += nth) {  // bias tile of conv2: [128 n][8 k] no-swizzle core matrices, k = 0 / 1 = hi / lo
+            const uint32_t off = (uint32_t)W16_B2T + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u;
+            put_split(img, off, off + 2u, a.b2[r][n] * s2 * (1.0f / T16_BIAS_ONE));
         }
         float *pb = pimg + P16_BLK0 + r * P16_BLK;
         for (int i = tid; i < 32; i += nth) {

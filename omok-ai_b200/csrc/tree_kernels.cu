@@ -36,6 +36,7 @@ struct TreeArgs {
     uint32_t *slot_base, *slot_count;
     const float *P, *V;
     int max_rows;
+    int vloss;  // OPT-IN, NOT the reference's semantics: virtual loss inside a round (omk_search_set_virtual_loss)
 };
 
 __device__ __forceinline__ int tree_of(const TreeArgs &a, int slot) { return a.ids ? a.ids[slot] : slot + a.id_base; }
@@ -344,9 +345,23 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
                 backup_path(tn, path, depth + 1, five ? 1.0f : 0.0f, root_n, root_w);
             } else {
                 req[nreq] = (uint16_t)id;  // :182-187 queue for the evaluator
+                if (a.vloss) {
+                    // VIRTUAL LOSS (opt-in; the reference has none, :80-90 reads the statistics as they are): the pending
+                    // evaluation counts as one visit with value -1 on every edge of its path, so the round's next
+                    // simulations spread over other lines.  k_apply replaces it with the real value (n + 0, w + v + 1).
+                    path[depth] = (x << 8) | (uint32_t)action;
+                    for (int d = depth; d >= 0; --d) {
+                        uint8_t *pn = node_ptr(tn, path[d] >> 8);
+                        const int pa = path[d] & 0xFF;
+                        node_edge_n(pn)[pa] += 1u;
+                        node_edge_w(pn)[pa] = __fsub_rn(node_edge_w(pn)[pa], 1.0f);
+                    }
+                    root_n += 1u;
+                }
             }
         }
         if (c.status == kInProgress) ++nreq; else restart = true;  // a terminal child was backed up along the path
+        if (a.vloss) restart = true;                                // ... or a virtual loss changed it
         set81(h.cmask, action);  // the kept copy of the leaf's header follows the one in memory
 #ifdef OMK_NO_DESCENT_REUSE
         restart = true;  // A/B build: the first version's behaviour, a full descent per simulation
@@ -501,14 +516,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_apply(TreeArgs a, int m
                     uint32_t cur_parent = meta[i][1] & 0xFFFFu, cur_action = (meta[i][1] >> 16) & 0xFFu;
                     while (cur_parent != kNoNode) {
                         uint8_t *pn = node_ptr(tn, cur_parent);
-                        node_edge_n(pn)[cur_action] += 1u;
-                        node_edge_w(pn)[cur_action] = __fadd_rn(node_edge_w(pn)[cur_action], v);
+                        if (a.vloss) {  // the visit was counted at selection time with value -1: swap in the real value
+                            node_edge_w(pn)[cur_action] = __fadd_rn(node_edge_w(pn)[cur_action], __fadd_rn(v, 1.0f));
+                        } else {
+                            node_edge_n(pn)[cur_action] += 1u;
+                            node_edge_w(pn)[cur_action] = __fadd_rn(node_edge_w(pn)[cur_action], v);
+                        }
                         v = -v;
                         const uint32_t w9 = reinterpret_cast<const uint32_t *>(pn)[9];
                         cur_parent = w9 & 0xFFFFu;
                         cur_action = (w9 >> 16) & 0xFFu;
                     }
-                    root_n += 1u;
+                    if (!a.vloss) root_n += 1u;
                     root_w = __fadd_rn(root_w, v);
                 }
             }
@@ -973,6 +992,7 @@ static TreeArgs make_args(omk_ctx *c, const int32_t *ids_dev, int n) {
     a.P = c->ws.P;
     a.V = c->ws.V;
     a.max_rows = c->ws.max_rows;
+    a.vloss = c->virtual_loss;
     return a;
 }
 static inline int warp_grid(int n) { return (n + kWarpsPerBlock - 1) / kWarpsPerBlock; }

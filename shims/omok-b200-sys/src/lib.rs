@@ -97,6 +97,7 @@ extern "C" {
     // tree pool (alpha-zero/src/agent.rs, parallel_mcts_executor.rs, mcts_executor.rs; mcts/src/*.rs)
     pub fn omk_pool_new_games(ctx: *mut omk_ctx, ids: *const i32, n: i32, streams: *const u32, evaluator: i32) -> i32;
     pub fn omk_pool_search(ctx: *mut omk_ctx, ids: *const i32, n: i32, count: i32, batch_size: i32, epsilon: f32, alpha: f32, evaluator: i32) -> i32;
+    pub fn omk_search_set_virtual_loss(ctx: *mut omk_ctx, enabled: i32) -> i32;
     pub fn omk_pool_sample(ctx: *mut omk_ctx, ids: *const i32, n: i32, modes: *const u8, temperatures: *const f32, out_actions: *mut i32, out_policy: *mut f32) -> i32;
     pub fn omk_pool_policy(ctx: *mut omk_ctx, ids: *const i32, n: i32, out_policy: *mut f32, out_valid: *mut u8) -> i32;
     pub fn omk_pool_ensure_action(ctx: *mut omk_ctx, ids: *const i32, actions: *const i32, n: i32, evaluator: i32) -> i32;
