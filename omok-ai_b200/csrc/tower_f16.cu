@@ -45,9 +45,11 @@ constexpr int W16_W0HI = 0, W16_W0LO = 8192, W16_PW = 16384, W16_W2 = 20480;
 // T16_BIAS_ONE, the rest zero) and whose B operand is this tile: [128 n][8 k] fp16, K-major WITHOUT swizzle (core matrices
 // of 8 rows x 16 bytes), k = 0 / 1 = hi / lo halves of b2[n] * 2^s / T16_BIAS_ONE.  The second k-chunk of the K = 16
 // instruction points (leading-byte-offset) at a block of zeros shared by both weight buffers.  Epilogue 3 then is
-// x = lrelu(d * 2^-s + x): per channel pair one FFMA2 instead of FFMA2 + FADD2 and no constant-bank load of the bias.
-constexpr int W16_B2T = 36864;
-constexpr int W16_BYTES = 36864 + 2048;
+// x = lrelu(d * 2^-s + x): per channel pair one FFMA2 instead of FFMA2 + FADD2 and no constant-bank load of the bias; epilogues
+// 1 and 2 are lrelu(d * 2^-s) = max(d * 2^-s, d * 0.2 * 2^-s) in packed fp32x2 multiplies, no bias operand at all.
+constexpr int W16_B2T = 36864;                 // conv2: [128 n][8 k]
+constexpr int W16_B0T = 38912, W16_B1T = 39424;  // conv0 / conv1: [32 n][8 k] each (the same construction for b0 and b1)
+constexpr int W16_BYTES = 36864 + 2048 + 1024;
 constexpr float T16_BIAS_ONE = 64.0f;  // |b2| up to 65504 * 64 / 2^s stays finite in the fp16 tile
 // The small fp32 parameters travel as a KERNEL ARGUMENT (7.9 KB of the constant bank): every use is warp-uniform, so
 // biases, stem and depthwise weights become constant-bank operands of the FMAs instead of shared-memory loads.
@@ -67,8 +69,8 @@ static_assert(sizeof(Tower16Params) == P16_FLOATS * 4 && sizeof(Tower16Block) ==
 constexpr int T16_HSTRIDE = 36;                     // fp32 depthwise tile row stride (floats): conflict-free float4 rows
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int S16_W = 0;                                      // 2 x 38 KB weight images
-constexpr int S16_ZERO = 2 * W16_BYTES;                       // 77824: 2 KB of zeros (second k-chunk of the bias MMA)
-constexpr int S16_H = S16_ZERO + 2048;                        // 79872: [162 rows (two positions)][36] fp32
+constexpr int S16_ZERO = 2 * W16_BYTES;                       // 2 KB of zeros (second k-chunk of the bias MMAs)
+constexpr int S16_H = S16_ZERO + 2048;                        // [162 rows (two positions)][36] fp32
 constexpr int S16_IMG = S16_H + 162 * T16_HSTRIDE * 4;        // three 243-float input images (boards path: block 0's conv0 table)
 constexpr int S16_TAB = S16_IMG + 736 * 4;                    // fp32 stem table, 8 input combinations x 132 words
 constexpr int T16_TABSTRIDE = 132;                            // words per combination: 128 + 4, so the 8 rows start 4 banks apart
@@ -158,10 +160,16 @@ __device__ __forceinline__ void t16_stem(const Tower16Params &P, float v0, float
 // convolution (one per product, three partial accumulators added here) beat a single chain by 14 %.  With warp-uniform
 // operands and unrolled chains the MMAs issue back to back (tower 0.749 -> 0.658 ms) and ONE chain per convolution is
 // faster again (0.648 ms): two TMEM loads and two adds per element less in each of these epilogues.
-template <int HALF>
-__device__ __forceinline__ void t16_bias_lrelu16(const float *bias32, float inv, const float *d, float *o) {
+// (the bias is in the accumulator: it went through the MMA as one more k-step)
+__device__ __forceinline__ void t16_lrelu_scaled16(float inv, const float *d, float *o) {
+    const float2 i2 = make_float2(inv, inv), j2 = make_float2(0.2f * inv, 0.2f * inv);  // 0.2 * 2^-s is exact up to fp32(0.2)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = t16_lrelu(fmaf(d[c], inv, bias32[HALF * 16 + c]));
+    for (int c = 0; c < 16; c += 2) {
+        const float2 v = make_float2(d[c], d[c + 1]);
+        const float2 a = __fmul2_rn(v, i2), b = __fmul2_rn(v, j2);
+        o[c] = fmaxf(a.x, b.x);
+        o[c + 1] = fmaxf(a.y, b.y);
+    }
 }
 // depthwise 3x3, SAME zero padding, no bias (lib.rs:204-216): 16 channels of pixel (y, x0) from the fp32 tile.
 // (Measured and rejected, twice: branch-free variants whose off-board taps read zeros.  The second one used a zero-padded
@@ -371,6 +379,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                     umma_f16_ts(dcol, ahi, blo + off, T16_IDESC_N32, 1u);
                     umma_f16_ts(dcol, ahi, bhi + off, T16_IDESC_N32, 1u);
                 }
+                umma_f16_ts(dcol, tmem_base + TC_ONE, desc_nosw(wb0 + W16_B0T, sbase + S16_ZERO - (wb0 + W16_B0T), 128u), T16_IDESC_N32, 1u);  // + b0
                 umma_commit(bar_mma);
             }
         } else if (lane == 0) {
@@ -385,8 +394,8 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             tmem_ld16(tlane + TC_ACC, d);
             tmem_ld16(tlane + TC_ACC + 16, d + 16);
             tmem_wait_ld();
-            t16_bias_lrelu16<0>(P.blk[0].b0, P.blk[0].inv[0], d, o);
-            t16_bias_lrelu16<1>(P.blk[0].b0, P.blk[0].inv[0], d + 16, o + 16);
+            t16_lrelu_scaled16(P.blk[0].inv[0], d, o);
+            t16_lrelu_scaled16(P.blk[0].inv[0], d + 16, o + 16);
             if (lane < 8) {
 #pragma unroll
                 for (int c = 0; c < 32; c += 4)
@@ -470,6 +479,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                             umma_f16_ts(dcol, ahi, blo + off, T16_IDESC_N32, 1u);
                             umma_f16_ts(dcol, ahi, bhi + off, T16_IDESC_N32, 1u);
                         }
+                        umma_f16_ts(dcol, tmem_base + TC_ONE, desc_nosw(wb + W16_B0T, sbase + S16_ZERO - (wb + W16_B0T), 128u), T16_IDESC_N32, 1u);  // + b0
                         umma_commit(bar_mma);
                     }
                 } else if (lane == 0) {
@@ -498,7 +508,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                 } else {
                     tmem_ld16(tlane + TC_ACC + half * 16, d);
                     tmem_wait_ld();
-                    T16_HALF(t16_bias_lrelu16<0>(B.b0, B.inv[0], d, o), t16_bias_lrelu16<1>(B.b0, B.inv[0], d, o));
+                    t16_lrelu_scaled16(B.inv[0], d, o);
                 }
                 if (in_tile) {
                     float *hrow = H0 + (slot * kCells + p) * T16_HSTRIDE + half * 16;
@@ -546,6 +556,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                         umma_f16_ts(dcol, ahi, blo + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
                         umma_f16_ts(dcol, ahi, bhi + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
                     }
+                    umma_f16_ts(dcol, tmem_base + TC_ONE, desc_nosw(wb + W16_B1T, sbase + S16_ZERO - (wb + W16_B1T), 128u), T16_IDESC_N32, 1u);  // + b1
                     umma_commit(bar_mma);
                 }
             } else if (lane == 0) {
@@ -561,7 +572,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                 float d[16], o[16];
                 tmem_ld16(tlane + TC_ACC + half * 16, d);
                 tmem_wait_ld();
-                T16_HALF(t16_bias_lrelu16<0>(B.b1, B.inv[1], d, o), t16_bias_lrelu16<1>(B.b1, B.inv[1], d, o));
+                t16_lrelu_scaled16(B.inv[1], d, o);
                 t16_store_group(tlane + TC_H + (uint32_t)(half * 16), o);
             }
             tmem_wait_st();
@@ -680,6 +691,11 @@ __global__ void k_tower16_pack(Tower16PackArgs a, const uint32_t *absmax, uint8_
         for (int i = tid; i < 32 * 128; i += nth) {  // W2[k][n]: k = cin 0..31, n = cout 0..127
             const int k = i >> 7, n = i & 127;
             put_split(img, W16_W2 + swz128b(n, k * 2), W16_W2 + swz128b(n, 64 + k * 2), a.w2[r][k * 128 + n] * s2);
+        }
+        for (int n = tid; n < 32; n += nth) {   // bias tiles of conv0 / conv1: [32 n][8 k]
+            const uint32_t off = (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u;
+            put_split(img, W16_B0T + off, W16_B0T + off + 2u, a.b0[r][n] * s0 * (1.0f / T16_BIAS_ONE));
+            put_split(img, W16_B1T + off, W16_B1T + off + 2u, a.b1[r][n] * s1 * (1.0f / T16_BIAS_ONE));
         }
         for (int n = tid; n < 128; n += nth) {  // bias tile of conv2: [128 n][8 k] no-swizzle core matrices, k = 0 / 1 = hi / lo
             const uint32_t off = (uint32_t)W16_B2T + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u;
