@@ -41,7 +41,7 @@ for rep in reports:
         rows_out.append(rec)
         rd = float(r[col["dram__bytes_read.sum"]]) * UNIT_BYTES[units[col["dram__bytes_read.sum"]]]
         wr = float(r[col["dram__bytes_write.sum"]]) * UNIT_BYTES[units[col["dram__bytes_write.sum"]]]
-        key = short + ("_heads" if ", 128, 1" in name else "_fc1" if "<512" in name else "")
+        key = short + ("_heads" if ", 128, 1" in name or ", (int)128, (bool)1" in name else "_fc1" if "<512" in name or "<(int)512" in name else "")
         traffic.setdefault(key, []).append(rd + wr)
 keys = []
 for rec in rows_out:
@@ -53,5 +53,5 @@ with open(out_prefix + "_summary.csv", "w", newline="") as f:
     w.writeheader()
     w.writerows(rows_out)
 json.dump({k: {"dram_bytes_per_launch": sum(v) / len(v), "launches_captured": len(v)} for k, v in traffic.items()},
-          open(os.path.join(os.path.dirname(out_prefix) or ".", "r01_ncu_traffic.json"), "w"), indent=1)
+          open(os.path.join(os.path.dirname(out_prefix) or ".", (re.match(r"(r\d+)_", os.path.basename(out_prefix)) or [None, "r00"])[1] + "_ncu_traffic.json"), "w"), indent=1)
 print(open(out_prefix + "_summary.csv").read()[:3000])

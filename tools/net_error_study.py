@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=4000)
     ap.add_argument("--layer-rows", type=int, default=600, help="rows per weight set whose tower output is compared (166 KB per row)")
     ap.add_argument("--paths", nargs="+", default=["tc", "simt"], help="tc = tensor-core kernels (product), simt = fp32 CUDA-core A/B kernels, cpu32 = PyTorch-CPU fp32 (yardstick)")
+    ap.add_argument("--fc0-chunk", type=int, default=9, help="k-blocks of fc0 per TMEM drain: 9 (default) or 3 (omk_debug_set_fc0_chunk)")
     ap.add_argument("--label", default="")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -74,7 +75,8 @@ def main():
     boards, turns = positions(args.positions, 12345)
     modes = (np.arange(args.positions) // 3) % 2  # EnvTurnMode::Player / ::Opponent alternate within each band
     ctx = omk.Context(device=0, capacity_envs=4, capacity_trees=4, capacity_nodes=64, seed=0)
-    result = {"label": args.label, "positions": args.positions, "stones": {"early": "0-30", "middle": "30-60", "late": "60-80"},
+    ctx.debug_set_fc0_chunk(args.fc0_chunk)
+    result = {"label": args.label, "fc0_chunk": args.fc0_chunk, "positions": args.positions, "stones": {"early": "0-30", "middle": "30-60", "late": "60-80"},
               "tolerance": 1e-3, "sets": {}}
     t_start = time.time()
     for set_name, params in weight_sets(no, args.seeds):
