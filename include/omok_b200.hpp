@@ -166,6 +166,16 @@ class AgentModel {
         omk::check(omk_net_eval_images(ctx_->raw(), input.data(), n, p.data(), v.data()));
         return {std::move(p), std::move(v)};
     }
+    // AgentModel::train (agent_model.rs:136-168): one Adadelta step on (input [n*243], policy_target [n*81],
+    // value_target [n]) and the reference's second forward: (p_loss, v_loss, loss) after the update
+    struct Losses { float p_loss, v_loss, loss; };
+    Losses train(const std::vector<float> &input, const std::vector<float> &policy_target, const std::vector<float> &value_target) const {
+        const int32_t n = (int32_t)(input.size() / 243);
+        if (policy_target.size() != (size_t)n * OMK_CELLS || value_target.size() != (size_t)n) throw omk::Error(OMK_ERR_INVALID, "train: target sizes");
+        float l[3] = {0, 0, 0};
+        omk::check(omk_train_step(ctx_->raw(), input.data(), policy_target.data(), value_target.data(), n, l));
+        return {l[0], l[1], l[2]};
+    }
 
   private:
     omk::Context *ctx_;

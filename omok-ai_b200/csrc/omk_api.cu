@@ -186,6 +186,8 @@ static int32_t check_device_error(omk_ctx *c) {
         copy_h2d(c, c->dev_error, &z, sizeof z, c->stream);
     }
     if (e & 1u) return fail(OMK_ERR_CAPACITY, "a tree ran out of node slots (capacity_nodes=" + std::to_string(c->cap_nodes) + ")");
+    if (e & 4u)
+        return fail(OMK_ERR_STATE, "the self-play driver sampled a move its tree refused (play_action returned None): the transition stream of this call is not usable");
     if (e & 2u)
         return fail(OMK_ERR_NUMERIC, "the network produced a non-finite policy or value (activation beyond the fp16 operand range "
                                      "of the tensor-core path, |x| >= 65504, or non-finite weights)");

@@ -52,10 +52,13 @@ struct GemmEpi {
     int accumulate = 0;           // C += result
 };
 
+// Split-K (gridDim.z > 1, products with K in the thousands and few output tiles: the weight gradients of the 1x1
+// convolutions, fc0's forward): slice z walks k in [z * k_per_split, (z + 1) * k_per_split) and stores its raw partial tile
+// to part[z][M][N]; k_tgemm_reduce adds the slices IN ORDER and applies the epilogue -- still a fixed summation order.
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
     k_tgemm(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C, int M, int N, int K, int lda, int ldb,
-            int ldc, GemmEpi e) {
+            int ldc, GemmEpi e, int k_per_split, float *__restrict__ part) {
     __shared__ float As[16][64 + 1];
     __shared__ float Bs[16][64 + 1];
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -65,7 +68,8 @@ __global__ void __launch_bounds__(256)
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-    for (int k0 = 0; k0 < K; k0 += 16) {
+    const int k_begin = (int)blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
         // stage a 64 x 16 slice of op(A) and a 16 x 64 slice of op(B); out-of-range elements are zeros
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -74,13 +78,13 @@ __global__ void __launch_bounds__(256)
             if (TA) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
             const int gm = m0 + m, gk = k0 + k;
             float v = 0.0f;
-            if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            if (gm < M && gk < k_end) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
             As[k][m] = v;
             int n, kb;
             if (TB) { kb = idx & 15; n = idx >> 4; } else { n = idx & 63; kb = idx >> 6; }
             const int gn = n0 + n, gkb = k0 + kb;
             float w = 0.0f;
-            if (gn < N && gkb < K) w = TB ? B[(size_t)gn * ldb + gkb] : B[(size_t)gkb * ldb + gn];
+            if (gn < N && gkb < k_end) w = TB ? B[(size_t)gn * ldb + gkb] : B[(size_t)gkb * ldb + gn];
             Bs[kb][n] = w;
         }
         __syncthreads();
@@ -107,6 +111,10 @@ __global__ void __launch_bounds__(256)
             const int n = n0 + tx * 4 + j;
             if (n >= N) continue;
             float v = acc[i][j];
+            if (part) {  // split-K slice: raw partial sums, the epilogue runs in k_tgemm_reduce
+                part[((size_t)blockIdx.z * M + m) * N + n] = v;
+                continue;
+            }
             const size_t o = (size_t)m * ldc + n;
             if (e.bias) v += e.bias[n];
             if (e.res) v += e.res[o];
@@ -118,11 +126,45 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+__global__ void k_tgemm_reduce(const float *__restrict__ part, int splits, int M, int N, float *__restrict__ C, int ldc, GemmEpi e) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)M * N) return;
+    const int m = (int)(idx / N), n = (int)(idx % N);
+    float v = 0.0f;
+    for (int z = 0; z < splits; ++z) v += part[((size_t)z * M + m) * N + n];
+    const size_t o = (size_t)m * ldc + n;
+    if (e.bias) v += e.bias[n];
+    if (e.res) v += e.res[o];
+    if (e.act) v = v > 0.0f ? v : kTLrelu * v;
+    if (e.gate) v *= e.gate[o] > 0.0f ? 1.0f : kTLrelu;
+    if (e.accumulate) v += C[o];
+    C[o] = v;
+}
+
+static float *g_splitk_scratch(omk_ctx *c, size_t floats);  // grow-only scratch of the training state
+
 template <bool TA, bool TB>
-static void tgemm(cudaStream_t s, const float *A, const float *B, float *C, int M, int N, int K, int lda, int ldb, int ldc,
+static void tgemm(omk_ctx *c, const float *A, const float *B, float *C, int M, int N, int K, int lda, int ldb, int ldc,
                   const GemmEpi &e) {
+    cudaStream_t s = c->stream;
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    k_tgemm<TA, TB><<<grid, 256, 0, s>>>(A, B, C, M, N, K, lda, ldb, ldc, e);
+    // few output tiles and a long K: slice K so that ~2 waves of CTAs exist (fixed slice size -> fixed summation order)
+    const int tiles = (int)(grid.x * grid.y);
+    if (K >= 2048 && tiles < 64) {
+        int splits = min(64, max(2, 296 / tiles));
+        int kps = ((K + splits - 1) / splits + 15) / 16 * 16;
+        splits = (K + kps - 1) / kps;
+        float *part = g_splitk_scratch(c, (size_t)splits * M * N);
+        if (part) {
+            grid.z = splits;
+            k_tgemm<TA, TB><<<grid, 256, 0, s>>>(A, B, C, M, N, K, lda, ldb, ldc, e, kps, part);
+            const long long tot = (long long)M * N;
+            k_tgemm_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(part, splits, M, N, C, ldc, e);
+            c->launches++;
+            return;
+        }
+    }
+    k_tgemm<TA, TB><<<grid, 256, 0, s>>>(A, B, C, M, N, K, lda, ldb, ldc, e, K, nullptr);
 }
 
 // out[n] = sum over m of X[m, n] in a fixed order: one block per 32 columns, 8 row groups, sequential within a group,
@@ -296,6 +338,8 @@ struct TrainState {
     float *d32a = nullptr, *d32b = nullptr;  // [n*81][32]
     float *da0 = nullptr, *da1 = nullptr, *dlogits = nullptr, *dvlogit = nullptr, *row_loss = nullptr;
     float *losses = nullptr;               // [3] device
+    float *splitk = nullptr;               // split-K partial tiles (grow-only)
+    size_t splitk_cap = 0;
     float *grads = nullptr;                // flat [kTParams] in checkpoint order
     float *accum = nullptr, *accum_update = nullptr;  // Adadelta slots, flat
     long long off[kNetTensors + 1] = {};
@@ -322,6 +366,20 @@ static TrainState *train_state(omk_ctx *c) {
         c->train_state = t;
     }
     return reinterpret_cast<TrainState *>(c->train_state);
+}
+
+static TrainState *train_state(omk_ctx *c);
+static float *g_splitk_scratch(omk_ctx *c, size_t floats) {
+    TrainState *t = train_state(c);
+    if (floats > t->splitk_cap) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(t->splitk);
+        t->splitk = nullptr;
+        t->splitk_cap = 0;
+        if (cudaMalloc(&t->splitk, sizeof(float) * floats) != cudaSuccess) return nullptr;
+        t->splitk_cap = floats;
+    }
+    return t->splitk;
 }
 
 static bool talloc(float **p, size_t count) {
@@ -357,7 +415,7 @@ void train_free(omk_ctx *c) {
     if (t->comm && t->p_comm_destroy) t->p_comm_destroy(t->comm);
     float *all[] = {t->img, t->pi, t->z, t->x[0], t->x[1], t->x[2], t->x[3], t->h0[0], t->h0[1], t->h0[2], t->hd[0], t->hd[1], t->hd[2],
                     t->h1[0], t->h1[1], t->h1[2], t->a0, t->a1, t->logits, t->vlogit, t->dx, t->dy, t->d32a, t->d32b, t->da0, t->da1,
-                    t->dlogits, t->dvlogit, t->row_loss, t->losses, t->grads, t->accum, t->accum_update};
+                    t->dlogits, t->dvlogit, t->row_loss, t->losses, t->grads, t->accum, t->accum_update, t->splitk};
     for (float *p : all) cudaFree(p);
     if (t->nccl_lib) dlclose(t->nccl_lib);
     delete t;
@@ -376,39 +434,39 @@ static void train_forward(omk_ctx *c, TrainState *t, int n) {
     GemmEpi e;
     e.bias = W[T_CONV_B];
     e.act = 1;
-    tgemm<false, false>(s, t->img, W[T_CONV_W], t->x[0], M, kTP, 3, 3, kTP, kTP, e);  // stem: the 243-float slot read as [81][3]
+    tgemm<false, false>(c, t->img, W[T_CONV_W], t->x[0], M, kTP, 3, 3, kTP, kTP, e);  // stem: the 243-float slot read as [81][3]
     for (int r = 0; r < 3; ++r) {
         float *const *B = W + T_BLK0 + 7 * r;
         GemmEpi e0;
         e0.bias = B[B_B0];
         e0.act = 1;
-        tgemm<false, false>(s, t->x[r], B[B_W0], t->h0[r], M, kTM, kTP, kTP, kTM, kTM, e0);
+        tgemm<false, false>(c, t->x[r], B[B_W0], t->h0[r], M, kTM, kTP, kTP, kTM, kTM, e0);
         const long long tot = (long long)M * kTM;
         k_dw<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(t->h0[r], B[B_DW], t->hd[r], n, 0, nullptr);
         GemmEpi e1;
         e1.bias = B[B_B1];
         e1.act = 1;
-        tgemm<false, false>(s, t->hd[r], B[B_PW], t->h1[r], M, kTM, kTM, kTM, kTM, kTM, e1);
+        tgemm<false, false>(c, t->hd[r], B[B_PW], t->h1[r], M, kTM, kTM, kTM, kTM, kTM, e1);
         GemmEpi e2;
         e2.bias = B[B_B2];
         e2.res = t->x[r];
         e2.act = 1;
-        tgemm<false, false>(s, t->h1[r], B[B_W2], t->x[r + 1], M, kTP, kTM, kTM, kTP, kTP, e2);
+        tgemm<false, false>(c, t->h1[r], B[B_W2], t->x[r + 1], M, kTP, kTM, kTM, kTP, kTP, e2);
     }
     GemmEpi f0;
     f0.bias = W[T_FC0_B];
     f0.act = 1;
-    tgemm<false, false>(s, t->x[3], W[T_FC0_W], t->a0, n, kTF, kTFlat, kTFlat, kTF, kTF, f0);  // NHWC flatten == the row itself
+    tgemm<false, false>(c, t->x[3], W[T_FC0_W], t->a0, n, kTF, kTFlat, kTFlat, kTF, kTF, f0);  // NHWC flatten == the row itself
     GemmEpi f1;
     f1.bias = W[T_FC1_B];
     f1.act = 1;
-    tgemm<false, false>(s, t->a0, W[T_FC1_W], t->a1, n, kTF, kTF, kTF, kTF, kTF, f1);
+    tgemm<false, false>(c, t->a0, W[T_FC1_W], t->a1, n, kTF, kTF, kTF, kTF, kTF, f1);
     GemmEpi hp;
     hp.bias = W[T_P_B];
-    tgemm<false, false>(s, t->a1, W[T_P_W], t->logits, n, kCells, kTF, kTF, kCells, kCells, hp);
+    tgemm<false, false>(c, t->a1, W[T_P_W], t->logits, n, kCells, kTF, kTF, kCells, kCells, hp);
     GemmEpi hv;
     hv.bias = W[T_V_B];
-    tgemm<false, false>(s, t->a1, W[T_V_W], t->vlogit, n, 1, kTF, kTF, 1, 1, hv);
+    tgemm<false, false>(c, t->a1, W[T_V_W], t->vlogit, n, 1, kTF, kTF, 1, 1, hv);
     c->launches += 5 + 3 * 4;
 }
 
@@ -432,28 +490,28 @@ static void train_backward(omk_ctx *c, TrainState *t, int n) {
     auto G = [&](int tensor) { return t->grads + t->off[tensor]; };
     GemmEpi none;
     // heads
-    tgemm<true, false>(s, t->a1, t->dlogits, G(T_P_W), kTF, kCells, n, kTF, kCells, kCells, none);   // a1^T . dlogits
+    tgemm<true, false>(c, t->a1, t->dlogits, G(T_P_W), kTF, kCells, n, kTF, kCells, kCells, none);   // a1^T . dlogits
     colsum(c, t->dlogits, n, kCells, G(T_P_B));
-    tgemm<true, false>(s, t->a1, t->dvlogit, G(T_V_W), kTF, 1, n, kTF, 1, 1, none);
+    tgemm<true, false>(c, t->a1, t->dvlogit, G(T_V_W), kTF, 1, n, kTF, 1, 1, none);
     colsum(c, t->dvlogit, n, 1, G(T_V_B));
-    tgemm<false, true>(s, t->dlogits, W[T_P_W], t->da1, n, kTF, kCells, kCells, kCells, kTF, none);  // dlogits . Pw^T
+    tgemm<false, true>(c, t->dlogits, W[T_P_W], t->da1, n, kTF, kCells, kCells, kCells, kTF, none);  // dlogits . Pw^T
     {   // da1 = (dlogits . Pw^T + dvlogit . Vw^T) * lrelu'(a1): second product accumulates, then the gate
         GemmEpi e;
         e.accumulate = 1;
-        tgemm<false, true>(s, t->dvlogit, W[T_V_W], t->da1, n, kTF, 1, 1, 1, kTF, e);
+        tgemm<false, true>(c, t->dvlogit, W[T_V_W], t->da1, n, kTF, 1, 1, 1, kTF, e);
         const long long tot = (long long)n * kTF;
         k_lrelu_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(t->da1, t->a1, t->da1, tot);
     }
     // fc1
-    tgemm<true, false>(s, t->a0, t->da1, G(T_FC1_W), kTF, kTF, n, kTF, kTF, kTF, none);
+    tgemm<true, false>(c, t->a0, t->da1, G(T_FC1_W), kTF, kTF, n, kTF, kTF, kTF, none);
     colsum(c, t->da1, n, kTF, G(T_FC1_B));
     GemmEpi g0;
     g0.gate = t->a0;
-    tgemm<false, true>(s, t->da1, W[T_FC1_W], t->da0, n, kTF, kTF, kTF, kTF, kTF, g0);
+    tgemm<false, true>(c, t->da1, W[T_FC1_W], t->da0, n, kTF, kTF, kTF, kTF, kTF, g0);
     // fc0
-    tgemm<true, false>(s, t->x[3], t->da0, G(T_FC0_W), kTFlat, kTF, n, kTFlat, kTF, kTF, none);
+    tgemm<true, false>(c, t->x[3], t->da0, G(T_FC0_W), kTFlat, kTF, n, kTFlat, kTF, kTF, none);
     colsum(c, t->da0, n, kTF, G(T_FC0_B));
-    tgemm<false, true>(s, t->da0, W[T_FC0_W], t->dx, n, kTFlat, kTF, kTF, kTF, kTFlat, none);  // d(flat) == d(x3) as [M][128]
+    tgemm<false, true>(c, t->da0, W[T_FC0_W], t->dx, n, kTFlat, kTF, kTF, kTF, kTFlat, none);  // d(flat) == d(x3) as [M][128]
     c->launches += 10;
     // residual blocks, last to first (network-utils lib.rs:386-461; network.rs:108-111)
     for (int r = 2; r >= 0; --r) {
@@ -461,27 +519,27 @@ static void train_backward(omk_ctx *c, TrainState *t, int n) {
         const int gb = T_BLK0 + 7 * r;
         const long long tot128 = (long long)M * kTP, tot32 = (long long)M * kTM;
         k_lrelu_bwd<<<(unsigned)((tot128 + 255) / 256), 256, 0, s>>>(t->dx, t->x[r + 1], t->dy, tot128);  // through the block's last lrelu
-        tgemm<true, false>(s, t->h1[r], t->dy, G(gb + B_W2), kTM, kTP, M, kTM, kTP, kTP, none);
+        tgemm<true, false>(c, t->h1[r], t->dy, G(gb + B_W2), kTM, kTP, M, kTM, kTP, kTP, none);
         colsum(c, t->dy, M, kTP, G(gb + B_B2));
         GemmEpi g1;
         g1.gate = t->h1[r];
-        tgemm<false, true>(s, t->dy, B[B_W2], t->d32a, M, kTM, kTP, kTP, kTP, kTM, g1);  // d(pointwise pre-activation)
-        tgemm<true, false>(s, t->hd[r], t->d32a, G(gb + B_PW), kTM, kTM, M, kTM, kTM, kTM, none);
+        tgemm<false, true>(c, t->dy, B[B_W2], t->d32a, M, kTM, kTP, kTP, kTP, kTM, g1);  // d(pointwise pre-activation)
+        tgemm<true, false>(c, t->hd[r], t->d32a, G(gb + B_PW), kTM, kTM, M, kTM, kTM, kTM, none);
         colsum(c, t->d32a, M, kTM, G(gb + B_B1));
-        tgemm<false, true>(s, t->d32a, B[B_PW], t->d32b, M, kTM, kTM, kTM, kTM, kTM, none);  // d(depthwise output)
+        tgemm<false, true>(c, t->d32a, B[B_PW], t->d32b, M, kTM, kTM, kTM, kTM, kTM, none);  // d(depthwise output)
         k_dw_wgrad<<<9, 256, 0, s>>>(t->h0[r], t->d32b, G(gb + B_DW), n);
         k_dw<<<(unsigned)((tot32 + 255) / 256), 256, 0, s>>>(t->d32b, B[B_DW], t->d32a, n, 1, t->h0[r]);  // d(conv0 pre-activation)
-        tgemm<true, false>(s, t->x[r], t->d32a, G(gb + B_W0), kTP, kTM, M, kTP, kTM, kTM, none);
+        tgemm<true, false>(c, t->x[r], t->d32a, G(gb + B_W0), kTP, kTM, M, kTP, kTM, kTM, none);
         colsum(c, t->d32a, M, kTM, G(gb + B_B0));
         GemmEpi skip;  // dx_r = dy (the skip connection) + d(conv0 pre-activation) . W0^T
         skip.res = t->dy;
-        tgemm<false, true>(s, t->d32a, B[B_W0], t->dx, M, kTP, kTM, kTM, kTM, kTP, skip);
+        tgemm<false, true>(c, t->d32a, B[B_W0], t->dx, M, kTP, kTM, kTM, kTM, kTP, skip);
         c->launches += 9;
     }
     // stem
     const long long tot128 = (long long)M * kTP;
     k_lrelu_bwd<<<(unsigned)((tot128 + 255) / 256), 256, 0, s>>>(t->dx, t->x[0], t->dy, tot128);
-    tgemm<true, false>(s, t->img, t->dy, G(T_CONV_W), 3, kTP, M, 3, kTP, kTP, none);
+    tgemm<true, false>(c, t->img, t->dy, G(T_CONV_W), 3, kTP, M, 3, kTP, kTP, none);
     colsum(c, t->dy, M, kTP, G(T_CONV_B));
     c->launches += 2;
 }

@@ -957,7 +957,7 @@ __global__ void k_sp_record(TreeArgs a, const int32_t *actions, const float *pol
     if (threadIdx.x == 0) actions_out[g] = actions[g];
 }
 
-__global__ void k_sp_advance(int g0, int n, int32_t *ply, const int8_t *status, unsigned long long *counters) {
+__global__ void k_sp_advance(int g0, int n, int32_t *ply, const int8_t *status, unsigned long long *counters, uint32_t *dev_error) {
     const int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= g0 + n) return;
     const int st = status[g];
@@ -966,6 +966,8 @@ __global__ void k_sp_advance(int g0, int n, int32_t *ply, const int8_t *status, 
         atomicAdd(&counters[0], 1ull);
     } else if (st == kInProgress) {
         ply[g] += 1;
+    } else {
+        atomicOr(dev_error, 4u);  // Option::None: the sampled move was refused -- the game would sit at this ply for ever
     }
 }
 
@@ -1019,7 +1021,7 @@ void launch_sp_record(omk_ctx *c, int n, const int32_t *mover, const int32_t *ac
     c->launches++;
 }
 void launch_sp_advance(omk_ctx *c, int g0, int n, const int8_t *status, unsigned long long *counters) {
-    k_sp_advance<<<(n + 127) / 128, 128, 0, c->stream>>>(g0, n, c->sp_ply, status, counters);
+    k_sp_advance<<<(n + 127) / 128, 128, 0, c->stream>>>(g0, n, c->sp_ply, status, counters, c->dev_error);
     c->launches++;
 }
 void launch_root_noise(omk_ctx *c, const int32_t *ids_dev, int n, float epsilon, float alpha) {

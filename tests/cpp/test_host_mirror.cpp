@@ -97,6 +97,25 @@ int main(int argc, char **argv) {
         REQUIRE(after.first == before.first && after.second == before.second);
         REQUIRE(alpha_zero::ModelIO::variable_names().size() == 31);
     }
+    {  // AgentModel::train through omk_train_step: the loss of a fixed minibatch falls, the new weights answer evaluate_pv
+        alpha_zero::AgentModel model(ctx, 5);
+        const int n = 8;
+        std::vector<float> img((size_t)n * 243, 0.0f), pi((size_t)n * 81, 0.0f), z((size_t)n, 0.0f);
+        for (int i = 0; i < n; ++i) {
+            img[(size_t)i * 243 + 2 * i] = 1.0f;                       // one stone of the side to move
+            for (int k = 162; k < 243; ++k) img[(size_t)i * 243 + k] = 1.0f;
+            pi[(size_t)i * 81 + (i * 7 + 3) % 81] = 1.0f;
+            z[i] = (i & 1) ? 1.0f : -1.0f;
+        }
+        const auto before = model.evaluate_pv(img);
+        const auto first = model.train(img, pi, z);
+        alpha_zero::AgentModel::Losses last = first;
+        for (int it = 0; it < 40; ++it) last = model.train(img, pi, z);
+        REQUIRE(first.loss == first.loss && last.loss < first.loss);
+        REQUIRE(first.p_loss + first.v_loss > 0.999f * first.loss && first.p_loss + first.v_loss < 1.001f * first.loss);
+        const auto after = model.evaluate_pv(img);
+        REQUIRE(after.first != before.first);
+    }
     std::printf("cpp host mirror ok\n");
     return 0;
 }

@@ -126,7 +126,10 @@ def test_split_calls_equal_the_fused_step_and_weights_reach_the_kernels(omk, no)
     rp, rv, _ = no.forward_boards(a.net_get_params(), boards, turns, dtype=torch.float64)
     big = rp > 1e-12
     assert np.max(np.abs(p[big] - rp[big]) / rp[big]) < 1e-3
-    assert np.max(np.abs(v - rv) / np.maximum(np.abs(rv), 1e-3)) < 1e-3
+    # values: tanh of a logit of scale ~20 -- relative error only where it is well conditioned ("Values")
+    assert np.max(np.abs(v - rv)) < 2e-4
+    far = np.abs(rv) >= 0.1
+    assert np.max(np.abs(v - rv)[far] / np.abs(rv)[far]) < 1e-3
     a.close()
     b.close()
 
