@@ -656,11 +656,13 @@ struct Tower16PackArgs {
     const float *conv_w, *conv_b;
     const float *w0[3], *b0[3], *dw[3], *pw[3], *b1[3], *w2[3], *b2[3];
 };
-__global__ void k_tower16_absmax(Tower16PackArgs a, uint32_t *absmax /*[9]*/) {
-    const int which = blockIdx.x;  // 3 * r + {0: w0, 1: pw, 2: w2}
+__global__ void k_tower16_absmax(Tower16PackArgs a, uint32_t *absmax /*[18]: weights [9], then their biases [9]*/) {
+    const int which = blockIdx.x % 9;  // 3 * r + {0: w0, 1: pw, 2: w2}
+    const bool bias = blockIdx.x >= 9;
     const int r = which / 3, m = which % 3;
-    const float *w = m == 0 ? a.w0[r] : (m == 1 ? a.pw[r] : a.w2[r]);
-    const int n = m == 1 ? 1024 : 4096;
+    const float *w = bias ? (m == 0 ? a.b0[r] : (m == 1 ? a.b1[r] : a.b2[r])) : (m == 0 ? a.w0[r] : (m == 1 ? a.pw[r] : a.w2[r]));
+    const int n = bias ? (m == 2 ? 128 : 32) : (m == 1 ? 1024 : 4096);
+    absmax += bias ? 9 : 0;
     uint32_t mx = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) mx = max(mx, __float_as_uint(w[i]) & 0x7FFFFFFFu);
 #pragma unroll
@@ -677,8 +679,15 @@ __global__ void k_tower16_pack(Tower16PackArgs a, const uint32_t *absmax, uint8_
     const int nth = gridDim.x * blockDim.x;
     for (int r = 0; r < 3; ++r) {
         uint8_t *img = wimg + (size_t)r * W16_BYTES;
-        const float s0 = f16_split_scale(absmax[3 * r + 0]), s1 = f16_split_scale(absmax[3 * r + 1]),
-                    s2 = f16_split_scale(absmax[3 * r + 2]);
+        // power-of-two scale of a weight tensor, limited so that its bias tile (b * 2^s / T16_BIAS_ONE) stays below 2^14 too:
+        // a network with tiny weights and large biases gets less up-scaling instead of an overflowing bias operand
+        auto scale_of = [&](int which) {
+            float sc = f16_split_scale(absmax[which]);
+            const float bmax = __uint_as_float(absmax[9 + which]);
+            while (bmax * sc * (1.0f / T16_BIAS_ONE) >= 16384.0f && sc > 1.0f) sc *= 0.5f;
+            return sc;
+        };
+        const float s0 = scale_of(3 * r + 0), s1 = scale_of(3 * r + 1), s2 = scale_of(3 * r + 2);
         for (int i = tid; i < 128 * 32; i += nth) {  // W0[k][n]: k = cin 0..127, n = cout 0..31
             const int k = i >> 5, n = i & 31;
             const uint32_t off = (uint32_t)(k >> 6) * 4096u + swz128b(n, (k & 63) * 2);
@@ -724,7 +733,7 @@ bool tower16_prepare_weights(omk_ctx *c) {
     if (!w.tower16_wimg) {
         if (cudaMalloc(&w.tower16_wimg, 3 * W16_BYTES) != cudaSuccess) return false;
         if (cudaMalloc(&w.tower16_pimg, sizeof(float) * P16_FLOATS) != cudaSuccess) return false;
-        if (cudaMalloc(&w.tower16_absmax, sizeof(uint32_t) * 9) != cudaSuccess) return false;
+        if (cudaMalloc(&w.tower16_absmax, sizeof(uint32_t) * 18) != cudaSuccess) return false;
     }
     Tower16PackArgs a;
     a.conv_w = w.t[0];
@@ -734,9 +743,9 @@ bool tower16_prepare_weights(omk_ctx *c) {
         a.w0[r] = w.t[b + 0]; a.b0[r] = w.t[b + 1]; a.dw[r] = w.t[b + 2]; a.pw[r] = w.t[b + 3];
         a.b1[r] = w.t[b + 4]; a.w2[r] = w.t[b + 5]; a.b2[r] = w.t[b + 6];
     }
-    cudaMemsetAsync(w.tower16_absmax, 0, sizeof(uint32_t) * 9, c->stream);
+    cudaMemsetAsync(w.tower16_absmax, 0, sizeof(uint32_t) * 18, c->stream);
     cudaMemsetAsync(w.tower16_wimg, 0, 3 * W16_BYTES, c->stream);
-    k_tower16_absmax<<<9, 256, 0, c->stream>>>(a, w.tower16_absmax);
+    k_tower16_absmax<<<18, 256, 0, c->stream>>>(a, w.tower16_absmax);
     k_tower16_pack<<<16, 256, 0, c->stream>>>(a, w.tower16_absmax, w.tower16_wimg, w.tower16_pimg);
     c->launches += 2;
     // the fp32 parameter image is passed to k_tower16 by value (constant bank): keep a host copy

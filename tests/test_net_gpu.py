@@ -322,3 +322,35 @@ def test_fc0_fine_chunk_keeps_batch_invariance(omk):
     with pytest.raises(omk.OmkError):
         ctx.debug_set_fc0_chunk(5)
     ctx.close()
+
+
+def test_tower_biases_through_the_mma_survive_large_biases_and_tiny_weights(omk):
+    """The tower's biases travel through the MMA as an fp16 hi/lo tile of b * 2^s / 64 (tower_f16.cu): a network whose
+    1x1 weights are tiny (large power-of-two scale) and whose biases are of order one must not overflow that tile -- the
+    scale is limited by the bias magnitude instead -- and must still meet the tolerance."""
+    import torch
+
+    from oracle import net_oracle as no
+
+    rng = np.random.default_rng(5)
+    params = no.random_params(2)
+    names = [n for n, _ in no.PARAM_SPECS]
+    for i, (name, shape) in enumerate(no.PARAM_SPECS):
+        if name.startswith("res") and name[5:] in ("w0", "pw", "w2"):
+            params[i] = (params[i] * np.float32(0.02)).astype(np.float32)      # tiny 1x1 weights
+        if name.startswith("res") and name[5:] in ("b0", "b1", "b2"):
+            params[i] = rng.uniform(-3.0, 3.0, size=shape).astype(np.float32)  # biases of order one
+    # keep the logits in a sane range for a relative comparison of priors
+    params[names.index("p_w")] = (params[names.index("p_w")] * np.float32(0.2)).astype(np.float32)
+    ctx = omk.Context(device=0, capacity_envs=1, capacity_trees=1, capacity_nodes=16, seed=0)
+    ctx.net_load_params(params)
+    boards, turns = random_positions(300, 9)
+    p, v = ctx.net_eval(boards, turns)
+    rp, rv, _ = no.forward_boards(params, boards, turns, dtype=torch.float64)
+    big = rp > 1e-12
+    assert np.isfinite(p).all() and np.max(np.abs(p[big] - rp[big]) / rp[big]) < REL
+    assert np.max(np.abs(v - rv)) < 5e-4
+    imgs = np.stack([no.encode_image(b, int(t)) for b, t in zip(boards, turns)])
+    p2, v2 = ctx.net_eval_images(imgs)
+    assert p2.tobytes() == p.tobytes() and v2.tobytes() == v.tobytes()  # boards path (tables) == image path, bit for bit
+    ctx.close()
