@@ -597,6 +597,7 @@ const char *train_report_losses(omk_ctx *c, int n, float *out3) {
         k_scale<<<1, 32, 0, c->stream>>>(t->losses, 3, 1.0f / (float)t->world);
         c->launches++;
     }
+    c->d2h_bytes += (int64_t)sizeof(float) * 3;
     if (cudaMemcpyAsync(out3, t->losses, sizeof(float) * 3, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return "loss copy failed";
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return "stream synchronisation failed";
     return cudaPeekAtLastError() == cudaSuccess ? nullptr : cudaGetErrorString(cudaGetLastError());

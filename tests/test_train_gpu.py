@@ -187,3 +187,43 @@ def test_two_rank_nccl_step_equals_the_full_batch_step(omk, no):
     for c in ranks:
         c.train_comm_destroy()
         c.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 130])
+def test_ragged_minibatch_sizes(omk, no, n):
+    """Tile edges of the training GEMMs (64 x 64 x 16 tiles, K slices): minibatches of 1, 3 and 130 positions give gradients
+    within the same bars as the 24-position case, and a step returns finite losses."""
+    ctx = omk.Context(device=0, capacity_envs=4, capacity_trees=4, capacity_nodes=64, seed=0)
+    params = params_with_biases(no, 7)
+    ctx.net_load_params(params)
+    images, pi, z = make_batch(no, n, 40 + n)
+    ctx.train_backward(images, pi, z)
+    got = ctx.train_get_grads()
+    _, want = no.loss_and_grads(params, images, pi, z)
+    for (name, _), g, w in zip(no.PARAM_SPECS, got, want):
+        scale = float(np.abs(w).max())
+        if scale == 0.0:
+            assert not g.any(), name
+            continue
+        bar = 5e-4 if name in ("v_w", "v_b") else 1e-4
+        assert float(np.abs(g.astype(np.float64) - w).max()) <= bar * scale, name
+    losses = ctx.train_apply()
+    assert all(np.isfinite(losses)) and abs(losses[0] + losses[1] - losses[2]) <= 1e-5 * abs(losses[2])
+    ctx.close()
+
+
+def test_transfer_counters_follow_the_calls(omk, no):
+    """omk_ctx_transfer_bytes (bench.py's e2e byte counts): a network call on n boards copies n * 82 bytes in and n * 82
+    floats out; a train step copies n * (243 + 81 + 1) floats in and 3 floats out."""
+    ctx = omk.Context(device=0, capacity_envs=4, capacity_trees=4, capacity_nodes=64, seed=0)
+    ctx.net_init_random(0)
+    h0, d0 = ctx.transfer_bytes
+    boards = np.zeros((10, 81), np.uint8)
+    ctx.net_eval(boards, np.zeros(10, np.uint8))
+    h1, d1 = ctx.transfer_bytes
+    assert 10 * 82 <= h1 - h0 <= 10 * 82 + 64 and 10 * 82 * 4 <= d1 - d0 <= 10 * 82 * 4 + 64, (h1 - h0, d1 - d0)
+    images, pi, z = make_batch(no, 6, 1)
+    ctx.train_step(images, pi, z)
+    h2, d2 = ctx.transfer_bytes
+    assert 6 * 325 * 4 <= h2 - h1 <= 6 * 325 * 4 + 64 and 12 <= d2 - d1 <= 12 + 64, (h2 - h1, d2 - d1)
+    ctx.close()

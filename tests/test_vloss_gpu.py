@@ -59,3 +59,18 @@ def test_virtual_loss_spreads_a_round_and_is_refused_with_the_parity_evaluator(o
     ctx.search_set_virtual_loss(False)
     ctx.pool_new_games(n=2, evaluator=omk.EVAL_HASH)
     ctx.close()
+
+
+def test_self_play_driver_runs_with_virtual_loss(omk):
+    """The device-resident driver with the opt-in mode: positions, simulation counts and the transition stream stay
+    consistent (every policy sums to one and is zero on occupied cells)."""
+    G, plies = 16, 6
+    ctx = omk.Context(device=0, capacity_envs=4, capacity_trees=2 * G, capacity_nodes=2048, seed=2)
+    ctx.net_init_random(0)
+    ctx.search_set_virtual_loss(True)
+    ctx.selfplay_begin(G, 64, 16, 0.25, 0.03, 1.0, 30, omk.EVAL_NET)
+    stats, boards, policy, status, actions = ctx.selfplay_run(plies, profile=0, want_transitions=True)
+    assert int(stats.positions) == G * plies and int(stats.simulations) == G * plies * 64
+    assert np.allclose(policy.sum(-1), 1.0, atol=1e-5) and (policy[boards != 0] == 0).all()
+    assert (status >= 0).all()
+    ctx.close()
