@@ -40,16 +40,37 @@ constexpr uint32_t T16_TMEM_COLS = 256;
 constexpr uint32_t TC_X = 0, TC_D3 = 0, TC_H = 128, TC_ACC = 160, TC_ONE = 192;  // TC_ONE: 8 columns, the bias MMA's constant A group
 // per-block weight image (bytes).  W0^T [32 n][128 k]: hi and lo, each two k-atoms of [32 rows x 128 B];
 // PW^T [32 n][32 k] and W2^T [128 n][32 k]: hi in bytes [0,64) and lo in bytes [64,128) of each 128-byte row
-constexpr int W16_W0HI = 0, W16_W0LO = 8192, W16_PW = 16384, W16_W2 = 20480;
+// (the three bias tiles sit between W0 and PW so that, once conv0 has read W0 and its bias tile, bytes [0, 16896) of the
+// image are dead for the rest of the block: the row stencil's A tile lives there)
+constexpr int W16_W0HI = 0, W16_W0LO = 8192, W16_PW = 19456, W16_W2 = 23552;
 // conv2's bias b2 goes THROUGH THE MMA: one extra k-step whose A operand is a constant group of TMEM columns (k = 0, 1 hold
 // T16_BIAS_ONE, the rest zero) and whose B operand is this tile: [128 n][8 k] fp16, K-major WITHOUT swizzle (core matrices
 // of 8 rows x 16 bytes), k = 0 / 1 = hi / lo halves of b2[n] * 2^s / T16_BIAS_ONE.  The second k-chunk of the K = 16
 // instruction points (leading-byte-offset) at a block of zeros shared by both weight buffers.  Epilogue 3 then is
 // x = lrelu(d * 2^-s + x): per channel pair one FFMA2 instead of FFMA2 + FADD2 and no constant-bank load of the bias; epilogues
 // 1 and 2 are lrelu(d * 2^-s) = max(d * 2^-s, d * 0.2 * 2^-s) in packed fp32x2 multiplies, no bias operand at all.
-constexpr int W16_B2T = 36864;                 // conv2: [128 n][8 k]
-constexpr int W16_B0T = 38912, W16_B1T = 39424;  // conv0 / conv1: [32 n][8 k] each (the same construction for b0 and b1)
+constexpr int W16_B0T = 16384, W16_B1T = 16896;  // conv0 / conv1: [32 n][8 k] each (the same construction for b0 and b1)
+constexpr int W16_B2T = 17408;                   // conv2: [128 n][8 k]
 constexpr int W16_BYTES = 36864 + 2048 + 1024;
+static_assert(W16_PW == W16_B2T + 2048 && W16_PW % 1024 == 0 && W16_W2 == W16_PW + 4096 && W16_BYTES == W16_W2 + 16384, "weight image layout");
+// ROW STENCIL (default; -DOMK_T16_PIXEL_STENCIL builds the previous form for A/B).  The depthwise 3x3 is computed by threads
+// that own a BOARD ROW x a CHANNEL PAIR (a half-warp = one board row x 32 channels) instead of a pixel x 16 channels: a thread
+// slides over the nine columns of its row, loads each input (three rows x nine columns, one LDS.64 each: 27 loads for 9
+// outputs x 2 channels instead of 9 neighbour rows x 16 channels = 36 LDS.128 for one pixel) and accumulates into the three
+// outputs it touches with packed fp32x2 FMAs whose weight operands are nine register pairs.  Shared-memory wavefronts of the
+// phase: 8 warps x 54 instead of 8 x 144.  The outputs leave as fp16 hi / lo straight into conv1's A OPERAND IN SHARED MEMORY
+// (the transposition back to "lane = pixel" that tensor memory would need is free there): K-major without swizzle, core
+// matrices of 8 pixel rows x 16 bytes, 8-row groups contiguous (SBO = 128), so a pixel row R of k-chunk c sits at
+// c * T16_A_CHUNK + 16 R -- affine in R, every store offset is an immediate -- and the chunk stride of 2048 + 32 bytes spreads
+// a half-warp's four k-chunks (and the other half-warp's row, nine pixels on) over all 32 banks: one wavefront per STS.32.
+// Chunks 0..3: hi of channels 8c..8c+7, chunks 4..7: lo.
+constexpr int T16_A_CHUNK = 2080, T16_A_BYTES = 7 * T16_A_CHUNK + 2048;
+static_assert(T16_A_BYTES <= W16_B1T, "the A tile overlays W0 hi / lo and conv0's bias tile only");
+#ifdef OMK_T16_PIXEL_STENCIL
+constexpr bool T16_ROWS = false;
+#else
+constexpr bool T16_ROWS = true;
+#endif
 constexpr float T16_BIAS_ONE = 64.0f;  // |b2| up to 65504 * 64 / 2^s stays finite in the fp16 tile
 // The small fp32 parameters travel as a KERNEL ARGUMENT (7.9 KB of the constant bank): every use is warp-uniform, so
 // biases, stem and depthwise weights become constant-bank operands of the FMAs instead of shared-memory loads.
@@ -247,6 +268,47 @@ __device__ __forceinline__ uint32_t t16_req_combo(const T16Req &r, const T16ReqS
     const uint32_t stones = ch0 | (ch1 << 1) | (ch2 << 2);
     return q.turn ? ((r.meta & 1u) ^ 1u) * 7u : stones;  // turn plane: 1.0 when black is to move
 }
+__device__ __forceinline__ float2 t16_lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));  // volatile: stays behind the barrier it follows
+    return v;
+}
+__device__ __forceinline__ void t16_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// Row stencil: depthwise 3x3 (SAME zero padding, no bias; lib.rs:204-216) of one board row x one channel pair.  `up`, `mid`,
+// `dn` address the three input rows in the fp32 tile (a row off the board points at the shared block of zeros: the taps
+// then add 0 * w, exactly); w[ky * 3 + kx] are this thread's nine weight pairs.  Output column xo of the row is pixel row
+// r0 + xo of the CTA's 128 (stored when it is one of them: the pair's middle position straddles the CTAs) and goes to
+// conv1's A tile as packed fp16 hi (chunk c) / lo (chunk 4 + c) words.
+__device__ __forceinline__ void t16_row_stencil(uint32_t up, uint32_t mid, uint32_t dn, const float2 *w, uint32_t a_addr, int r0) {
+    // (all loads and FMAs first, the splits and stores after: a store between the columns would pin every later load behind it)
+    float2 o[kSide];
+    constexpr uint32_t PX = T16_HSTRIDE * 4;
+#pragma unroll
+    for (int xi = 0; xi < kSide; ++xi) {
+        const float2 i0 = t16_lds64(up + xi * PX), i1 = t16_lds64(mid + xi * PX), i2 = t16_lds64(dn + xi * PX);
+        // input column xi is the kx = 2 tap of output xi - 1, the kx = 1 tap of output xi, the kx = 0 tap of output xi + 1
+        if (xi > 0) {
+            o[xi - 1] = __ffma2_rn(i0, w[2], o[xi - 1]); o[xi - 1] = __ffma2_rn(i1, w[5], o[xi - 1]); o[xi - 1] = __ffma2_rn(i2, w[8], o[xi - 1]);
+        }
+        // (output xi's first tap is its kx = 0 one, from column xi - 1, except in column 0)
+        o[xi] = xi > 0 ? __ffma2_rn(i0, w[1], o[xi]) : __fmul2_rn(i0, w[1]);
+        o[xi] = __ffma2_rn(i1, w[4], o[xi]); o[xi] = __ffma2_rn(i2, w[7], o[xi]);
+        if (xi + 1 < kSide) {
+            o[xi + 1] = __fmul2_rn(i0, w[0]);
+            o[xi + 1] = __ffma2_rn(i1, w[3], o[xi + 1]); o[xi + 1] = __ffma2_rn(i2, w[6], o[xi + 1]);
+        }
+    }
+#pragma unroll
+    for (int xo = 0; xo < kSide; ++xo) {
+        uint32_t hi, lo;
+        split2_f16(o[xo].x, o[xo].y, hi, lo);
+        const int R = r0 + xo;
+        if (R >= 0 && R < 128) {
+            t16_sts32(a_addr + (uint32_t)(xo * 16), hi);
+            t16_sts32(a_addr + (uint32_t)(xo * 16 + 4 * T16_A_CHUNK), lo);
+        }
+    }
+}
 #define T16_HALF(call_0, call_1) do { if (half == 0) { call_0; } else { call_1; } } while (0)
 
 // BOARDS: the hot path (packed request rows).  Block 0's conv0 + epilogue 1 are then a TABLE as well: the stem output of a
@@ -259,7 +321,7 @@ template <bool STAMPS, bool BOARDS>
 __global__ void __launch_bounds__(T16_THREADS, 2)
     k_tower16(const uint8_t *__restrict__ wimg, const __grid_constant__ Tower16Params P, const NNIn *__restrict__ nn_in,
               const float *__restrict__ images, const uint32_t *n_req, int max_rows, const __grid_constant__ CUtensorMap map_hi,
-              const __grid_constant__ CUtensorMap map_lo) {
+              const __grid_constant__ CUtensorMap map_lo, const float *__restrict__ pimg) {
     extern __shared__ uint8_t t16_smem_raw[];
     // (the broadcasts below tell ptxas that these values are warp-uniform: the MMA issue code then runs on uniform registers)
     const int rows = __shfl_sync(0xffffffffu, (int)min(*n_req, (uint32_t)max_rows), 0);
@@ -277,6 +339,14 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     // held by CTA 0, 47..56 held by CTA 1) are mirrored into the peer's tile with st.async, which signals the peer's
     // "band" mbarrier by transaction bytes: no cluster-wide barrier and no fence in the loop.
     const bool band = j == 1 && (rank == 0 ? p >= 37 : p <= 56);
+    // Row stencil: half-warp (warp, lane >> 4) owns board-row unit 2 * warp + (lane >> 4) of this CTA's 128 pixel rows --
+    // rank 0: position 0 rows 0..8, position 1 rows 0..5 (row 5: its first two pixels); rank 1: position 1 rows 5..8 (row 5:
+    // the other seven), position 2 rows 0..8 -- and the lane's channel pair.  Row 5 of the middle position is computed by
+    // both CTAs, each storing its own pixels; the inputs those need are its own rows and the mirrored band, as before.
+    const int unit = warp * 2 + (lane >> 4), cp = lane & 15;
+    const bool has_unit = unit < (rank == 0 ? 15 : 13);
+    const int uj = rank == 0 ? (unit >= 9 ? 1 : 0) : (unit < 4 ? 1 : 2);
+    const int urow = rank == 0 ? (unit >= 9 ? unit - 9 : unit) : (unit < 4 ? unit + 5 : unit - 4);
 
     uint8_t *sm = t16_smem_raw + ((1024u - (smem_u32(t16_smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(sm);
@@ -524,10 +594,27 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                                      ::"r"(ra + c * 4), "f"(o[c]), "f"(o[c + 1]), "f"(o[c + 2]), "f"(o[c + 3]), "r"(peer_band) : "memory");
                 }
             }
+            [[maybe_unused]] float2 wdw[9];
+            if constexpr (T16_ROWS) {  // this thread's nine depthwise weight pairs (L1-resident after the first iteration; the latency hides behind the band wait)
+                const float2 *wp = reinterpret_cast<const float2 *>(pimg + P16_BLK0 + r * P16_BLK + P16_DW) + cp;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) wdw[k] = __ldg(wp + k * 16);
+                // block 0 of the boards path never waited for its weight image (conv0 is a table): the A tile below overlays W0
+                if (BOARDS && r == 0 && warp == 7) mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
+            }
             T16_WAIT(bar_band, g & 1u);      // the band mirrored by the peer has arrived, and (CTA barrier) this CTA's rows are in the tile
             T16_STAMP(2 + r * 8 + 1);
             // conv1 depthwise 3x3 -> A operand of the pointwise conv
-            {
+            if constexpr (T16_ROWS) {
+                if (has_unit) {
+                    const uint32_t mid = sbase + S16_H + (uint32_t)((((uj - (int)rank) * kCells + urow * kSide) * T16_HSTRIDE + cp * 2) * 4);
+                    const uint32_t zero = sbase + S16_ZERO + (uint32_t)(cp * 8);
+                    const uint32_t up = urow > 0 ? mid - kSide * T16_HSTRIDE * 4 : zero, dn = urow < kSide - 1 ? mid + kSide * T16_HSTRIDE * 4 : zero;
+                    const int r0 = uj * kCells + urow * kSide - (int)rank * 128;
+                    t16_row_stencil(up, mid, dn, wdw, (uint32_t)((int)(wb + (cp >> 2) * T16_A_CHUNK + (cp & 3) * 4) + r0 * 16), r0);
+                }
+                fence_proxy_async_smem();  // the A tile was written through the generic proxy; conv1 reads it through the async proxy
+            } else {
                 float a[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) a[c] = 0.0f;
@@ -537,8 +624,8 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                     T16_HALF(t16_stencil<0>(B, Hpos, y, xx0, a), t16_stencil<1>(B, Hpos, y, xx0, a));
                 }
                 t16_store_group(tlane + TC_H + (uint32_t)(half * 16), a);
+                tmem_wait_st();
             }
-            tmem_wait_st();
             T16_STAMP(2 + r * 8 + 2);
             // ================= conv1 pointwise: 1x1 32 -> 32 (A = H in TMEM) =================
             fence_before();
@@ -551,10 +638,18 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                     const uint32_t dcol = tmem_base + TC_ACC;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t ahi = tmem_base + TC_H + 16u * ks;
-                        umma_f16_ts(dcol, ahi + 8u, bhi + (uint64_t)(2 * ks), T16_IDESC_N32, ks != 0);
-                        umma_f16_ts(dcol, ahi, blo + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
-                        umma_f16_ts(dcol, ahi, bhi + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
+                        if constexpr (T16_ROWS) {  // A from shared memory: hi chunks 2 ks, 2 ks + 1; lo chunks 4 + 2 ks, 5 + 2 ks
+                            const uint64_t ahi = desc_nosw(wb + (uint32_t)(2 * ks * T16_A_CHUNK), T16_A_CHUNK, 128u);
+                            const uint64_t alo = desc_nosw(wb + (uint32_t)((4 + 2 * ks) * T16_A_CHUNK), T16_A_CHUNK, 128u);
+                            umma_f16_ss<1>(dcol, alo, bhi + (uint64_t)(2 * ks), T16_IDESC_N32, ks != 0);
+                            umma_f16_ss<1>(dcol, ahi, blo + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
+                            umma_f16_ss<1>(dcol, ahi, bhi + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
+                        } else {
+                            const uint32_t ahi = tmem_base + TC_H + 16u * ks;
+                            umma_f16_ts(dcol, ahi + 8u, bhi + (uint64_t)(2 * ks), T16_IDESC_N32, ks != 0);
+                            umma_f16_ts(dcol, ahi, blo + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
+                            umma_f16_ts(dcol, ahi, bhi + (uint64_t)(2 * ks), T16_IDESC_N32, 1u);
+                        }
                     }
                     umma_f16_ts(dcol, tmem_base + TC_ONE, desc_nosw(wb + W16_B1T, sbase + S16_ZERO - (wb + W16_B1T), 128u), T16_IDESC_N32, 1u);  // + b1
                     umma_commit(bar_mma);
@@ -820,8 +915,9 @@ bool launch_tower_f16(omk_ctx *c, const float *images_dev, int rows_bound) {
     const uint32_t *n_req = c->ws.n_req;
     const void *mh = nullptr, *ml = nullptr;  // tensor maps of the write-out over this workspace's act0 arrays
     if (!fc16_tower_store_maps(c, &mh, &ml)) return false;
+    const float *pimg = c->net.tower16_pimg;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, wimg, params, nn_in, images_dev, n_req, rows_bound,
-                                             *reinterpret_cast<const CUtensorMap *>(mh), *reinterpret_cast<const CUtensorMap *>(ml));
+                                             *reinterpret_cast<const CUtensorMap *>(mh), *reinterpret_cast<const CUtensorMap *>(ml), pimg);
     if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_tower16): %s\n", cudaGetErrorString(e));
     c->launches++;
     return e == cudaSuccess;
