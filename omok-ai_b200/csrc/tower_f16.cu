@@ -18,7 +18,10 @@
 //   * a CTA needs 256 TMEM columns, 107 KB of shared memory and <= 128 registers per thread, so TWO CTAs are
 //     resident per SM: one CTA's MMA / barrier latencies hide behind the other's CUDA-core epilogues (the 3 x TF32
 //     kernel this replaces needed all 512 columns and ran one 8-warp CTA per SM, every phase exposed).
-// Warp w works on TMEM lane quadrant w%4 and channel half w/4.  The elected thread of warp 0 issues the MMA chains.
+// Warp w works on TMEM lane quadrant w%4 and channel set h = w/4 of the residual stream: channels [32h, 32h+32) and
+// [64+32h, 64+32h+32) (x[0..31], x[32..63] of its threads) -- so that conv2's output columns [0,64) serve the FIRST pass of
+// epilogue 3 of every warp and [64,128) the second: conv2 runs as two N = 64 halves with their own completion barriers
+// (the second half's MMAs hide behind the first pass).  The elected thread of warp 0 issues the MMA chains.
 //
 // TMEM columns: X/D3 [0,128)  16-channel group kk of x: hi [16kk,16kk+8) lo [16kk+8,16kk+16); the conv2 accumulator
 //                             D3 (fp32, 128 columns) aliases it: x's TMEM copy is dead once conv0 has read it
@@ -103,7 +106,12 @@ constexpr int T16_SMEM_BYTES = S16_BAR + 64 + 1024;           // 111 KB: two CTA
 static_assert(8 * T16_TABSTRIDE * 4 <= 37 * T16_HSTRIDE * 4, "the packed stem table fits below the first mirrored band row of the tile it borrows");
 static_assert(2 * (T16_SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
 constexpr uint32_t T16_BAND_BYTES = 10 * 32 * 4;              // mirrored stencil band: 10 pixel rows x 32 channels fp32
-constexpr uint32_t T16_IDESC_N32 = idesc_f16(128, 32), T16_IDESC_N128 = idesc_f16(128, 128);
+constexpr uint32_t T16_IDESC_N32 = idesc_f16(128, 32), T16_IDESC_N64 = idesc_f16(128, 64), T16_IDESC_N128 = idesc_f16(128, 128);
+#ifdef OMK_T16_NO_SPLIT2
+constexpr bool T16_SPLIT2 = false;   // conv2 as one N = 128 chain (A/B)
+#else
+constexpr bool T16_SPLIT2 = true;
+#endif
 static_assert(W16_BYTES >= 8 * 4608 && W16_BYTES % 64 == 0, "the idle weight buffer doubles as eight per-warp staging tiles (4 KB used, 512-byte aligned)");
 static_assert(S16_BAR % 8 == 0, "mbarriers are 8-byte aligned");
 
@@ -114,6 +122,11 @@ __device__ long long g_t16_dbg[64];  // phase timestamps of CTA 0's second itera
 // Wait for one of the CTA's mbarriers.  ONE warp polls it, the others block on the CTA barrier (no issue slots): with all
 // eight warps polling, try_wait + branch pairs were 10 % of the kernel's issued instructions.
 #define T16_WAIT(bar, parity) do { if (warp == 7) mbar_wait((bar), (parity)); __syncthreads(); } while (0)
+#ifdef OMK_T16_ALLPOLL
+#define T16_WAIT_MMA(bar, parity) mbar_wait((bar), (parity))
+#else
+#define T16_WAIT_MMA(bar, parity) T16_WAIT(bar, parity)
+#endif
 __device__ __forceinline__ float t16_lrelu(float v) { return fmaxf(v, 0.2f * v); }  // alpha < 1: max(v, alpha v)
 
 // split 16 fp32 values (one 16-channel group) into 8 packed hi words + 8 packed lo words and store them as A-operand columns
@@ -164,7 +177,7 @@ template <int HALF>
 __device__ __forceinline__ void t16_stem(const Tower16Params &P, float v0, float v1, float v2, float *x) {
 #pragma unroll
     for (int c = 0; c < 64; c += 2) {
-        const int ch = HALF * 64 + c;
+        const int ch = HALF * 32 + c + (c >= 32 ? 32 : 0);  // x[c] is channel t16_chan(HALF, c)
         float2 s = __ffma2_rn(make_float2(v0, v0), make_float2(P.wstem[0][ch], P.wstem[0][ch + 1]),
                               make_float2(P.bstem[ch], P.bstem[ch + 1]));
         s = __ffma2_rn(make_float2(v1, v1), make_float2(P.wstem[1][ch], P.wstem[1][ch + 1]), s);
@@ -309,6 +322,26 @@ __device__ __forceinline__ void t16_row_stencil(uint32_t up, uint32_t mid, uint3
         }
     }
 }
+// first channel of x[c .. c + 15] (c a multiple of 16) of a thread with channel set h
+__device__ __forceinline__ int t16_chan(int h, int c) { return 32 * h + c + (c >= 32 ? 32 : 0); }
+// conv0's accumulator chain over the 8 k-groups of X plus the bias step (one elected thread; all operands warp-uniform).
+// (Measured and rejected: issuing k-groups 0..3 of the NEXT block's conv0 from the middle of epilogue 3, once every warp's
+// first pass is in tensor memory -- warp 0 then waits for the slowest warp before its own second pass: +-0.)
+__device__ __forceinline__ void t16_issue_conv0(uint32_t tmem_base, uint32_t wb, uint32_t zero) {
+    constexpr int K0 = 0, K1 = 8;
+    const uint64_t bhi = desc_sw128(wb + W16_W0HI), blo = desc_sw128(wb + W16_W0LO);
+    const uint32_t dcol = tmem_base + TC_ACC;
+#pragma unroll
+    for (int kk = K0; kk < K1; ++kk) {
+        const uint64_t off = (uint64_t)(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
+        const uint32_t ahi = tmem_base + TC_X + 16u * kk;
+        umma_f16_ts(dcol, ahi + 8u, bhi + off, T16_IDESC_N32, kk != 0);
+        umma_f16_ts(dcol, ahi, blo + off, T16_IDESC_N32, 1u);
+        umma_f16_ts(dcol, ahi, bhi + off, T16_IDESC_N32, 1u);
+    }
+    if (K1 == 8)
+        umma_f16_ts(dcol, tmem_base + TC_ONE, desc_nosw(wb + W16_B0T, zero - (wb + W16_B0T), 128u), T16_IDESC_N32, 1u);  // + b0
+}
 #define T16_HALF(call_0, call_1) do { if (half == 0) { call_0; } else { call_1; } } while (0)
 
 // BOARDS: the hot path (packed request rows).  Block 0's conv0 + epilogue 1 are then a TABLE as well: the stem output of a
@@ -356,7 +389,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
     float *T0 = IMG;  // boards path: block 0's conv0 table, 8 rows x T16_HSTRIDE floats (the image buffer is unused there)
     uint32_t *TW = reinterpret_cast<uint32_t *>(sm + S16_H);  // packed stem table: used once, before the tile is
     const uint32_t bar_w0 = sbase + S16_BAR, bar_mma = sbase + S16_BAR + 16, bar_band = sbase + S16_BAR + 24,
-                   bar_free = sbase + S16_BAR + 32, tmem_slot = sbase + S16_BAR + 40;
+                   bar_free = sbase + S16_BAR + 32, tmem_slot = sbase + S16_BAR + 40, bar_mma2 = sbase + S16_BAR + 48;
     const uint32_t peer_h0 = mapa(sbase + S16_H, rank ^ 1u);
     const uint32_t peer_band = mapa(bar_band, rank ^ 1u), peer_free = mapa(bar_free, rank ^ 1u);
 
@@ -366,6 +399,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
         mbar_init(bar_mma, 8);   // one tcgen05.commit per warp
         mbar_init(bar_band, 1);  // one arrive.expect_tx per block + the peer's 1280 mirrored bytes
         mbar_init(bar_free, 1);  // the peer's "I have read your band" arrival
+        mbar_init(bar_mma2, 1);  // conv2's second half (one commit by the issuing thread)
         mbar_fence_init();
     }
     // Stem tables.  A board's input pixel is one of 8 bit triples (encoder.rs:22-43 writes only 0.0 / 1.0), so the stem
@@ -438,18 +472,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             if (elect_one()) {
                 fence_after();
                 mbar_wait(bar_w0, 0u);
-                const uint32_t wb0 = sbase + S16_W;
-                const uint64_t bhi = desc_sw128(wb0 + W16_W0HI), blo = desc_sw128(wb0 + W16_W0LO);
-                const uint32_t dcol = tmem_base + TC_ACC;
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {  // the same chain as conv0 in the loop below
-                    const uint64_t off = (uint64_t)(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
-                    const uint32_t ahi = tmem_base + TC_X + 16u * kk;
-                    umma_f16_ts(dcol, ahi + 8u, bhi + off, T16_IDESC_N32, kk != 0);
-                    umma_f16_ts(dcol, ahi, blo + off, T16_IDESC_N32, 1u);
-                    umma_f16_ts(dcol, ahi, bhi + off, T16_IDESC_N32, 1u);
-                }
-                umma_f16_ts(dcol, tmem_base + TC_ONE, desc_nosw(wb0 + W16_B0T, sbase + S16_ZERO - (wb0 + W16_B0T), 128u), T16_IDESC_N32, 1u);  // + b0
+                t16_issue_conv0(tmem_base, sbase + S16_W, sbase + S16_ZERO);  // the same chain as conv0 in the loop below
                 umma_commit(bar_mma);
             }
         } else if (lane == 0) {
@@ -501,7 +524,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             const float v0 = im[3 * pc], v1 = im[3 * pc + 1], v2 = im[3 * pc + 2];
             T16_HALF(t16_stem<0>(P, v0, v1, v2, x), t16_stem<1>(P, v0, v1, v2, x));
 #pragma unroll
-            for (int c = 0; c < 4; ++c) t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c * 16), x + c * 16);
+            for (int c = 0; c < 4; ++c) t16_store_group(tlane + TC_X + (uint32_t)t16_chan(half, c * 16), x + c * 16);
         } else {
             // ---- packed boards: the stem of this pixel is a table row ----
             // (block 0's conv0 is a table too, so the packed operand words of the stem row are not needed here: only the
@@ -509,10 +532,10 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
             combo = t16_req_combo(cur, spec);
             // prefetch the next triple's request row: its global-load latency hides behind this whole iteration
             if (tr + n_pairs < n_triples) cur = t16_req_load(nn_in + min((tr + n_pairs) * 3 + j, rows - 1), spec);
-            const float4 *tx = reinterpret_cast<const float4 *>(T32 + combo * T16_TABSTRIDE + half * 64);
+            const float4 *tx = reinterpret_cast<const float4 *>(T32 + combo * T16_TABSTRIDE + half * 32);
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                const float4 v = tx[c];
+                const float4 v = tx[c + (c >= 8 ? 8 : 0)];  // x[32..63] are channels 64 + 32 half ..
                 x[4 * c + 0] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
             }
         }
@@ -539,17 +562,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                     if (elect_one()) {
                         fence_after();
                         mbar_wait(bar_w0 + 8 * (g & 1u), (g >> 1) & 1u);
-                        const uint64_t bhi = desc_sw128(wb + W16_W0HI), blo = desc_sw128(wb + W16_W0LO);
-                        const uint32_t dcol = tmem_base + TC_ACC;
-#pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) {
-                            const uint64_t off = (uint64_t)(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
-                            const uint32_t ahi = tmem_base + TC_X + 16u * kk;
-                            umma_f16_ts(dcol, ahi + 8u, bhi + off, T16_IDESC_N32, kk != 0);
-                            umma_f16_ts(dcol, ahi, blo + off, T16_IDESC_N32, 1u);
-                            umma_f16_ts(dcol, ahi, bhi + off, T16_IDESC_N32, 1u);
-                        }
-                        umma_f16_ts(dcol, tmem_base + TC_ONE, desc_nosw(wb + W16_B0T, sbase + S16_ZERO - (wb + W16_B0T), 128u), T16_IDESC_N32, 1u);  // + b0
+                        t16_issue_conv0(tmem_base, wb, sbase + S16_ZERO);
                         umma_commit(bar_mma);
                     }
                 } else if (lane == 0) {
@@ -560,7 +573,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                     }
                     umma_commit(bar_mma);
                 }
-                T16_WAIT(bar_mma, mma_uses & 1u);
+                T16_WAIT_MMA(bar_mma, mma_uses & 1u);
                 ++mma_uses;
                 fence_after();
             }
@@ -659,7 +672,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                 if (warp == 3) mbar_arrive_cluster_relaxed(peer_free);  // the peer may overwrite this CTA's mirrored band (all stencil loads were consumed before the barrier above)
                 umma_commit(bar_mma);
             }
-            T16_WAIT(bar_mma, mma_uses & 1u);
+            T16_WAIT_MMA(bar_mma, mma_uses & 1u);
             ++mma_uses;
             fence_after();
             T16_STAMP(2 + r * 8 + 3);
@@ -679,24 +692,44 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                 if (elect_one()) {
                     fence_after();
                     const uint64_t bhi0 = desc_sw128(wb + W16_W2);
+                    if constexpr (T16_SPLIT2) {
+                        // two N = 64 halves (output channels [0,64) then [64,128): 64 rows of W2^T = 8 KB, 64 rows of the bias tile = 1 KB),
+                        // each with its own completion barrier: epilogue 3's first pass needs only the first
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint64_t bhi = bhi0 + (uint64_t)(ks * 2), blo = bhi0 + (uint64_t)(4 + ks * 2);
-                        const uint32_t ahi = tmem_base + TC_H + 16u * ks;
-                        umma_f16_ts(tmem_base + TC_D3, ahi + 8u, bhi, T16_IDESC_N128, ks != 0);
-                        umma_f16_ts(tmem_base + TC_D3, ahi, blo, T16_IDESC_N128, 1u);
-                        umma_f16_ts(tmem_base + TC_D3, ahi, bhi, T16_IDESC_N128, 1u);
+                        for (int nh = 0; nh < 2; ++nh) {
+                            const uint32_t dcol = tmem_base + TC_D3 + 64u * nh;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint64_t bhi = bhi0 + (uint64_t)(nh * 512 + ks * 2), blo = bhi0 + (uint64_t)(nh * 512 + 4 + ks * 2);
+                                const uint32_t ahi = tmem_base + TC_H + 16u * ks;
+                                umma_f16_ts(dcol, ahi + 8u, bhi, T16_IDESC_N64, ks != 0);
+                                umma_f16_ts(dcol, ahi, blo, T16_IDESC_N64, 1u);
+                                umma_f16_ts(dcol, ahi, bhi, T16_IDESC_N64, 1u);
+                            }
+                            const uint32_t bt = wb + W16_B2T + 1024u * nh;
+                            umma_f16_ts(dcol, tmem_base + TC_ONE, desc_nosw(bt, sbase + S16_ZERO - bt, 128u), T16_IDESC_N64, 1u);  // + b2 * 2^s
+                            umma_commit(nh ? bar_mma2 : bar_mma);
+                        }
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t bhi = bhi0 + (uint64_t)(ks * 2), blo = bhi0 + (uint64_t)(4 + ks * 2);
+                            const uint32_t ahi = tmem_base + TC_H + 16u * ks;
+                            umma_f16_ts(tmem_base + TC_D3, ahi + 8u, bhi, T16_IDESC_N128, ks != 0);
+                            umma_f16_ts(tmem_base + TC_D3, ahi, blo, T16_IDESC_N128, 1u);
+                            umma_f16_ts(tmem_base + TC_D3, ahi, bhi, T16_IDESC_N128, 1u);
+                        }
+                        // + b2 * 2^s: constant A group x bias tile (k-chunk 0 = the tile, k-chunk 1 = the shared zero block)
+                        umma_f16_ts(tmem_base + TC_D3, tmem_base + TC_ONE, desc_nosw(wb + W16_B2T, sbase + S16_ZERO - (wb + W16_B2T), 128u),
+                                    T16_IDESC_N128, 1u);
+                        umma_commit(bar_mma);
                     }
-                    // + b2 * 2^s: constant A group x bias tile (k-chunk 0 = the tile, k-chunk 1 = the shared zero block)
-                    umma_f16_ts(tmem_base + TC_D3, tmem_base + TC_ONE, desc_nosw(wb + W16_B2T, sbase + S16_ZERO - (wb + W16_B2T), 128u),
-                                T16_IDESC_N128, 1u);
-                    umma_commit(bar_mma);
                 }
             } else if (lane == 0) {
                 fence_after();
                 umma_commit(bar_mma);
             }
-            T16_WAIT(bar_mma, mma_uses & 1u);
+            T16_WAIT_MMA(bar_mma, mma_uses & 1u);
             ++mma_uses;
             fence_after();
             T16_STAMP(2 + r * 8 + 5);
@@ -704,13 +737,20 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
 #pragma unroll
             for (int c2 = 0; c2 < 4; c2 += 2) {
                 float d[32];
-                tmem_ld16(tlane + TC_D3 + half * 64 + c2 * 16, d);
-                tmem_ld16(tlane + TC_D3 + half * 64 + c2 * 16 + 16, d + 16);
+                const int ch0 = t16_chan(half, c2 * 16);  // 32 half (first pass), 64 + 32 half (second pass)
+                if constexpr (T16_SPLIT2) {
+                    if (c2) {  // the second half of conv2 (columns [64,128)) has its own barrier: complete long before this point
+                        mbar_wait(bar_mma2, g & 1u);
+                        fence_after();
+                    }
+                }
+                tmem_ld16(tlane + TC_D3 + ch0, d);
+                tmem_ld16(tlane + TC_D3 + ch0 + 16, d + 16);
                 tmem_wait_ld();
                 T16_HALF(t16_residual32<0>(B, c2 * 16, d, x), t16_residual32<1>(B, c2 * 16, d, x));
                 if (r < 2) {
-                    t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16), x + c2 * 16);
-                    t16_store_group(tlane + TC_X + (uint32_t)(half * 64 + c2 * 16 + 16), x + c2 * 16 + 16);
+                    t16_store_group(tlane + TC_X + (uint32_t)ch0, x + c2 * 16);
+                    t16_store_group(tlane + TC_X + (uint32_t)(ch0 + 16), x + c2 * 16 + 16);
                 } else {
                     // ---- flatten NHWC (network.rs:127-137): the tower's output leaves as fp16 hi / lo, 32 channels per
                     // pass.  This block's weight buffer is idle now (conv2 has completed) and holds the staging tiles;
@@ -720,7 +760,7 @@ __global__ void __launch_bounds__(T16_THREADS, 2)
                         if (lane == 0) bulk_wait_read0();
                         __syncwarp();
                     }
-                    t16_store_pass(tile, lane, x + c2 * 16, &map_hi, &map_lo, half * 64 + c2 * 16, (int)rank * 128 + q * 32, tr);
+                    t16_store_pass(tile, lane, x + c2 * 16, &map_hi, &map_lo, ch0, (int)rank * 128 + q * 32, tr);
                 }
             }
             tmem_wait_st();
