@@ -6,16 +6,17 @@
 // the design is about latency and data placement, not MMA throughput:
 //   * the ACTIVATIONS are the A operand and live in TENSOR MEMORY (lane = pixel row, two fp16 channels per 32-bit
 //     column, hi and lo parts of a 16-channel group side by side); threads write them with tcgen05.st straight
-//     from registers -- no swizzled shared-memory stores at all;
+//     from registers (conv0, conv2).  conv1's A operand is the exception: the depthwise stencil runs on threads that own
+//     a board row x a channel pair, so its outputs go to a no-swizzle K-major tile in SHARED memory (see T16_A_CHUNK);
 //   * the WEIGHTS are the B operand in shared memory, K-major SWIZZLE_128B, hi and lo parts, scaled by a power of
 //     two and pre-swizzled once on the device (k_tower16_pack), so one block's 36 KB image arrives by plain bulk
 //     copies (cp.async.bulk) into a double buffer, one block ahead;
 //   * the residual stream x stays in REGISTERS (a thread owns one pixel row x 64 channels) across all three blocks;
-//     the depthwise 3x3 goes through a small fp32 shared tile;
+//     the depthwise 3x3 reads a small fp32 shared tile that epilogue 1 writes (the transposition pixel -> board row);
 //   * a CTA PAIR (2x1 cluster) walks position TRIPLES: the 243 pixel rows of three positions fill 243 of the pair's
 //     256 TMEM lanes.  The middle position straddles the two CTAs; the stencil band it needs from the peer is
 //     mirrored through distributed shared memory;
-//   * a CTA needs 256 TMEM columns, 107 KB of shared memory and <= 128 registers per thread, so TWO CTAs are
+//   * a CTA needs 256 TMEM columns, 111 KB of shared memory and <= 128 registers per thread, so TWO CTAs are
 //     resident per SM: one CTA's MMA / barrier latencies hide behind the other's CUDA-core epilogues (the 3 x TF32
 //     kernel this replaces needed all 512 columns and ran one 8-warp CTA per SM, every phase exposed).
 // Warp w works on TMEM lane quadrant w%4 and channel set h = w/4 of the residual stream: channels [32h, 32h+32) and
