@@ -143,6 +143,11 @@ OMK_API int32_t omk_debug_set_tower_mode(omk_ctx *ctx, int32_t mode);
  * tensor-core accumulator truncates, so the shorter chunk is more accurate (max relative prior error 2.1e-4 -> 1.6e-4 on
  * 20 000 positions) at +0.8 % fc0 time on large batches and slower small batches (env OMK_FC0_CHUNK=3).               */
 OMK_API int32_t omk_debug_set_fc0_chunk(omk_ctx *ctx, int32_t k_blocks);
+/* fc0 tail balancing (fc_f16.cu FcBal), 0 = off (default) / 1 = on (env OMK_FC0_BALANCE=1 sets the default): the CTA-pair
+ * fc0 shares the K range of its last, partial wave of tiles with the otherwise idle CTA pairs; bit-identical rows either
+ * way (tested).  Measured on B200 (profiles/r02_fc0_tail_balancing.md): it pays only for pools of ~256 games on one lane;
+ * with two search lanes the "idle" pairs are where the other lane's kernels run, and the step gets slower. */
+OMK_API int32_t omk_debug_set_fc0_balance(omk_ctx *ctx, int32_t on);
 /* clock64 phase timestamps of one iteration inside k_tower16 (64 values; tests/tools/check_f16.py) */
 OMK_API int32_t omk_debug_tower_timing(omk_ctx *ctx, int64_t *out64);
 OMK_API int32_t omk_debug_get_buffer(omk_ctx *ctx, int32_t which, float *out, int64_t count);

@@ -115,6 +115,7 @@ def load_library():
     L.omk_debug_set_fc0_mode.argtypes = [vp, i32]
     L.omk_debug_set_tower_mode.argtypes = [vp, i32]
     L.omk_debug_set_fc0_chunk.argtypes = [vp, i32]
+    L.omk_debug_set_fc0_balance.argtypes = [vp, i32]
     L.omk_debug_set_lane_min_trees.argtypes = [vp, i32]
     L.omk_debug_get_buffer.argtypes = [vp, i32, vp, i64]
     L.omk_debug_tower_timing.argtypes = [vp, vp]
@@ -290,6 +291,9 @@ class Context:
 
     def debug_set_tower_mode(self, mode: int):
         self._check(self.L.omk_debug_set_tower_mode(self.h, mode))
+
+    def debug_set_fc0_balance(self, on: bool):
+        self._check(self.L.omk_debug_set_fc0_balance(self.h, 1 if on else 0))
 
     def debug_set_fc0_chunk(self, k_blocks: int):
         self._check(self.L.omk_debug_set_fc0_chunk(self.h, k_blocks))

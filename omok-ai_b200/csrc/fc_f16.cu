@@ -54,6 +54,31 @@ constexpr int F_CHUNK1 = OMK_F_CHUNK1;            // fc1: 8 k-blocks
 constexpr int F_CHUNKH = OMK_F_CHUNKH;            // heads: 8 k-blocks
 constexpr int kSplitKMaxRows = 2048;              // fc0 batches up to here take the split-K path (36 CTAs per 128 rows): 95 vs 152 us at 2048 rows, 181 vs 158 us at 4096
 
+// TAIL BALANCING of the CTA-pair fc0 (bit-exact).  A launch of T pair-tiles on P resident CTA pairs runs whole waves; in
+// the last, partial wave (R = T mod P tiles) the other H = P - R pairs would idle (the search lanes launch 64 tiles for 74
+// pairs).  Instead the R "main" pairs accumulate only the first m chunks of their tile, and the H "helper" pairs compute the
+// last `tail` = NCHUNK - m chunks of every main tile as stand-alone chunk sums, stored raw to a scratch buffer; a main pair
+// then adds its tile's tail chunks IN ORDER after its own m -- the same partial sums in the same order as the unsplit loop,
+// so every row keeps its bits (tests/test_net_gpu.py::test_batch_invariance, ::test_fc0_tail_balancing) -- and runs the usual
+// epilogue.  A helper's units form one flat k-block stream (no pipeline refill between units).  Helpers have the lowest
+// block indices of the wave, so they are resident before the mains that wait for them (per-tile release / acquire counters
+// in global memory, bounded spins that trap instead of hanging).
+struct FcBal {
+    int full;         // clusters [0, full): whole tiles (earlier, complete waves)
+    int helpers;      // clusters [full, full + helpers): helper pairs
+    int m, tail;      // a main tile: chunks [0, m) by its own pair, [m, m + tail) by helpers
+    int mains;        // main tiles (clusters [full + helpers, full + helpers + mains), tile = cluster - helpers)
+    float4 *partial;  // [mains * tail units][2 CTAs][8 drain warps][32 float4 groups][32 lanes]
+    uint32_t *flags;  // [2][mains]: arrived helper warps per main tile, main warps done with the tile
+};
+constexpr int F_BAL_TAIL_MAX = 4;
+constexpr size_t F_BAL_UNIT_F4 = 2 * 8 * 32 * 32;  // float4 per unit (one 256 x 256 chunk sum)
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <bool PAIR, int BN>
 struct FcCfg {
     static constexpr int kStages = PAIR ? 3 : 2;
@@ -78,7 +103,8 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
            const float *__restrict__ bias, const float *__restrict__ inv_scale_p, float *__restrict__ C,
            __half *__restrict__ C_hi, __half *__restrict__ C_lo, const uint32_t *n_req, int max_rows,
-           float *__restrict__ P_out = nullptr, float *__restrict__ V_out = nullptr, uint32_t *dev_error = nullptr) {
+           float *__restrict__ P_out = nullptr, float *__restrict__ V_out = nullptr, uint32_t *dev_error = nullptr,
+           const FcBal bal = FcBal{}) {
     using Cfg = FcCfg<PAIR, BN>;
     static_assert(!HEADS || (BN == 128 && !PAIR), "the heads epilogue needs a whole logit row per thread");
     constexpr int CG = PAIR ? 2 : 1;
@@ -93,14 +119,33 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
     const int rows = (int)min(*n_req, (uint32_t)max_rows);
     uint32_t rank = 0;
     int m0, n0;
+    // (pair kernel) this cluster's role and its sequence of chunks: whole tile = chunks [0, NCHUNK) of one tile; main = chunks
+    // [0, m) of one tile, then the helpers' tail sums; helper = units [u0, u1), unit u = chunk m + u % tail of main tile u / tail
+    [[maybe_unused]] int role = 0, n_seq = NCHUNK, u0 = 0;  // role: 0 whole, 1 main, 2 helper
+    [[maybe_unused]] int tile = 0;
     if constexpr (PAIR) {
-        // blockIdx.x = ((pair * 2 + n_tile) * 2 + rank): the two N tiles of one row pair are neighbours in launch order so
-        // that the second reads its A rows from L2, not from DRAM
+        // tile = pair * 2 + n_tile: the two N tiles of one row pair are neighbours in launch order so that the second reads
+        // its A rows from L2, not from DRAM
         rank = cluster_rank();
-        const int pair = blockIdx.x >> 2;
+        const int cid = blockIdx.x >> 1;
+        tile = cid;
+        if (cid >= bal.full && bal.helpers > 0) {
+            if (cid < bal.full + bal.helpers) {
+                role = 2;
+                const int units = bal.mains * bal.tail, h = cid - bal.full;
+                const int per = (units + bal.helpers - 1) / bal.helpers;
+                u0 = h * per;
+                n_seq = max(0, min(units, u0 + per) - u0);
+            } else {
+                role = 1;
+                tile = cid - bal.helpers;
+                n_seq = bal.m;
+            }
+        }
+        const int pair = tile >> 1;
         m0 = pair * 256 + (int)rank * F_BM;
-        n0 = (int)((blockIdx.x >> 1) & 1u) * BN;
-        if (pair * 256 >= rows) return;  // uniform for the whole cluster
+        n0 = (tile & 1) * BN;
+        if (role != 2 && pair * 256 >= rows) return;  // uniform for the whole cluster
     } else {
         m0 = blockIdx.y * F_BM;
         n0 = blockIdx.x * BN;
@@ -139,18 +184,37 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
-            for (int kb = 0; kb < NKB; ++kb) {
+            if constexpr (PAIR) {  // both CTAs load; the transaction bytes of both land on the leader's barrier
+                int it = 0;  // flat k-block counter of this cluster (the ring runs through unit boundaries)
+                for (int i = 0; i < n_seq; ++i) {
+                    int ch = i, mm = m0, nn = n0;
+                    if (role == 2) {
+                        const int u = u0 + i, tl = bal.full + u / bal.tail;
+                        ch = bal.m + u % bal.tail;
+                        mm = (tl >> 1) * 256 + (int)rank * F_BM;
+                        nn = (tl & 1) * BN;
+                        if ((tl >> 1) * 256 >= rows) continue;  // that main pair has left: nobody reads this unit
+                    }
+                    for (int kc = 0; kc < CHUNK; ++kc, ++it) {
+                        const int kb = ch * CHUNK + kc, s = it % Cfg::kStages;
+                        const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
+                        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                        const uint32_t st = base + s * Cfg::kStageBytes;
+                        const uint32_t lbar = mapa(full0 + 8 * s, 0);
+                        if (leader) mbar_expect_tx(full0 + 8 * s, 2 * Cfg::kStageBytes);
+                        tma_load_2d_2sm(st, &map_a_hi, lbar, kb * F_BK, mm);
+                        tma_load_2d_2sm(st + F_A_BYTES, &map_a_lo, lbar, kb * F_BK, mm);
+                        tma_load_2d_2sm(st + 2 * F_A_BYTES, &map_b_hi, lbar, kb * F_BK, nn + (int)rank * 128);
+                        tma_load_2d_2sm(st + 2 * F_A_BYTES + Cfg::kBBytes, &map_b_lo, lbar, kb * F_BK, nn + (int)rank * 128);
+                    }
+                }
+            }
+            for (int kb = 0; kb < (PAIR ? 0 : NKB); ++kb) {
                 const int s = kb % Cfg::kStages;
                 const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 const uint32_t st = base + s * Cfg::kStageBytes;
-                if constexpr (PAIR) {  // both CTAs load; the transaction bytes of both land on the leader's barrier
-                    const uint32_t lbar = mapa(full0 + 8 * s, 0);
-                    if (leader) mbar_expect_tx(full0 + 8 * s, 2 * Cfg::kStageBytes);
-                    tma_load_2d_2sm(st, &map_a_hi, lbar, (kb_base + kb) * F_BK, m0);
-                    tma_load_2d_2sm(st + F_A_BYTES, &map_a_lo, lbar, (kb_base + kb) * F_BK, m0);
-                    tma_load_2d_2sm(st + 2 * F_A_BYTES, &map_b_hi, lbar, (kb_base + kb) * F_BK, n0 + (int)rank * 128);
-                    tma_load_2d_2sm(st + 2 * F_A_BYTES + Cfg::kBBytes, &map_b_lo, lbar, (kb_base + kb) * F_BK, n0 + (int)rank * 128);
+                if constexpr (PAIR) {
                 } else {
                     const uint32_t bar = full0 + 8 * s;
                     mbar_expect_tx(bar, Cfg::kStageBytes);
@@ -163,16 +227,19 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
         }
     } else if (warp == 1) {
         if (leader && lane == 0) {  // ===== MMA issuer (the leader CTA of a pair) =====
-            for (int ch = 0; ch < NCHUNK; ++ch) {
-                const int buf = ch & 1;
-                const uint32_t use = (uint32_t)(ch >> 1);
+            for (int i = 0, ci = 0, it = 0; i < n_seq; ++i) {  // ci: chunks issued, it: k-blocks consumed (ring position)
+                if constexpr (PAIR) {
+                    if (role == 2 && ((bal.full + (u0 + i) / bal.tail) >> 1) * 256 >= rows) continue;  // skipped unit (see the producer)
+                }
+                const int buf = ci & 1;
+                const uint32_t use = (uint32_t)(ci >> 1);
+                ++ci;
                 mbar_wait(tmem_empty0 + 8 * buf, (use & 1u) ^ 1u);  // drained (passes at once for the first use)
                 fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
-                for (int kc = 0; kc < CHUNK; ++kc) {
-                    const int kb = ch * CHUNK + kc;
-                    const int s = kb % Cfg::kStages;
-                    const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
+                for (int kc = 0; kc < CHUNK; ++kc, ++it) {
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
                     mbar_wait(full0 + 8 * s, ph);
                     fence_after();
                     const uint32_t st = base + s * Cfg::kStageBytes;
@@ -195,9 +262,20 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
         float acc[128];
 #pragma unroll
         for (int j = 0; j < 128; ++j) acc[j] = 0.0f;
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-            const int buf = ch & 1;
-            const uint32_t use = (uint32_t)(ch >> 1);
+        for (int ch = 0, ci = 0; ch < n_seq; ++ch) {
+            [[maybe_unused]] float4 *unit_dst = nullptr;  // helper: where this unit's raw chunk sums go
+            [[maybe_unused]] int unit_main = 0;
+            if constexpr (PAIR) {
+                if (role == 2) {
+                    const int u = u0 + ch;
+                    unit_main = u / bal.tail;
+                    if (((bal.full + unit_main) >> 1) * 256 >= rows) continue;  // skipped unit (see the producer)
+                    unit_dst = bal.partial + (((size_t)u * 2 + rank) * 8 + (size_t)(warp - 2)) * 1024 + lane;
+                }
+            }
+            const int buf = ci & 1;
+            const uint32_t use = (uint32_t)(ci >> 1);
+            ++ci;
             mbar_wait(tmem_full0 + 8 * buf, use & 1u);
             fence_after();
 #pragma unroll
@@ -205,13 +283,25 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 128 + c), v);
                 tmem_wait_ld();
+                if (PAIR && role == 2) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c + j] += v[j];
+                    for (int j = 0; j < 32; j += 4) unit_dst[(size_t)((c + j) >> 2) * 32] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c + j] += v[j];
+                }
             }
             fence_before();
             __syncwarp();
             if (lane == 0) {
                 if constexpr (PAIR) mbar_arrive_cluster(mapa(tmem_empty0 + 8 * buf, 0)); else mbar_arrive(tmem_empty0 + 8 * buf);
+            }
+            if constexpr (PAIR) {
+                if (role == 2) {  // release this warp's share of the unit to the main pair of the tile
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(bal.flags + unit_main, 1u);
+                }
             }
             if constexpr (SPLITK) {  // raw partial sums of THIS chunk: C[chunk index][row in tile][512]; the accumulator restarts
                 const int prow = m0 + q * 32 + lane;
@@ -222,6 +312,30 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
                 }
 #pragma unroll
                 for (int j = 0; j < 128; ++j) acc[j] = 0.0f;
+            }
+        }
+        if constexpr (PAIR) {
+            if (role == 1) {  // the tile's tail chunks, computed by helper pairs: add them in order behind this pair's own m chunks
+                const int k = tile - bal.full;
+                const uint32_t need = (uint32_t)bal.tail * 16u;  // 8 drain warps x 2 CTAs per unit
+                uint32_t spin = 0;
+                while (ld_acquire_u32(bal.flags + k) < need) {
+                    if (++spin > (1u << 22)) __trap();  // a scheduling assumption broke: fail loudly instead of hanging
+                    __nanosleep(64);
+                }
+                for (int j = 0; j < bal.tail; ++j) {
+                    const float4 *src = bal.partial + (((size_t)(k * bal.tail + j) * 2 + rank) * 8 + (size_t)(warp - 2)) * 1024 + lane;
+#pragma unroll
+                    for (int c4 = 0; c4 < 32; ++c4) {
+                        const float4 v = __ldcg(src + (size_t)c4 * 32);
+                        acc[4 * c4 + 0] += v.x; acc[4 * c4 + 1] += v.y; acc[4 * c4 + 2] += v.z; acc[4 * c4 + 3] += v.w;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && atomicAdd(bal.flags + 128 + k, 1u) == 15u) {  // the last of the tile's 16 main warps re-arms the counters
+                    atomicExch(bal.flags + k, 0u);
+                    atomicExch(bal.flags + 128 + k, 0u);
+                }
             }
         }
         const int row = m0 + q * 32 + lane;
@@ -256,7 +370,7 @@ __global__ void __launch_bounds__((FcCfg<PAIR, BN>::kThreads), 1)
                 prow[80] = acc[80] * inv;
                 V_out[row] = tanhf(vlogit);
             }
-        } else if (row < rows) {  // rows past the batch are never stored (the tile may extend past the workspace)
+        } else if (row < rows && role != 2) {  // rows past the batch are never stored (the tile may extend past the workspace)
 #pragma unroll
             for (int j = 0; j < 128; j += 8) {
                 float o[8];
@@ -424,6 +538,9 @@ struct ActMaps {  // tensor maps over one workspace's activation buffers (each s
     int a_rows = 0;
     float *splitk_partial = nullptr;  // [splitk_chunks][splitk_rows][512] fp32 partial sums of this workspace's split-K fc0
     int splitk_rows = 0, splitk_chunks = 0;
+    float4 *bal_partial = nullptr;    // tail-balancing scratch of this workspace's pair fc0: [units][F_BAL_UNIT_F4]
+    int bal_units = 0;
+    uint32_t *bal_flags = nullptr;    // [256]
 };
 struct Fc16State {
     CUtensorMap map0_b_hi, map0_b_lo;  // fc0 (B boxes of 128 rows: the pair kernel loads half tiles)
@@ -433,6 +550,7 @@ struct Fc16State {
     int next_victim = 0;
     bool weights_ready = false;
     CUtensorMap map0s_b_hi, map0s_b_lo;  // fc0 weights with 256-row boxes (one-CTA split-K kernel for small batches)
+    int pair_slots = 0;                  // CTA pairs of the fc0 pair kernel the device holds at once (0 = not queried yet)
 };
 
 static Fc16State *state16_of(omk_ctx *c) {
@@ -442,7 +560,11 @@ static Fc16State *state16_of(omk_ctx *c) {
 
 void fc16_free(omk_ctx *c) {
     if (c->fc16_state)
-        for (ActMaps &m : reinterpret_cast<Fc16State *>(c->fc16_state)->acts) cudaFree(m.splitk_partial);
+        for (ActMaps &m : reinterpret_cast<Fc16State *>(c->fc16_state)->acts) {
+            cudaFree(m.splitk_partial);
+            cudaFree(m.bal_partial);
+            cudaFree(m.bal_flags);
+        }
     delete reinterpret_cast<Fc16State *>(c->fc16_state);
     c->fc16_state = nullptr;
 }
@@ -551,7 +673,7 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
         cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         sk<<<dim3(F_N / F_BN, mt, F_K0 / F_BK / F_SPLITK_KB), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
             am->map0_a_hi, am->map0_a_lo, s->map0s_b_hi, s->map0s_b_lo, c->net.t[24], c->net.fc_inv_scale, am->splitk_partial, nullptr,
-            nullptr, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr);
+            nullptr, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr, FcBal{});
         k_fc0_reduce<<<(rows_bound * 64 + 255) / 256, 256, 0, c->stream>>>(am->splitk_partial, kChunks, ws_rows, c->net.t[24],
                                                                             c->net.fc_inv_scale, c->ws.act1_h16, c->ws.act1_l16,
                                                                             c->ws.n_req, rows_bound);
@@ -580,8 +702,49 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
     const uint32_t *nreq_p = c->ws.n_req;
     float *no_p = nullptr, *no_v = nullptr;
     uint32_t *no_err = nullptr;
+    // tail balancing (see FcBal): the last, partial wave of tiles shares its K range with the otherwise idle pairs
+    FcBal bal{};
+    if (!fine && c->fc0_balance) {
+        if (s->pair_slots == 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+            s->pair_slots = n > 0 ? n : -1;
+        }
+        const int P = s->pair_slots, T = (F_N / F_BN) * pairs, NC = F_K0 / F_BK / F_CHUNK0;
+        const int R = P > 0 ? T % P : 0, H = P - R;
+        if (R > 0 && R <= 128 && H > 0) {
+            int tail = 0;
+            for (int t = 1; t <= F_BAL_TAIL_MAX; ++t)
+                if ((R * t + H - 1) / H + 1 <= NC - t) tail = t;  // the helpers' units fit beside the mains' own chunks
+            if (tail > 0) {
+                const int units = R * tail;
+                bool ok = true;
+                if (!am->bal_flags) {
+                    ok = cudaMalloc(&am->bal_flags, sizeof(uint32_t) * 256) == cudaSuccess &&
+                         cudaMemsetAsync(am->bal_flags, 0, sizeof(uint32_t) * 256, c->stream) == cudaSuccess;
+                }
+                if (ok && am->bal_units < units) {
+                    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+                    cudaFree(am->bal_partial);
+                    am->bal_partial = nullptr;
+                    am->bal_units = 0;
+                    ok = cudaMalloc(&am->bal_partial, sizeof(float4) * F_BAL_UNIT_F4 * (size_t)units) == cudaSuccess;
+                    if (ok) am->bal_units = units;
+                }
+                if (!ok) return false;
+                bal.full = T - R;
+                bal.helpers = H;
+                bal.mains = R;
+                bal.tail = tail;
+                bal.m = NC - tail;
+                bal.partial = am->bal_partial;
+                bal.flags = am->bal_flags;
+                cfg.gridDim = dim3(2 * (T + H), 1);
+            }
+        }
+    }
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, am->map0_a_hi, am->map0_a_lo, s->map0_b_hi, s->map0_b_lo, bias_p, inv_p, c_f32,
-                                             c_hi, c_lo, nreq_p, rows_bound, no_p, no_v, no_err);
+                                             c_hi, c_lo, nreq_p, rows_bound, no_p, no_v, no_err, bal);
     if (e != cudaSuccess) fprintf(stderr, "omok_b200: cudaLaunchKernelEx(k_fc16 pair): %s\n", cudaGetErrorString(e));
     c->launches++;
     return e == cudaSuccess && check_launch("fc0 (fp16 split)");
@@ -598,7 +761,7 @@ bool launch_fc1_f16(omk_ctx *c, int rows_bound) {
     const int mt = (rows_bound + F_BM - 1) / F_BM;
     kern<<<dim3(F_N / F_BN, mt), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
         am->map1_a_hi, am->map1_a_lo, s->map1_b_hi, s->map1_b_lo, c->net.t[26], c->net.fc_inv_scale + 1, nullptr, c->ws.act2_h16,
-        c->ws.act2_l16, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr);
+        c->ws.act2_l16, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr, FcBal{});
     c->launches++;
     return check_launch("fc1 (fp16 split)");
 }
@@ -614,7 +777,7 @@ bool launch_heads_f16(omk_ctx *c, int rows_bound) {
     const int mt = (rows_bound + F_BM - 1) / F_BM;
     kern<<<dim3(1, mt), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
         am->map2_a_hi, am->map2_a_lo, s->map2_b_hi, s->map2_b_lo, c->net.heads_b, c->net.fc_inv_scale + 2, nullptr, nullptr, nullptr,
-        c->ws.n_req, rows_bound, c->ws.P, c->ws.V, c->dev_error);
+        c->ws.n_req, rows_bound, c->ws.P, c->ws.V, c->dev_error, FcBal{});
     c->launches++;
     return check_launch("heads (fp16 split)");
 }

@@ -295,6 +295,7 @@ extern "C" int32_t omk_ctx_create(int32_t device, int32_t capacity_envs, int32_t
     if (const char *m = getenv("OMK_TOWER")) c->tower_mode = parse_mode(m);
     if (const char *m = getenv("OMK_LANE_MIN_TREES")) c->lane_min_trees = atoi(m);
     if (const char *m = getenv("OMK_FC0_CHUNK")) c->fc0_chunk = atoi(m) == 3 ? 3 : 9;
+    if (const char *m = getenv("OMK_FC0_BALANCE")) c->fc0_balance = atoi(m) != 0;
     if (const char *m = getenv("OMK_SEARCH_VIRTUAL_LOSS")) c->virtual_loss = atoi(m) != 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
@@ -568,6 +569,11 @@ extern "C" int32_t omk_debug_set_fc0_mode(omk_ctx *c, int32_t mode) {
 extern "C" int32_t omk_debug_set_tower_mode(omk_ctx *c, int32_t mode) {
     if (mode != 0 && mode != 1) return fail(OMK_ERR_INVALID, "tower mode must be 1 (tcgen05 3xFP16) or 0 (fp32 CUDA cores, A/B check)");
     c->tower_mode = mode;
+    return OMK_OK;
+}
+extern "C" int32_t omk_debug_set_fc0_balance(omk_ctx *c, int32_t on) {
+    if (on != 0 && on != 1) return fail(OMK_ERR_INVALID, "fc0 balance must be 0 or 1");
+    c->fc0_balance = on;
     return OMK_OK;
 }
 extern "C" int32_t omk_debug_set_fc0_chunk(omk_ctx *c, int32_t k_blocks) {

@@ -83,6 +83,7 @@ extern "C" {
     pub fn omk_debug_set_fc0_mode(ctx: *mut omk_ctx, mode: i32) -> i32;
     pub fn omk_debug_set_tower_mode(ctx: *mut omk_ctx, mode: i32) -> i32;
     pub fn omk_debug_set_fc0_chunk(ctx: *mut omk_ctx, k_blocks: i32) -> i32;
+    pub fn omk_debug_set_fc0_balance(ctx: *mut omk_ctx, on: i32) -> i32;
     pub fn omk_debug_tower_timing(ctx: *mut omk_ctx, out64: *mut i64) -> i32;
     pub fn omk_debug_get_buffer(ctx: *mut omk_ctx, which: i32, out: *mut f32, count: i64) -> i32;
     pub fn omk_debug_set_lane_min_trees(ctx: *mut omk_ctx, min_trees: i32) -> i32;

@@ -84,6 +84,30 @@ def test_batch_invariance(net):
         assert q.tobytes() == P[lo:hi].tobytes() and w.tobytes() == V[lo:hi].tobytes()
 
 
+@pytest.mark.parametrize("n", [4500, 8040, 9400, 17000])
+def test_fc0_tail_balancing_keeps_every_row(net, n):
+    """The CTA-pair fc0 shares the K range of its last, partial wave of tiles with the otherwise idle pairs (fc_f16.cu FcBal:
+    helper pairs compute the tail chunks, the tile's own pair adds them in order).  Every row must keep the bits it gets
+    from the split-K path (batches of <= 2048 rows: every chunk a CTA, chunks added in order).  4500 rows = 36 tiles beside
+    38 helper pairs, 8040 = a search lane's 64 tiles, 9400 = 74 tiles (a full wave: nothing to balance), 17000 = one whole
+    wave + a balanced second one."""
+    ctx, params, no = net
+    boards, turns = random_positions(n, 1000 + n)
+    ctx.debug_set_fc0_balance(True)  # opt-in (default off: see include/omok_b200.h)
+    try:
+        P, V = ctx.net_eval(boards, turns)
+        P2, V2 = ctx.net_eval(boards, turns)  # again: re-armed counters, same scratch buffer
+    finally:
+        ctx.debug_set_fc0_balance(False)
+    assert P2.tobytes() == P.tobytes() and V2.tobytes() == V.tobytes()
+    P0, V0 = ctx.net_eval(boards, turns)  # the unbalanced pair kernel
+    assert P0.tobytes() == P.tobytes() and V0.tobytes() == V.tobytes()
+    for lo in range(0, n, 2048):  # ... and the split-K path
+        hi = min(n, lo + 2048)
+        q, w = ctx.net_eval(boards[lo:hi], turns[lo:hi])
+        assert q.tobytes() == P[lo:hi].tobytes() and w.tobytes() == V[lo:hi].tobytes(), (n, lo)
+
+
 @pytest.mark.parametrize("n", [1, 7, 8, 127, 128, 129, 255, 256, 257, 513])
 def test_small_and_ragged_batches(omk, n):
     """Tile edges: batches below / at / above the 128-row MMA tile and the 256-row CTA-pair tile, each in a FRESH context
