@@ -115,3 +115,63 @@ def test_environment_agrees_on_random_playouts(orc):
             assert pe.legal_move_count == ce.legal_move_count
             if ps is not None and ps != 0:
                 break
+
+
+# ---- the network oracle against a second restatement (tests/pyref_net.py: numpy, explicit tap / channel loops) ----
+def _random_net_params(seed):
+    from oracle import net_oracle
+
+    rng = np.random.default_rng(seed)
+    params = net_oracle.random_params(seed)
+    for i, (name, shape) in enumerate(net_oracle.PARAM_SPECS):  # the recipe's biases are zero: give every bias a value
+        if len(shape) == 1:
+            params[i] = rng.normal(0.0, 0.3, size=shape).astype(np.float32)
+    return params
+
+
+def _random_positions(n, seed):
+    rng = np.random.default_rng(seed)
+    boards = np.zeros((n, 81), np.uint8)
+    turns = np.zeros(n, np.uint8)
+    for b in range(n):
+        k = int(rng.integers(0, 81))
+        for j, c in enumerate(rng.permutation(81)[:k]):
+            boards[b, c] = 1 + (j % 2)
+        turns[b] = int(rng.integers(0, 2))
+    return boards, turns
+
+
+def test_input_image_agrees_with_second_restatement():
+    import pyref_net
+    from oracle import net_oracle
+
+    boards, turns = _random_positions(40, 5)
+    for b, t in zip(boards, turns):
+        for opp in (False, True):
+            a = net_oracle.encode_image(b, int(t), opponent_mode=opp)
+            r = pyref_net.encode_nn_input(b, black_to_move=(t == 0), opponent_mode=opp)
+            assert a.astype(np.float64).tobytes() == r.tobytes()
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_network_forward_agrees_with_second_restatement(seed):
+    """Every layer of oracle/net_oracle.py (torch conv2d graph, fp64) against the numpy restatement written from the Rust
+    graph builder and TensorFlow's op semantics: stem, the three bottleneck blocks (depthwise filter layout [kh][kw][c],
+    SAME padding, one bias after the pointwise conv, residual add before the last leaky-relu), NHWC flatten order, fc0, fc1,
+    both heads.  fp64 on both sides: agreement to rounding."""
+    import torch
+
+    import pyref_net
+    from oracle import net_oracle
+
+    params = _random_net_params(seed)
+    boards, turns = _random_positions(10, 100 + seed)
+    imgs = np.stack([net_oracle.encode_image(b, int(t), opponent_mode=bool(i % 2)) for i, (b, t) in enumerate(zip(boards, turns))])
+    a = net_oracle.forward_layers(params, imgs, dtype=torch.float64)
+    r = pyref_net.forward(params, imgs)
+    for k in ("tower", "fc0", "fc1", "logits", "vlogit", "P", "V"):
+        scale = max(np.abs(r[k]).max(), 1e-30)
+        assert np.abs(np.asarray(a[k], np.float64) - r[k]).max() <= 1e-11 * scale, k
+    # the fp32 forward the GPU tests compare against is the same graph
+    p32, v32, lg32 = net_oracle.forward(params, imgs)
+    assert np.abs(p32 - r["P"]).max() <= 2e-4 * r["P"].max() and np.abs(v32 - r["V"]).max() <= 1e-4
