@@ -69,25 +69,36 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
     const int k_begin = (int)blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
-    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
-        // stage a 64 x 16 slice of op(A) and a 16 x 64 slice of op(B); out-of-range elements are zeros
+    // The next k-step's 64 x 16 slice of op(A) and 16 x 64 slice of op(B) are fetched into registers while this one is
+    // multiplied (a CTA with a long K and few neighbours is otherwise a chain of exposed global-load latencies: 2.4 us per
+    // k-step measured); out-of-range elements are zeros.  The summation order is unchanged.
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int idx = t + 256 * i;  // 0..1023
             int m, k;
             if (TA) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
             const int gm = m0 + m, gk = k0 + k;
-            float v = 0.0f;
-            if (gm < M && gk < k_end) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-            As[k][m] = v;
+            ra[i] = 0.0f;
+            if (gm < M && gk < k_end) ra[i] = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
             int n, kb;
             if (TB) { kb = idx & 15; n = idx >> 4; } else { n = idx & 63; kb = idx >> 6; }
             const int gn = n0 + n, gkb = k0 + kb;
-            float w = 0.0f;
-            if (gn < N && gkb < k_end) w = TB ? B[(size_t)gn * ldb + gkb] : B[(size_t)gkb * ldb + gn];
-            Bs[kb][n] = w;
+            rb[i] = 0.0f;
+            if (gn < N && gkb < k_end) rb[i] = TB ? B[(size_t)gn * ldb + gkb] : B[(size_t)gkb * ldb + gn];
+        }
+    };
+    if (k_begin < k_end) fetch(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = t + 256 * i;
+            if (TA) As[idx >> 6][idx & 63] = ra[i]; else As[idx & 15][idx >> 4] = ra[i];
+            if (TB) Bs[idx & 15][idx >> 4] = rb[i]; else Bs[idx >> 6][idx & 63] = rb[i];
         }
         __syncthreads();
+        if (k0 + 16 < k_end) fetch(k0 + 16);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             float a[4], b[4];
@@ -131,7 +142,13 @@ __global__ void k_tgemm_reduce(const float *__restrict__ part, int splits, int M
     if (idx >= (long long)M * N) return;
     const int m = (int)(idx / N), n = (int)(idx % N);
     float v = 0.0f;
-    for (int z = 0; z < splits; ++z) v += part[((size_t)z * M + m) * N + n];
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {  // four independent loads in flight, added in slice order
+        const float p0 = part[((size_t)z * M + m) * N + n], p1 = part[((size_t)(z + 1) * M + m) * N + n],
+                    p2 = part[((size_t)(z + 2) * M + m) * N + n], p3 = part[((size_t)(z + 3) * M + m) * N + n];
+        v += p0; v += p1; v += p2; v += p3;
+    }
+    for (; z < splits; ++z) v += part[((size_t)z * M + m) * N + n];
     const size_t o = (size_t)m * ldc + n;
     if (e.bias) v += e.bias[n];
     if (e.res) v += e.res[o];
@@ -148,13 +165,15 @@ static void tgemm(omk_ctx *c, const float *A, const float *B, float *C, int M, i
                   const GemmEpi &e) {
     cudaStream_t s = c->stream;
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    // few output tiles and a long K: slice K so that ~2 waves of CTAs exist (fixed slice size -> fixed summation order)
+    // few output tiles: slice K so that ~2 waves of CTAs exist (fixed slice size -> fixed summation order).  One CTA walks
+    // its K in steps of 16 with a CTA barrier each, so a 16-tile product with K = 512 (fc1 and the heads on a minibatch of
+    // 128) was 32 dependent steps on 16 SMs: 85 us; sliced, 2 steps on 256 CTAs.
     const int tiles = (int)(grid.x * grid.y);
-    if (K >= 2048 && tiles < 64) {
-        int splits = min(64, max(2, 296 / tiles));
-        int kps = ((K + splits - 1) / splits + 15) / 16 * 16;
+    if (K >= 128 && tiles < 592) {  // fewer than four CTAs per SM: aim at eight
+        int splits = min(64, max(2, 1184 / tiles));
+        int kps = max(32, ((K + splits - 1) / splits + 15) / 16 * 16);
         splits = (K + kps - 1) / kps;
-        float *part = g_splitk_scratch(c, (size_t)splits * M * N);
+        float *part = splits >= 2 ? g_splitk_scratch(c, (size_t)splits * M * N) : nullptr;
         if (part) {
             grid.z = splits;
             k_tgemm<TA, TB><<<grid, 256, 0, s>>>(A, B, C, M, N, K, lda, ldb, ldc, e, kps, part);
@@ -167,22 +186,43 @@ static void tgemm(omk_ctx *c, const float *A, const float *B, float *C, int M, i
     k_tgemm<TA, TB><<<grid, 256, 0, s>>>(A, B, C, M, N, K, lda, ldb, ldc, e, K, nullptr);
 }
 
-// out[n] = sum over m of X[m, n] in a fixed order: one block per 32 columns, 8 row groups, sequential within a group,
-// groups added in order
-__global__ void k_colsum(const float *__restrict__ X, int M, int N, int ld, float *__restrict__ out) {
+// out[n] = sum over m of X[m, n] in a fixed order.  The rows are cut into gridDim.y slices; a CTA sums its slice of 32
+// columns (8 row groups, sequential within a group, groups added in order) into slice_sums[slice][n], and the LAST CTA of a
+// column block to finish adds the slices in slice order -- whichever CTA that is, the order of the additions is the same,
+// so the result is deterministic without a second launch.  (One CTA per 32 columns walking all 10 368 rows of a bias
+// gradient was 115-137 us per call, 30 % of the step.)  `done` counters re-arm themselves.
+constexpr int kRedSlicesMax = 64;
+__global__ void k_colsum(const float *__restrict__ X, int M, int N, int ld, float *__restrict__ out, float *__restrict__ slice_sums,
+                         uint32_t *__restrict__ done) {
     __shared__ float part[8][33];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, c = blockIdx.x * 32 + lane, g = threadIdx.x >> 5;
+    const int slices = (int)gridDim.y, rows_per = (M + slices - 1) / slices;
+    const int m_begin = (int)blockIdx.y * rows_per, m_end = min(M, m_begin + rows_per);
     float s = 0.0f;
     if (c < N)
-        for (int m = g; m < M; m += 8) s += X[(size_t)m * ld + c];
-    part[g][threadIdx.x & 31] = s;
+        for (int m = m_begin + g; m < m_end; m += 8) s += X[(size_t)m * ld + c];
+    part[g][lane] = s;
     __syncthreads();
     if (g == 0 && c < N) {
         float tot = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tot += part[i][threadIdx.x & 31];
+        for (int i = 0; i < 8; ++i) tot += part[i][lane];
+        if (slices == 1) out[c] = tot; else slice_sums[(size_t)blockIdx.y * N + c] = tot;
+    }
+    if (slices == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(done + blockIdx.x, 1u) == (uint32_t)slices - 1u;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (g == 0 && c < N) {
+        float tot = 0.0f;
+        for (int z = 0; z < slices; ++z) tot += __ldcg(slice_sums + (size_t)z * N + c);
         out[c] = tot;
     }
+    if (threadIdx.x == 0) done[blockIdx.x] = 0u;
 }
 
 // depthwise 3x3, SAME zero padding, stride 1, no bias (network-utils lib.rs:204-216) on [n][81][32]; dw is [3][3][32]
@@ -212,13 +252,18 @@ __global__ void k_dw(const float *__restrict__ in, const float *__restrict__ dw,
     out[idx] = acc;
 }
 // weight gradient: ddw[tap][c] = sum over positions b and pixels p of in[b][p + tap][c] * dout[b][p][c]
-// one block per tap (9), 32 channels x 8 position groups; groups added in order
-__global__ void k_dw_wgrad(const float *__restrict__ in, const float *__restrict__ dout, float *__restrict__ ddw, int n) {
+// grid (9 taps, slices of positions); a CTA = 32 channels x 8 position groups over its slice, groups added in order; the last
+// CTA of a tap adds the slices in slice order (see k_colsum; nine CTAs walking the whole minibatch were 250 us per call)
+__global__ void k_dw_wgrad(const float *__restrict__ in, const float *__restrict__ dout, float *__restrict__ ddw, int n,
+                           float *__restrict__ slice_sums, uint32_t *__restrict__ done) {
     __shared__ float part[8][33];
+    __shared__ bool last;
     const int tap = blockIdx.x, ky = tap / 3, kx = tap % 3;
     const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int slices = (int)gridDim.y, per = (n + slices - 1) / slices;
+    const int b_begin = (int)blockIdx.y * per, b_end = min(n, b_begin + per);
     float s = 0.0f;
-    for (int b = g; b < n; b += 8) {
+    for (int b = b_begin + g; b < b_end; b += 8) {
         const float *ip = in + (size_t)b * kCells * kTM, *dp = dout + (size_t)b * kCells * kTM;
         for (int p = 0; p < kCells; ++p) {
             const int y = p / kSide + ky - 1, x = p % kSide + kx - 1;
@@ -232,8 +277,21 @@ __global__ void k_dw_wgrad(const float *__restrict__ in, const float *__restrict
         float tot = 0.0f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) tot += part[i][c];
+        if (slices == 1) ddw[tap * kTM + c] = tot; else slice_sums[((size_t)blockIdx.y * 9 + tap) * kTM + c] = tot;
+    }
+    if (slices == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(done + tap, 1u) == (uint32_t)slices - 1u;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (g == 0) {
+        float tot = 0.0f;
+        for (int z = 0; z < slices; ++z) tot += __ldcg(slice_sums + ((size_t)z * 9 + tap) * kTM + c);
         ddw[tap * kTM + c] = tot;
     }
+    if (threadIdx.x == 0) done[tap] = 0u;
 }
 
 // elementwise: y = x * lrelu'(gate)
@@ -311,16 +369,26 @@ __global__ void k_scale(float *x, long long n, float f) {
     if (i < n) x[i] *= f;
 }
 
-// tensorflow ApplyAdadelta (see the header of this file)
-__global__ void k_adadelta(float *__restrict__ var, float *__restrict__ accum, float *__restrict__ accum_update, const float *__restrict__ g,
-                           long long n, float lr, float rho, float eps) {
+// tensorflow ApplyAdadelta (see the header of this file) on all 31 tensors in one launch: the variables are separate
+// allocations, the gradient and the two slot arrays are flat in checkpoint order (element i of the flat index belongs to
+// the tensor whose [off[k], off[k + 1]) holds it)
+struct AdadeltaTensors {
+    float *var[kNetTensors];
+    long long off[kNetTensors + 1];
+};
+__global__ void k_adadelta(const AdadeltaTensors T, float *__restrict__ accum, float *__restrict__ accum_update, const float *__restrict__ g,
+                           float lr, float rho, float eps) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= T.off[kNetTensors]) return;
+    int k = 0;
+#pragma unroll 1
+    while (i >= T.off[k + 1]) ++k;
+    float *var = T.var[k] + (i - T.off[k]);
     const float gi = g[i];
     const float a = rho * accum[i] + (1.0f - rho) * gi * gi;
     const float upd = sqrtf(accum_update[i] + eps) * (1.0f / sqrtf(a + eps)) * gi;
     accum[i] = a;
-    var[i] -= lr * upd;
+    *var -= lr * upd;
     accum_update[i] = rho * accum_update[i] + (1.0f - rho) * upd * upd;
 }
 
@@ -340,6 +408,8 @@ struct TrainState {
     float *losses = nullptr;               // [3] device
     float *splitk = nullptr;               // split-K partial tiles (grow-only)
     size_t splitk_cap = 0;
+    float *red_sums = nullptr;             // [kRedSlicesMax][512]: slice sums of the column sums / depthwise weight gradients
+    uint32_t *red_done = nullptr;          // [32] arrival counters of those reductions (self re-arming)
     float *grads = nullptr;                // flat [kTParams] in checkpoint order
     float *accum = nullptr, *accum_update = nullptr;  // Adadelta slots, flat
     long long off[kNetTensors + 1] = {};
@@ -394,6 +464,8 @@ static bool train_ensure(omk_ctx *c, TrainState *t, int n) {
             return false;
         cudaMemsetAsync(t->accum, 0, sizeof(float) * kTParams, c->stream);
         cudaMemsetAsync(t->accum_update, 0, sizeof(float) * kTParams, c->stream);
+        if (!talloc(&t->red_sums, (size_t)kRedSlicesMax * kTF) || cudaMalloc(&t->red_done, sizeof(uint32_t) * 32) != cudaSuccess) return false;
+        cudaMemsetAsync(t->red_done, 0, sizeof(uint32_t) * 32, c->stream);
     }
     if (n <= t->cap_n) return true;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
@@ -415,8 +487,9 @@ void train_free(omk_ctx *c) {
     if (t->comm && t->p_comm_destroy) t->p_comm_destroy(t->comm);
     float *all[] = {t->img, t->pi, t->z, t->x[0], t->x[1], t->x[2], t->x[3], t->h0[0], t->h0[1], t->h0[2], t->hd[0], t->hd[1], t->hd[2],
                     t->h1[0], t->h1[1], t->h1[2], t->a0, t->a1, t->logits, t->vlogit, t->dx, t->dy, t->d32a, t->d32b, t->da0, t->da1,
-                    t->dlogits, t->dvlogit, t->row_loss, t->losses, t->grads, t->accum, t->accum_update, t->splitk};
+                    t->dlogits, t->dvlogit, t->row_loss, t->losses, t->grads, t->accum, t->accum_update, t->splitk, t->red_sums};
     for (float *p : all) cudaFree(p);
+    cudaFree(t->red_done);
     if (t->nccl_lib) dlclose(t->nccl_lib);
     delete t;
     c->train_state = nullptr;
@@ -477,8 +550,9 @@ static void train_losses(omk_ctx *c, TrainState *t, int n, bool with_grads) {
     c->launches += 2;
 }
 
-static void colsum(omk_ctx *c, const float *X, int M, int N, float *out) {
-    k_colsum<<<(N + 31) / 32, 256, 0, c->stream>>>(X, M, N, N, out);
+static void colsum(omk_ctx *c, TrainState *t, const float *X, int M, int N, float *out) {
+    const int slices = min(kRedSlicesMax, max(1, M / 256));  // N <= 512: at most 16 column blocks, 16 counters
+    k_colsum<<<dim3((N + 31) / 32, slices), 256, 0, c->stream>>>(X, M, N, N, out, t->red_sums, t->red_done);
     c->launches++;
 }
 
@@ -491,9 +565,9 @@ static void train_backward(omk_ctx *c, TrainState *t, int n) {
     GemmEpi none;
     // heads
     tgemm<true, false>(c, t->a1, t->dlogits, G(T_P_W), kTF, kCells, n, kTF, kCells, kCells, none);   // a1^T . dlogits
-    colsum(c, t->dlogits, n, kCells, G(T_P_B));
+    colsum(c, t, t->dlogits, n, kCells, G(T_P_B));
     tgemm<true, false>(c, t->a1, t->dvlogit, G(T_V_W), kTF, 1, n, kTF, 1, 1, none);
-    colsum(c, t->dvlogit, n, 1, G(T_V_B));
+    colsum(c, t, t->dvlogit, n, 1, G(T_V_B));
     tgemm<false, true>(c, t->dlogits, W[T_P_W], t->da1, n, kTF, kCells, kCells, kCells, kTF, none);  // dlogits . Pw^T
     {   // da1 = (dlogits . Pw^T + dvlogit . Vw^T) * lrelu'(a1): second product accumulates, then the gate
         GemmEpi e;
@@ -504,13 +578,13 @@ static void train_backward(omk_ctx *c, TrainState *t, int n) {
     }
     // fc1
     tgemm<true, false>(c, t->a0, t->da1, G(T_FC1_W), kTF, kTF, n, kTF, kTF, kTF, none);
-    colsum(c, t->da1, n, kTF, G(T_FC1_B));
+    colsum(c, t, t->da1, n, kTF, G(T_FC1_B));
     GemmEpi g0;
     g0.gate = t->a0;
     tgemm<false, true>(c, t->da1, W[T_FC1_W], t->da0, n, kTF, kTF, kTF, kTF, kTF, g0);
     // fc0
     tgemm<true, false>(c, t->x[3], t->da0, G(T_FC0_W), kTFlat, kTF, n, kTFlat, kTF, kTF, none);
-    colsum(c, t->da0, n, kTF, G(T_FC0_B));
+    colsum(c, t, t->da0, n, kTF, G(T_FC0_B));
     tgemm<false, true>(c, t->da0, W[T_FC0_W], t->dx, n, kTFlat, kTF, kTF, kTF, kTFlat, none);  // d(flat) == d(x3) as [M][128]
     c->launches += 10;
     // residual blocks, last to first (network-utils lib.rs:386-461; network.rs:108-111)
@@ -520,17 +594,17 @@ static void train_backward(omk_ctx *c, TrainState *t, int n) {
         const long long tot128 = (long long)M * kTP, tot32 = (long long)M * kTM;
         k_lrelu_bwd<<<(unsigned)((tot128 + 255) / 256), 256, 0, s>>>(t->dx, t->x[r + 1], t->dy, tot128);  // through the block's last lrelu
         tgemm<true, false>(c, t->h1[r], t->dy, G(gb + B_W2), kTM, kTP, M, kTM, kTP, kTP, none);
-        colsum(c, t->dy, M, kTP, G(gb + B_B2));
+        colsum(c, t, t->dy, M, kTP, G(gb + B_B2));
         GemmEpi g1;
         g1.gate = t->h1[r];
         tgemm<false, true>(c, t->dy, B[B_W2], t->d32a, M, kTM, kTP, kTP, kTP, kTM, g1);  // d(pointwise pre-activation)
         tgemm<true, false>(c, t->hd[r], t->d32a, G(gb + B_PW), kTM, kTM, M, kTM, kTM, kTM, none);
-        colsum(c, t->d32a, M, kTM, G(gb + B_B1));
+        colsum(c, t, t->d32a, M, kTM, G(gb + B_B1));
         tgemm<false, true>(c, t->d32a, B[B_PW], t->d32b, M, kTM, kTM, kTM, kTM, kTM, none);  // d(depthwise output)
-        k_dw_wgrad<<<9, 256, 0, s>>>(t->h0[r], t->d32b, G(gb + B_DW), n);
+        k_dw_wgrad<<<dim3(9, min(kRedSlicesMax, max(1, n / 8))), 256, 0, s>>>(t->h0[r], t->d32b, G(gb + B_DW), n, t->red_sums, t->red_done + 16);
         k_dw<<<(unsigned)((tot32 + 255) / 256), 256, 0, s>>>(t->d32b, B[B_DW], t->d32a, n, 1, t->h0[r]);  // d(conv0 pre-activation)
         tgemm<true, false>(c, t->x[r], t->d32a, G(gb + B_W0), kTP, kTM, M, kTP, kTM, kTM, none);
-        colsum(c, t->d32a, M, kTM, G(gb + B_B0));
+        colsum(c, t, t->d32a, M, kTM, G(gb + B_B0));
         GemmEpi skip;  // dx_r = dy (the skip connection) + d(conv0 pre-activation) . W0^T
         skip.res = t->dy;
         tgemm<false, true>(c, t->d32a, B[B_W0], t->dx, M, kTP, kTM, kTM, kTM, kTP, skip);
@@ -540,7 +614,7 @@ static void train_backward(omk_ctx *c, TrainState *t, int n) {
     const long long tot128 = (long long)M * kTP;
     k_lrelu_bwd<<<(unsigned)((tot128 + 255) / 256), 256, 0, s>>>(t->dx, t->x[0], t->dy, tot128);
     tgemm<true, false>(c, t->img, t->dy, G(T_CONV_W), 3, kTP, M, 3, kTP, kTP, none);
-    colsum(c, t->dy, M, kTP, G(T_CONV_B));
+    colsum(c, t, t->dy, M, kTP, G(T_CONV_B));
     c->launches += 2;
 }
 
@@ -574,12 +648,11 @@ const char *train_apply_step(omk_ctx *c) {
         k_scale<<<(unsigned)((kTParams + 255) / 256), 256, 0, c->stream>>>(t->grads, kTParams, 1.0f / (float)t->world);
         c->launches++;
     }
-    for (int i = 0; i < kNetTensors; ++i) {
-        const long long len = kTLen[i];
-        k_adadelta<<<(unsigned)((len + 255) / 256), 256, 0, c->stream>>>(c->net.t[i], t->accum + t->off[i], t->accum_update + t->off[i],
-                                                                         t->grads + t->off[i], len, 0.01f, 0.95f, 1e-8f);
-    }
-    c->launches += kNetTensors;
+    AdadeltaTensors T;
+    for (int i = 0; i < kNetTensors; ++i) T.var[i] = c->net.t[i];
+    for (int i = 0; i <= kNetTensors; ++i) T.off[i] = t->off[i];
+    k_adadelta<<<(unsigned)((kTParams + 255) / 256), 256, 0, c->stream>>>(T, t->accum, t->accum_update, t->grads, 0.01f, 0.95f, 1e-8f);
+    c->launches++;
     t->steps++;
     return cudaPeekAtLastError() == cudaSuccess ? nullptr : cudaGetErrorString(cudaGetLastError());
 }
