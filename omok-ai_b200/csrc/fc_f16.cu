@@ -421,11 +421,23 @@ __global__ void k_fc0_reduce(const float *__restrict__ partial, int nchunks, int
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-    for (int z = 0; z < nchunks; ++z) {
-        const float *p = partial + ((size_t)z * ws_rows + row) * F_N + j;
-        const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
-        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    // six chunks' loads in flight at a time, added in chunk order (one chunk at a time was a chain of 18 / 54 exposed L2
+    // latencies: 8.5 us for a batch of 8 rows)
+    for (int z0 = 0; z0 < nchunks; z0 += 6) {
+        float4 a[6], b[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int z = min(z0 + i, nchunks - 1);
+            const float *p = partial + ((size_t)z * ws_rows + row) * F_N + j;
+            a[i] = *reinterpret_cast<const float4 *>(p);
+            b[i] = *reinterpret_cast<const float4 *>(p + 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (z0 + i >= nchunks) break;
+            acc[0] += a[i].x; acc[1] += a[i].y; acc[2] += a[i].z; acc[3] += a[i].w;
+            acc[4] += b[i].x; acc[5] += b[i].y; acc[6] += b[i].z; acc[7] += b[i].w;
+        }
     }
     const float inv_scale = *inv_scale_p;
     float o[8];
@@ -668,12 +680,25 @@ bool launch_fc0_f16(omk_ctx *c, int rows_bound) {
             am->splitk_rows = ws_rows;
             am->splitk_chunks = kChunks;
         }
-        using Cfg = FcCfg<false, 256>;
-        auto sk = fine ? k_fc16<F_K0, F_CHUNK0_FINE, false, 256, false, true> : k_fc16<F_K0, F_CHUNK0, false, 256, false, true>;
-        cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-        sk<<<dim3(F_N / F_BN, mt, F_K0 / F_BK / F_SPLITK_KB), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
-            am->map0_a_hi, am->map0_a_lo, s->map0s_b_hi, s->map0s_b_lo, c->net.t[24], c->net.fc_inv_scale, am->splitk_partial, nullptr,
-            nullptr, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr, FcBal{});
+        static const int narrow_env = getenv("OMK_FC0_SPLITK_NARROW") ? atoi(getenv("OMK_FC0_SPLITK_NARROW")) : -1;
+        if (mt <= (narrow_env >= 0 ? narrow_env : 2)) {
+            // one or two row tiles (a single game's rounds of 8, Agent::new): 128-column tiles double the CTAs (72 per row tile
+            // instead of 36 on 148 SMs) and halve each CTA's MMA time and weight bytes.  An output element's sum does not
+            // depend on the width of the tile it is computed in: same products, same chunks, same order (test_batch_invariance).
+            using Cfg = FcCfg<false, 128>;
+            auto sk = fine ? k_fc16<F_K0, F_CHUNK0_FINE, false, 128, false, true> : k_fc16<F_K0, F_CHUNK0, false, 128, false, true>;
+            cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+            sk<<<dim3(F_N / 128, mt, F_K0 / F_BK / F_SPLITK_KB), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+                am->map0_a_hi, am->map0_a_lo, s->map0_b_hi, s->map0_b_lo, c->net.t[24], c->net.fc_inv_scale, am->splitk_partial, nullptr,
+                nullptr, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr, FcBal{});
+        } else {
+            using Cfg = FcCfg<false, 256>;
+            auto sk = fine ? k_fc16<F_K0, F_CHUNK0_FINE, false, 256, false, true> : k_fc16<F_K0, F_CHUNK0, false, 256, false, true>;
+            cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+            sk<<<dim3(F_N / F_BN, mt, F_K0 / F_BK / F_SPLITK_KB), Cfg::kThreads, Cfg::kSmemBytes, c->stream>>>(
+                am->map0_a_hi, am->map0_a_lo, s->map0s_b_hi, s->map0s_b_lo, c->net.t[24], c->net.fc_inv_scale, am->splitk_partial, nullptr,
+                nullptr, c->ws.n_req, rows_bound, nullptr, nullptr, nullptr, FcBal{});
+        }
         k_fc0_reduce<<<(rows_bound * 64 + 255) / 256, 256, 0, c->stream>>>(am->splitk_partial, kChunks, ws_rows, c->net.t[24],
                                                                             c->net.fc_inv_scale, c->ws.act1_h16, c->ws.act1_l16,
                                                                             c->ws.n_req, rows_bound);
