@@ -81,7 +81,7 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 
 template <bool PAIR, int BN>
 struct FcCfg {
-    static constexpr int kStages = PAIR ? 3 : 2;
+    static constexpr int kStages = PAIR ? 3 : 2;  // (a third 64 KB stage for the 128-column tiles -- heads, narrow split-K fc0 -- measured +-0: same-box A/B)  // 64 KB stages: three fit (heads, the narrow split-K fc0); 96 KB stages: two
     static constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows loaded by one CTA
     static constexpr int kBBytes = kBRows * F_BK * 2;             // 16 / 32 KB
     static constexpr int kStageBytes = 2 * F_A_BYTES + 2 * kBBytes;  // 64 / 96 KB

@@ -189,10 +189,12 @@ def test_two_rank_nccl_step_equals_the_full_batch_step(omk, no):
         c.close()
 
 
-@pytest.mark.parametrize("n", [1, 3, 130])
+@pytest.mark.parametrize("n", [1, 3, 17, 67, 130])
 def test_ragged_minibatch_sizes(omk, no, n):
-    """Tile edges of the training GEMMs (64 x 64 x 16 tiles, K slices): minibatches of 1, 3 and 130 positions give gradients
-    within the same bars as the 24-position case, and a step returns finite losses."""
+    """Tile edges of the training GEMMs (64 x 64 x 16 tiles, K slices) and ragged last slices of the sliced reductions (17
+    positions: two position slices of the depthwise weight gradient, 9 + 8; 67: 21 row slices of the bias gradients, the last
+    one short): minibatches of 1 ... 130 positions give gradients within the same bars as the 24-position case, and a step
+    returns finite losses."""
     ctx = omk.Context(device=0, capacity_envs=4, capacity_trees=4, capacity_nodes=64, seed=0)
     params = params_with_biases(no, 7)
     ctx.net_load_params(params)
@@ -209,6 +211,25 @@ def test_ragged_minibatch_sizes(omk, no, n):
         assert float(np.abs(g.astype(np.float64) - w).max()) <= bar * scale, name
     losses = ctx.train_apply()
     assert all(np.isfinite(losses)) and abs(losses[0] + losses[1] - losses[2]) <= 1e-5 * abs(losses[2])
+    ctx.close()
+
+
+def test_gradient_is_deterministic_across_calls(omk, no):
+    """The sliced reductions (bias gradients, depthwise weight gradients: the last CTA to finish adds the slice sums in slice
+    order; arrival counters re-arm themselves) and the K-sliced GEMMs use no floating-point atomics: the same minibatch on the
+    same weights gives the same gradient bits, call after call and across minibatch sizes that change the slice counts in
+    between."""
+    ctx = omk.Context(device=0, capacity_envs=4, capacity_trees=4, capacity_nodes=64, seed=0)
+    ctx.net_load_params(params_with_biases(no, 11))
+    images, pi, z = make_batch(no, 96, 5)
+    ctx.train_backward(images, pi, z)
+    first = [g.copy() for g in ctx.train_get_grads()]
+    for other in (40, 96, 9):
+        oi, op, oz = make_batch(no, other, 6 + other)
+        ctx.train_backward(oi, op, oz)  # another slice count in between
+        ctx.train_backward(images, pi, z)
+        for (name, _), a, b in zip(no.PARAM_SPECS, first, ctx.train_get_grads()):
+            assert a.tobytes() == b.tobytes(), name
     ctx.close()
 
 
