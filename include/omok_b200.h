@@ -110,13 +110,14 @@ OMK_API int32_t omk_net_eval_images(omk_ctx *ctx, const float *images, int32_t n
  * accumulators live in the context and, as in the reference, are never saved), one minimize step, then a SECOND forward
  * that reports the losses.  images[n*243] = encode_nn_input's tensor, pi[n*81] = encode_nn_targets' policy target,
  * z[n] = its value target (alpha-zero/src/encoder.rs:10-68); out_losses[3] = {p_loss, v_loss, loss} after the update.
- * The updated weights are live for omk_net_eval / the searches when the call returns (a running self-play driver's
- * cached root prior is refreshed too).  fp32 CUDA kernels; correctness path, not the self-play hot path.             */
+ * The updated weights serve every later evaluation (omk_net_eval, the searches, the self-play driver and its cached
+ * root prior): the tensor-core operand images are rebuilt by the first entry point that evaluates the network after
+ * the step, not by each of an iteration's 600 steps.  fp32 CUDA kernels; correctness path, not the self-play hot path. */
 OMK_API int32_t omk_train_step(omk_ctx *ctx, const float *images, const float *pi, const float *z, int32_t n, float *out_losses);
 /* The same step in two halves, for callers that average the gradient themselves (data parallelism, BASELINE config 5):
  * omk_train_backward leaves the gradient of the local minibatch's mean loss in one flat DEVICE buffer (*out_count =
  * 5 643 250 floats, the 31 tensors in checkpoint order) and returns with the stream idle; omk_train_apply runs the
- * all-reduce of an attached communicator (below), Adadelta, the weight re-pack and the reporting forward.             */
+ * all-reduce of an attached communicator (below), Adadelta and the reporting forward.                                 */
 OMK_API int32_t omk_train_backward(omk_ctx *ctx, const float *images, const float *pi, const float *z, int32_t n,
                            void **out_grads_device, int64_t *out_count);
 OMK_API int32_t omk_train_apply(omk_ctx *ctx, float *out_losses);

@@ -258,11 +258,22 @@ static bool run_evaluator(omk_ctx *c, int evaluator, int rows_bound) {
             return fail(OMK_ERR_CUDA, "the evaluator failed to launch (see stderr); no result was applied to the trees"); \
     } while (0)
 
+static int32_t weights_changed(omk_ctx *c);
+// The trainer's 600 updates per iteration do not evaluate the network in between (the step's own forward passes read the fp32
+// weights), so omk_train_apply only marks the tensor-core operand images stale; they are rebuilt here, on the main stream and
+// before any search lane forks, by every entry point that is about to evaluate the network.
+static int32_t ensure_packed(omk_ctx *c) {
+    if (!c->net_pack_dirty) return OMK_OK;
+    c->net_pack_dirty = false;
+    return weights_changed(c);
+}
+
 static int32_t check_evaluator(omk_ctx *c, int evaluator) {
     if (evaluator != OMK_EVAL_NET && evaluator != OMK_EVAL_HASH) return fail(OMK_ERR_INVALID, "unknown evaluator");
     if (evaluator == OMK_EVAL_HASH && c->virtual_loss)
         return fail(OMK_ERR_STATE, "virtual loss is a non-reference search mode: it is refused with the parity evaluator (OMK_EVAL_HASH)");
     if (evaluator == OMK_EVAL_NET && !c->net.loaded) return fail(OMK_ERR_STATE, "network weights not loaded");
+    if (evaluator == OMK_EVAL_NET) return ensure_packed(c);
     return OMK_OK;
 }
 
@@ -402,6 +413,7 @@ extern "C" int32_t omk_net_load_params(omk_ctx *c, const float *const *tensors, 
             return fail(OMK_ERR_INVALID, "tensor " + std::to_string(i) + ": expected " + std::to_string(kLens[i]) + " elements");
     for (int i = 0; i < kNetTensors; ++i)
         CK(copy_h2d(c, c->net.t[i], tensors[i], sizeof(float) * (size_t)kLens[i], c->stream));
+    c->net_pack_dirty = false;  // rebuilt right here
     net_pack_heads(c);
     if (!fc16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split fc weight preparation failed");
     if (!tower16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split tower weight preparation failed");
@@ -422,6 +434,7 @@ extern "C" int32_t omk_net_get_params(omk_ctx *c, float *const *tensors, const i
 extern "C" int32_t omk_net_init_random(omk_ctx *c, uint64_t seed) {
     CK(cudaSetDevice(c->device));
     launch_net_init_random(c, seed);
+    c->net_pack_dirty = false;  // rebuilt right here
     net_pack_heads(c);
     if (!fc16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split fc weight preparation failed");
     if (!tower16_prepare_weights(c)) return fail(OMK_ERR_CUDA, "fp16-split tower weight preparation failed");
@@ -432,6 +445,8 @@ extern "C" int32_t omk_net_init_random(omk_ctx *c, uint64_t seed) {
 }
 
 static int32_t net_eval_common(omk_ctx *c, int n, const float *images_dev, float *out_p, float *out_v) {
+    int32_t rc_p = ensure_packed(c);
+    if (rc_p) return rc_p;
     if (!net_forward(c, images_dev, n)) return fail(OMK_ERR_CUDA, "the network forward failed to launch (see stderr)");
     // P rows are padded to 96 floats on the device; compact on the way out
     CK(cudaMemcpy2DAsync(out_p, sizeof(float) * kCells, c->ws.P, sizeof(float) * kRow, sizeof(float) * kCells, (size_t)n,
@@ -486,28 +501,34 @@ static int32_t weights_changed(omk_ctx *c) {
     return sp_refresh_root_policy(c);
 }
 
-extern "C" int32_t omk_train_backward(omk_ctx *c, const float *images, const float *pi, const float *z, int32_t n,
-                                      void **out_grads_device, int64_t *out_count) {
+static int32_t train_backward_impl(omk_ctx *c, const float *images, const float *pi, const float *z, int32_t n,
+                                   void **out_grads_device, int64_t *out_count, bool sync) {
     CK(cudaSetDevice(c->device));
     if (!c->net.loaded) return fail(OMK_ERR_STATE, "network weights not loaded");
     if (n < 1 || !images || !pi || !z) return fail(OMK_ERR_INVALID, "bad arguments");
     float *g = nullptr;
     c->train_n = 0;
     if (const char *e = train_backward_step(c, images, pi, z, n, &g)) return fail(OMK_ERR_CUDA, std::string("omk_train_backward: ") + e);
-    CK(cudaStreamSynchronize(c->stream));  // the caller may all-reduce the gradient buffer on its own stream
-    CK(cudaGetLastError());
+    if (sync) {  // the caller may all-reduce the gradient buffer on its own stream (the fused step stays on this one)
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+    }
     c->train_n = n;
     if (out_grads_device) *out_grads_device = g;
     if (out_count) *out_count = 5643250;
     return OMK_OK;
 }
 
+extern "C" int32_t omk_train_backward(omk_ctx *c, const float *images, const float *pi, const float *z, int32_t n,
+                                      void **out_grads_device, int64_t *out_count) {
+    return train_backward_impl(c, images, pi, z, n, out_grads_device, out_count, true);
+}
+
 extern "C" int32_t omk_train_apply(omk_ctx *c, float *out_losses) {
     CK(cudaSetDevice(c->device));
     if (c->train_n < 1) return fail(OMK_ERR_STATE, "omk_train_backward has not produced a gradient");
     if (const char *e = train_apply_step(c)) return fail(OMK_ERR_CUDA, std::string("omk_train_apply: ") + e);
-    int32_t rc = weights_changed(c);
-    if (rc) return rc;
+    c->net_pack_dirty = true;  // the operand images of the tensor-core path follow before the next evaluation (ensure_packed)
     float l[3] = {0, 0, 0};
     if (const char *e = train_report_losses(c, c->train_n, l)) return fail(OMK_ERR_CUDA, std::string("omk_train_apply: ") + e);
     c->train_n = 0;  // one gradient, one update
@@ -517,7 +538,7 @@ extern "C" int32_t omk_train_apply(omk_ctx *c, float *out_losses) {
 }
 
 extern "C" int32_t omk_train_step(omk_ctx *c, const float *images, const float *pi, const float *z, int32_t n, float *out_losses) {
-    int32_t rc = omk_train_backward(c, images, pi, z, n, nullptr, nullptr);
+    int32_t rc = train_backward_impl(c, images, pi, z, n, nullptr, nullptr, false);
     if (rc) return rc;
     return omk_train_apply(c, out_losses);
 }
@@ -1075,6 +1096,10 @@ extern "C" int32_t omk_selfplay_run(omk_ctx *c, int32_t plies, int32_t profile, 
     CK(cudaSetDevice(c->device));
     if (!c->sp_active) return fail(OMK_ERR_STATE, "omk_selfplay_begin has not been called");
     if (plies < 0) return fail(OMK_ERR_INVALID, "plies < 0");
+    if (c->sp_cfg.evaluator == OMK_EVAL_NET) {  // weights updated by the trainer since the last evaluation: operand images + the cached root prior
+        int32_t rc_p = ensure_packed(c);
+        if (rc_p) return rc_p;
+    }
     const omk_selfplay_config &cfg = c->sp_cfg;
     const int n = cfg.n_games;
     const int rounds = (cfg.count + cfg.batch_size - 1) / cfg.batch_size;

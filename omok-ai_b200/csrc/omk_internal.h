@@ -109,6 +109,8 @@ struct omk_ctx {
     void *tower16_params_host = nullptr;  // host copy of the tower's fp32 parameter image (kernel argument of k_tower16)
     void *train_state = nullptr;    // trainer step workspace, Adadelta slots, optional NCCL communicator (train_kernels.cu)
     int train_n = 0;                // positions of the minibatch currently on the device (omk_train_backward)
+    bool net_pack_dirty = false;    // omk_train_apply changed the fp32 weights: the tensor-core operand images (and a running self-play
+                                    // driver's cached root prior) are rebuilt before the next network evaluation (ensure_packed in omk_api.cu)
     int tower_mode = 1;             // tower: 1 = tcgen05 3xFP16 k_tower16 (the product path), 0 = fp32 CUDA-core k_tower (A/B check only)
 
     // self-play driver state

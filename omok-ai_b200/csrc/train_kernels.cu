@@ -41,7 +41,7 @@ constexpr long long kTParams = 5643250;
 // ---------------------------------------------------------------------------------------------------------------
 // C[M,N] = epilogue( op(A) . op(B) ), fp32, 64x64x16 tiles, 256 threads, 4x4 outputs per thread.
 //   TA: A is stored [K,M] (row-major) and read transposed; TB: B is stored [N,K].
-//   epilogue: (+ bias[n]) (+ res[m,n]) (lrelu if act) (* lrelu'(gate[m,n]) if gate) (+ C if accumulate)
+//   epilogue: (+ bias[n]) (+ res[m,n]) (lrelu if act) (+ C if accumulate) (* lrelu'(gate[m,n]) if gate)
 // K is walked in order by one CTA per output tile: the summation order of an output element is fixed.
 // ---------------------------------------------------------------------------------------------------------------
 struct GemmEpi {
@@ -50,6 +50,9 @@ struct GemmEpi {
     const float *gate = nullptr;  // [M,N], leading dimension ldc: multiply by (gate > 0 ? 1 : 0.2)
     int act = 0;                  // lrelu on the result
     int accumulate = 0;           // C += result
+    float *colsum = nullptr;      // [N]: also the column sums of op(B) over K (a weight-gradient product X^T . dY carries the
+                                  // bias gradient sum_rows dY with it: the CTAs of the first output row tile add up the B slices
+                                  // they stage anyway; K slices are added in slice order by k_tgemm_reduce)
 };
 
 // Split-K (gridDim.z > 1, products with K in the thousands and few output tiles: the weight gradients of the 1x1
@@ -69,6 +72,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
     const int k_begin = (int)blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+    const bool want_cs = e.colsum != nullptr && blockIdx.y == 0 && ty == 0;  // 16 threads x 4 columns of this n tile
+    float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     // The next k-step's 64 x 16 slice of op(A) and 16 x 64 slice of op(B) are fetched into registers while this one is
     // multiplied (a CTA with a long K and few neighbours is otherwise a chain of exposed global-load latencies: 2.4 us per
     // k-step measured); out-of-range elements are zeros.  The summation order is unchanged.
@@ -99,6 +104,12 @@ __global__ void __launch_bounds__(256)
         }
         __syncthreads();
         if (k0 + 16 < k_end) fetch(k0 + 16);
+        if (want_cs) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cs[j] += Bs[k][tx * 4 + j];
+        }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             float a[4], b[4];
@@ -112,6 +123,15 @@ __global__ void __launch_bounds__(256)
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
+    }
+    if (want_cs) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            if (part) part[(size_t)gridDim.z * M * N + (size_t)blockIdx.z * N + n] = cs[j];  // slice sums behind the partial tiles
+            else e.colsum[n] = cs[j];
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -130,8 +150,8 @@ __global__ void __launch_bounds__(256)
             if (e.bias) v += e.bias[n];
             if (e.res) v += e.res[o];
             if (e.act) v = v > 0.0f ? v : kTLrelu * v;
-            if (e.gate) v *= e.gate[o] > 0.0f ? 1.0f : kTLrelu;
             if (e.accumulate) v += C[o];
+            if (e.gate) v *= e.gate[o] > 0.0f ? 1.0f : kTLrelu;
             C[o] = v;
         }
     }
@@ -140,6 +160,12 @@ __global__ void __launch_bounds__(256)
 __global__ void k_tgemm_reduce(const float *__restrict__ part, int splits, int M, int N, float *__restrict__ C, int ldc, GemmEpi e) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)M * N) return;
+    if (e.colsum && idx < N) {  // the K slices' column sums of op(B), in slice order
+        const float *pc = part + (size_t)splits * M * N + idx;
+        float cs = 0.0f;
+        for (int z = 0; z < splits; ++z) cs += pc[(size_t)z * N];
+        e.colsum[idx] = cs;
+    }
     const int m = (int)(idx / N), n = (int)(idx % N);
     float v = 0.0f;
     int z = 0;
@@ -153,8 +179,8 @@ __global__ void k_tgemm_reduce(const float *__restrict__ part, int splits, int M
     if (e.bias) v += e.bias[n];
     if (e.res) v += e.res[o];
     if (e.act) v = v > 0.0f ? v : kTLrelu * v;
-    if (e.gate) v *= e.gate[o] > 0.0f ? 1.0f : kTLrelu;
     if (e.accumulate) v += C[o];
+    if (e.gate) v *= e.gate[o] > 0.0f ? 1.0f : kTLrelu;
     C[o] = v;
 }
 
@@ -173,7 +199,7 @@ static void tgemm(omk_ctx *c, const float *A, const float *B, float *C, int M, i
         int splits = min(64, max(2, 1184 / tiles));
         int kps = max(32, ((K + splits - 1) / splits + 15) / 16 * 16);
         splits = (K + kps - 1) / kps;
-        float *part = splits >= 2 ? g_splitk_scratch(c, (size_t)splits * M * N) : nullptr;
+        float *part = splits >= 2 ? g_splitk_scratch(c, (size_t)splits * M * N + (size_t)splits * N) : nullptr;
         if (part) {
             grid.z = splits;
             k_tgemm<TA, TB><<<grid, 256, 0, s>>>(A, B, C, M, N, K, lda, ldb, ldc, e, kps, part);
@@ -186,44 +212,7 @@ static void tgemm(omk_ctx *c, const float *A, const float *B, float *C, int M, i
     k_tgemm<TA, TB><<<grid, 256, 0, s>>>(A, B, C, M, N, K, lda, ldb, ldc, e, K, nullptr);
 }
 
-// out[n] = sum over m of X[m, n] in a fixed order.  The rows are cut into gridDim.y slices; a CTA sums its slice of 32
-// columns (8 row groups, sequential within a group, groups added in order) into slice_sums[slice][n], and the LAST CTA of a
-// column block to finish adds the slices in slice order -- whichever CTA that is, the order of the additions is the same,
-// so the result is deterministic without a second launch.  (One CTA per 32 columns walking all 10 368 rows of a bias
-// gradient was 115-137 us per call, 30 % of the step.)  `done` counters re-arm themselves.
 constexpr int kRedSlicesMax = 64;
-__global__ void k_colsum(const float *__restrict__ X, int M, int N, int ld, float *__restrict__ out, float *__restrict__ slice_sums,
-                         uint32_t *__restrict__ done) {
-    __shared__ float part[8][33];
-    __shared__ bool last;
-    const int lane = threadIdx.x & 31, c = blockIdx.x * 32 + lane, g = threadIdx.x >> 5;
-    const int slices = (int)gridDim.y, rows_per = (M + slices - 1) / slices;
-    const int m_begin = (int)blockIdx.y * rows_per, m_end = min(M, m_begin + rows_per);
-    float s = 0.0f;
-    if (c < N)
-        for (int m = m_begin + g; m < m_end; m += 8) s += X[(size_t)m * ld + c];
-    part[g][lane] = s;
-    __syncthreads();
-    if (g == 0 && c < N) {
-        float tot = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tot += part[i][lane];
-        if (slices == 1) out[c] = tot; else slice_sums[(size_t)blockIdx.y * N + c] = tot;
-    }
-    if (slices == 1) return;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(done + blockIdx.x, 1u) == (uint32_t)slices - 1u;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    if (g == 0 && c < N) {
-        float tot = 0.0f;
-        for (int z = 0; z < slices; ++z) tot += __ldcg(slice_sums + (size_t)z * N + c);
-        out[c] = tot;
-    }
-    if (threadIdx.x == 0) done[blockIdx.x] = 0u;
-}
 
 // depthwise 3x3, SAME zero padding, stride 1, no bias (network-utils lib.rs:204-216) on [n][81][32]; dw is [3][3][32]
 // forward: out[p][c] = sum_tap in[p + tap][c] * dw[tap][c]
@@ -252,8 +241,10 @@ __global__ void k_dw(const float *__restrict__ in, const float *__restrict__ dw,
     out[idx] = acc;
 }
 // weight gradient: ddw[tap][c] = sum over positions b and pixels p of in[b][p + tap][c] * dout[b][p][c]
-// grid (9 taps, slices of positions); a CTA = 32 channels x 8 position groups over its slice, groups added in order; the last
-// CTA of a tap adds the slices in slice order (see k_colsum; nine CTAs walking the whole minibatch were 250 us per call)
+// grid (9 taps, slices of positions); a CTA = 32 channels x 8 position groups over its slice, groups added in order, and stores
+// its slice sum; the LAST CTA of a tap to finish adds the slices in slice order -- whichever CTA that is, the order of the
+// additions is the same, so the result is deterministic without a second launch (nine CTAs walking the whole minibatch were
+// 250 us per call).  The `done` counters re-arm themselves.
 __global__ void k_dw_wgrad(const float *__restrict__ in, const float *__restrict__ dout, float *__restrict__ ddw, int n,
                            float *__restrict__ slice_sums, uint32_t *__restrict__ done) {
     __shared__ float part[8][33];
@@ -292,12 +283,6 @@ __global__ void k_dw_wgrad(const float *__restrict__ in, const float *__restrict
         ddw[tap * kTM + c] = tot;
     }
     if (threadIdx.x == 0) done[tap] = 0u;
-}
-
-// elementwise: y = x * lrelu'(gate)
-__global__ void k_lrelu_bwd(const float *__restrict__ x, const float *__restrict__ gate, float *__restrict__ y, long long n) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = x[i] * (gate[i] > 0.0f ? 1.0f : kTLrelu);
 }
 
 // per position: softmax cross entropy with the visit policy, squared value error, and their logit gradients for the
@@ -408,8 +393,8 @@ struct TrainState {
     float *losses = nullptr;               // [3] device
     float *splitk = nullptr;               // split-K partial tiles (grow-only)
     size_t splitk_cap = 0;
-    float *red_sums = nullptr;             // [kRedSlicesMax][512]: slice sums of the column sums / depthwise weight gradients
-    uint32_t *red_done = nullptr;          // [32] arrival counters of those reductions (self re-arming)
+    float *red_sums = nullptr;             // [kRedSlicesMax][9][32] slice sums of the depthwise weight gradients
+    uint32_t *red_done = nullptr;          // [32] arrival counters of that reduction (self re-arming)
     float *grads = nullptr;                // flat [kTParams] in checkpoint order
     float *accum = nullptr, *accum_update = nullptr;  // Adadelta slots, flat
     long long off[kNetTensors + 1] = {};
@@ -550,12 +535,6 @@ static void train_losses(omk_ctx *c, TrainState *t, int n, bool with_grads) {
     c->launches += 2;
 }
 
-static void colsum(omk_ctx *c, TrainState *t, const float *X, int M, int N, float *out) {
-    const int slices = min(kRedSlicesMax, max(1, M / 256));  // N <= 512: at most 16 column blocks, 16 counters
-    k_colsum<<<dim3((N + 31) / 32, slices), 256, 0, c->stream>>>(X, M, N, N, out, t->red_sums, t->red_done);
-    c->launches++;
-}
-
 // gradients of the mean loss with respect to all 31 tensors, into t->grads (checkpoint order)
 static void train_backward(omk_ctx *c, TrainState *t, int n) {
     cudaStream_t s = c->stream;
@@ -563,59 +542,56 @@ static void train_backward(omk_ctx *c, TrainState *t, int n) {
     const int M = n * kCells;
     auto G = [&](int tensor) { return t->grads + t->off[tensor]; };
     GemmEpi none;
+    auto with_colsum = [](float *bias_grad) { GemmEpi e; e.colsum = bias_grad; return e; };  // weight gradient + its bias gradient
     // heads
-    tgemm<true, false>(c, t->a1, t->dlogits, G(T_P_W), kTF, kCells, n, kTF, kCells, kCells, none);   // a1^T . dlogits
-    colsum(c, t, t->dlogits, n, kCells, G(T_P_B));
-    tgemm<true, false>(c, t->a1, t->dvlogit, G(T_V_W), kTF, 1, n, kTF, 1, 1, none);
-    colsum(c, t, t->dvlogit, n, 1, G(T_V_B));
+    tgemm<true, false>(c, t->a1, t->dlogits, G(T_P_W), kTF, kCells, n, kTF, kCells, kCells, with_colsum(G(T_P_B)));   // a1^T . dlogits
+    tgemm<true, false>(c, t->a1, t->dvlogit, G(T_V_W), kTF, 1, n, kTF, 1, 1, with_colsum(G(T_V_B)));
     tgemm<false, true>(c, t->dlogits, W[T_P_W], t->da1, n, kTF, kCells, kCells, kCells, kTF, none);  // dlogits . Pw^T
-    {   // da1 = (dlogits . Pw^T + dvlogit . Vw^T) * lrelu'(a1): second product accumulates, then the gate
+    {   // da1 = (dlogits . Pw^T + dvlogit . Vw^T) * lrelu'(a1): the second product accumulates and applies the gate
         GemmEpi e;
         e.accumulate = 1;
+        e.gate = t->a1;
         tgemm<false, true>(c, t->dvlogit, W[T_V_W], t->da1, n, kTF, 1, 1, 1, kTF, e);
-        const long long tot = (long long)n * kTF;
-        k_lrelu_bwd<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(t->da1, t->a1, t->da1, tot);
     }
     // fc1
-    tgemm<true, false>(c, t->a0, t->da1, G(T_FC1_W), kTF, kTF, n, kTF, kTF, kTF, none);
-    colsum(c, t, t->da1, n, kTF, G(T_FC1_B));
+    tgemm<true, false>(c, t->a0, t->da1, G(T_FC1_W), kTF, kTF, n, kTF, kTF, kTF, with_colsum(G(T_FC1_B)));
     GemmEpi g0;
     g0.gate = t->a0;
     tgemm<false, true>(c, t->da1, W[T_FC1_W], t->da0, n, kTF, kTF, kTF, kTF, kTF, g0);
     // fc0
-    tgemm<true, false>(c, t->x[3], t->da0, G(T_FC0_W), kTFlat, kTF, n, kTFlat, kTF, kTF, none);
-    colsum(c, t, t->da0, n, kTF, G(T_FC0_B));
-    tgemm<false, true>(c, t->da0, W[T_FC0_W], t->dx, n, kTFlat, kTF, kTF, kTF, kTFlat, none);  // d(flat) == d(x3) as [M][128]
-    c->launches += 10;
+    tgemm<true, false>(c, t->x[3], t->da0, G(T_FC0_W), kTFlat, kTF, n, kTFlat, kTF, kTF, with_colsum(G(T_FC0_B)));
+    // d(flat) == d(x3) as [M][128]; every gradient of the residual stream is needed only THROUGH the lrelu that produced the
+    // stream (network.rs:108-111), so the producing GEMM applies that gate in its epilogue instead of a separate pass
+    float *dy = t->dy, *dx = t->dx;
+    GemmEpi gx3;
+    gx3.gate = t->x[3];
+    tgemm<false, true>(c, t->da0, W[T_FC0_W], dy, n, kTFlat, kTF, kTF, kTF, kTFlat, gx3);
+    c->launches += 9;
     // residual blocks, last to first (network-utils lib.rs:386-461; network.rs:108-111)
     for (int r = 2; r >= 0; --r) {
         float *const *B = W + T_BLK0 + 7 * r;
         const int gb = T_BLK0 + 7 * r;
-        const long long tot128 = (long long)M * kTP, tot32 = (long long)M * kTM;
-        k_lrelu_bwd<<<(unsigned)((tot128 + 255) / 256), 256, 0, s>>>(t->dx, t->x[r + 1], t->dy, tot128);  // through the block's last lrelu
-        tgemm<true, false>(c, t->h1[r], t->dy, G(gb + B_W2), kTM, kTP, M, kTM, kTP, kTP, none);
-        colsum(c, t, t->dy, M, kTP, G(gb + B_B2));
+        const long long tot32 = (long long)M * kTM;
+        // (dy = the gradient through the block's last lrelu, written by the GEMM before this block)
+        tgemm<true, false>(c, t->h1[r], dy, G(gb + B_W2), kTM, kTP, M, kTM, kTP, kTP, with_colsum(G(gb + B_B2)));
         GemmEpi g1;
         g1.gate = t->h1[r];
-        tgemm<false, true>(c, t->dy, B[B_W2], t->d32a, M, kTM, kTP, kTP, kTP, kTM, g1);  // d(pointwise pre-activation)
-        tgemm<true, false>(c, t->hd[r], t->d32a, G(gb + B_PW), kTM, kTM, M, kTM, kTM, kTM, none);
-        colsum(c, t, t->d32a, M, kTM, G(gb + B_B1));
+        tgemm<false, true>(c, dy, B[B_W2], t->d32a, M, kTM, kTP, kTP, kTP, kTM, g1);  // d(pointwise pre-activation)
+        tgemm<true, false>(c, t->hd[r], t->d32a, G(gb + B_PW), kTM, kTM, M, kTM, kTM, kTM, with_colsum(G(gb + B_B1)));
         tgemm<false, true>(c, t->d32a, B[B_PW], t->d32b, M, kTM, kTM, kTM, kTM, kTM, none);  // d(depthwise output)
-        k_dw_wgrad<<<dim3(9, min(kRedSlicesMax, max(1, n / 8))), 256, 0, s>>>(t->h0[r], t->d32b, G(gb + B_DW), n, t->red_sums, t->red_done + 16);
+        k_dw_wgrad<<<dim3(9, min(kRedSlicesMax, max(1, n / 8))), 256, 0, s>>>(t->h0[r], t->d32b, G(gb + B_DW), n, t->red_sums, t->red_done);
         k_dw<<<(unsigned)((tot32 + 255) / 256), 256, 0, s>>>(t->d32b, B[B_DW], t->d32a, n, 1, t->h0[r]);  // d(conv0 pre-activation)
-        tgemm<true, false>(c, t->x[r], t->d32a, G(gb + B_W0), kTP, kTM, M, kTP, kTM, kTM, none);
-        colsum(c, t, t->d32a, M, kTM, G(gb + B_B0));
-        GemmEpi skip;  // dx_r = dy (the skip connection) + d(conv0 pre-activation) . W0^T
-        skip.res = t->dy;
-        tgemm<false, true>(c, t->d32a, B[B_W0], t->dx, M, kTP, kTM, kTM, kTM, kTP, skip);
-        c->launches += 9;
+        tgemm<true, false>(c, t->x[r], t->d32a, G(gb + B_W0), kTP, kTM, M, kTP, kTM, kTM, with_colsum(G(gb + B_B0)));
+        GemmEpi skip;  // (dy (the skip connection) + d(conv0 pre-activation) . W0^T) * lrelu'(x_r): the next block's (or the stem's) dy
+        skip.res = dy;
+        skip.gate = t->x[r];
+        tgemm<false, true>(c, t->d32a, B[B_W0], dx, M, kTP, kTM, kTM, kTM, kTP, skip);
+        float *tmp = dy; dy = dx; dx = tmp;
+        c->launches += 8;
     }
     // stem
-    const long long tot128 = (long long)M * kTP;
-    k_lrelu_bwd<<<(unsigned)((tot128 + 255) / 256), 256, 0, s>>>(t->dx, t->x[0], t->dy, tot128);
-    tgemm<true, false>(c, t->img, t->dy, G(T_CONV_W), 3, kTP, M, 3, kTP, kTP, none);
-    colsum(c, t, t->dy, M, kTP, G(T_CONV_B));
-    c->launches += 2;
+    tgemm<true, false>(c, t->img, dy, G(T_CONV_W), 3, kTP, M, 3, kTP, kTP, with_colsum(G(T_CONV_B)));
+    c->launches += 1;
 }
 
 static bool train_upload(omk_ctx *c, TrainState *t, const float *images, const float *pi, const float *z, int n) {

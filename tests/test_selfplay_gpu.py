@@ -46,6 +46,26 @@ def test_restarted_games_use_the_current_weights(omk):
             break
     else:
         pytest.fail("no game ended after the second weight change")
+    # the trainer's own entry point: omk_train_step marks the tensor-core operand images stale and the NEXT evaluation --
+    # here the driver itself, with no omk_net_eval in between -- rebuilds them together with the cached prior
+    rng = np.random.default_rng(3)
+    images = (rng.random((32, 243)) < 0.3).astype(np.float32)
+    pi = rng.random((32, 81)).astype(np.float32)
+    pi /= pi.sum(axis=1, keepdims=True)
+    z = rng.choice([-1.0, 1.0], size=32).astype(np.float32)
+    for _ in range(3):
+        ctx.train_step(images, pi, z)
+    for _ in range(200):
+        _, _, _, status, _ = ctx.selfplay_run(1, profile=0, want_transitions=True)
+        done = np.flatnonzero(status[0] > 0)
+        if done.size:
+            pol = ctx.pool_root_stats(2 * int(done[0]))[4]
+            p_trained, _ = ctx.net_eval(*empty)
+            assert not np.array_equal(p_trained, p_rand)
+            assert pol.tobytes() == p_trained[0].tobytes(), "restarted root prior must follow omk_train_step"
+            break
+    else:
+        pytest.fail("no game ended after the training steps")
     ctx.close()
 
 
