@@ -62,8 +62,8 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
     k_tgemm(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C, int M, int N, int K, int lda, int ldb,
             int ldc, GemmEpi e, int k_per_split, float *__restrict__ part) {
-    __shared__ float As[16][64 + 1];
-    __shared__ float Bs[16][64 + 1];
+    __shared__ __align__(16) float As[16][64 + 4];  // rows 16-byte aligned: the 4 x 4 register tile reads its operands as float4
+    __shared__ __align__(16) float Bs[16][64 + 4];
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     float acc[4][4];
@@ -112,11 +112,8 @@ __global__ void __launch_bounds__(256)
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]), b4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
