@@ -13,8 +13,12 @@
 //
 // This is NOT the self-play hot path: an iteration runs 600 steps of 128 positions against ~10^8 network evaluations
 // of self-play, so the kernels here are written for correctness and determinism (fp32 everywhere, fixed summation
-// orders, no atomics), not for the tensor cores: one generic tiled GEMM with transposes and fused epilogues, the
-// depthwise forward / data-gradient / weight-gradient kernels, column sums, the loss, and the optimizer.
+// orders, no floating-point atomics), not for the tensor cores: one generic tiled GEMM with transposes, K slicing and
+// fused epilogues (bias, residual, lrelu, the lrelu' gate of the backward pass, the bias gradient of a weight-gradient
+// product), the depthwise forward / data-gradient / weight-gradient kernels, the loss, and the optimizer.  At the
+// reference's own iteration shape (50 episodes, 600 updates) the step is most of an iteration on the GPU, so its
+// launch count and its low-parallelism reductions were worth fixing: 3.2 -> 1.2 ms per 128 positions
+// (profiles/r02_train_step.md).
 // Data parallelism (BASELINE config 5): the flat gradient (5 643 250 floats, 22.6 MB) is all-reduced over NCCL when a
 // communicator is attached (omk_train_comm_init; libnccl is loaded with dlopen, the library has no link dependency on
 // it) or handed to the caller between omk_train_backward and omk_train_apply.
