@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
     uint32_t cur_n = root_n;
     int depth = 0;
     NodeHdr h{};
-    for (int it = 0; it < batch && !err; ++it) {
-        ++sims;
+    int it = 0;
+    while (it < batch && !err) {
         // ---- select_leaf (node.rs:39-59) with the PUCT selector (:81-90, :277-286) ----
         if (restart) {
             x = 0;
@@ -293,6 +293,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
         __syncwarp();
 
         if (h.status != kInProgress) {  // :92-97 terminal leaf: backup its z, no expansion
+            ++it;
+            ++sims;
             if (lane == 0) {
                 const float z = (h.status == kBlackWin || h.status == kWhiteWin) ? 1.0f : 0.0f;
                 backup_path(tn, path, depth, z, root_n, root_w);
@@ -304,67 +306,116 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
             continue;
         }
 
-        // ---- :99-125 uniformly random unexpanded legal action (ascending candidate list) ----
+        // ---- :99-125 uniformly random unexpanded legal actions (ascending candidate list) ----
         uint32_t cand[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) cand[k] = ~(h.black[k] | h.white[k]) & ~h.cmask[k];
         cand[2] &= 0x1FFFFu;
         const int ncand = popc81(cand);
-        if (ncand == 0) continue;
-        const int action = nth_set81(cand, (int)rng_below(a.seed, stream, rng_counter, (uint32_t)ncand));
-
-        // ---- :127-135 place the stone on a clone of the leaf's environment ----
-        NodeHdr c = h;
-        uint32_t *mine = h.turn == 0 ? c.black : c.white;
-        set81(mine, action);
-        const bool five = makes_five_warp(mine, action, lane);
-        c.legal = h.legal - 1;
-        c.turn = h.turn ^ 1u;
-        c.status = five ? (h.turn == 0 ? kBlackWin : kWhiteWin) : (c.legal == 0 ? kDraw : kInProgress);
-        c.cmask[0] = c.cmask[1] = c.cmask[2] = 0;
-        c.parent = x;
-        c.action = (uint32_t)action;
-        c.has_policy = 0;
-
-        // ---- :158-175 expand: the child's prior is the leaf's policy entry (implicit) ----
-        if (n_nodes >= (uint32_t)a.cap_nodes) {
-            err = 1;
-            break;
+        if (ncand == 0) {  // (unreachable single-threaded, :119-125: the simulation is spent)
+            ++it;
+            ++sims;
+            continue;
         }
-        const uint32_t id = n_nodes++;
-        if (lane == 0) {
-            store_hdr(node_ptr(tn, id), c);
-            uint8_t *xn = node_ptr(tn, x);
-            reinterpret_cast<uint32_t *>(xn)[6 + (action >> 5)] =
-                sel3(h.cmask[0], h.cmask[1], h.cmask[2], action >> 5) | (1u << (action & 31));
-            node_edge_n(xn)[action] = 0u;
-            node_edge_w(xn)[action] = 0.0f;
-            node_child(xn)[action] = (uint16_t)id;
-            if (c.status != kInProgress) {  // :177-181 terminal child: backup the reward now
-                path[depth] = (x << 8) | (uint32_t)action;
-                backup_path(tn, path, depth + 1, five ? 1.0f : 0.0f, root_n, root_w);
-            } else {
-                req[nreq] = (uint16_t)id;  // :182-187 queue for the evaluator
-                if (a.vloss) {
-                    // VIRTUAL LOSS (opt-in; the reference has none, :80-90 reads the statistics as they are): the pending
-                    // evaluation counts as one visit with value -1 on every edge of its path, so the round's next
-                    // simulations spread over other lines.  k_apply replaces it with the real value (n + 0, w + v + 1).
-                    path[depth] = (x << 8) | (uint32_t)action;
-                    for (int d = depth; d >= 0; --d) {
-                        uint8_t *pn = node_ptr(tn, path[d] >> 8);
-                        const int pa = path[d] & 0xFF;
-                        node_edge_n(pn)[pa] += 1u;
-                        node_edge_w(pn)[pa] = __fsub_rn(node_edge_w(pn)[pa], 1.0f);
-                    }
-                    root_n += 1u;
+        // A RUN of expansions at this leaf.  Until a terminal child is backed up nothing the selection reads changes (see
+        // above), so the next simulations of the round come back to this leaf until it is full: their draws are made here
+        // one after the other (register work: the stream position and the shrinking candidate set are the only state that
+        // links them), and then LANE k places the stone of expansion k, tests five-in-a-row on its own registers and stores
+        // child k -- the serial chain of a round is K draws instead of K x (draw, stone, warp-ballot line scan, header
+        // store).  The run is cut behind the first terminal child: its reward is backed up at once (:177-181) and changes
+        // the statistics, so the draws made for the simulations behind it are handed back (the stream position recorded
+        // with expansion k is restored) and the walk restarts at the root -- the same children, ids, stream position and
+        // statistics as one simulation at a time (every oracle test).  Virtual loss changes the path after each expansion:
+        // runs of one.
+        const int K = a.vloss ? 1 : min(min(batch - it, ncand), 32);
+        int my_action = 0;
+        uint32_t my_ctr = rng_counter;
+        {
+            uint32_t cw[3] = {cand[0], cand[1], cand[2]};
+            uint32_t ctr = rng_counter;
+            for (int k = 0; k < K; ++k) {
+                const int act = nth_set81(cw, (int)rng_below(a.seed, stream, ctr, (uint32_t)(ncand - k)));
+                cw[act >> 5] &= ~(1u << (act & 31));  // (act >> 5 is warp-uniform)
+                if (lane == k) {
+                    my_action = act;
+                    my_ctr = ctr;
                 }
             }
         }
-        if (c.status == kInProgress) ++nreq; else restart = true;  // a terminal child was backed up along the path
-        if (a.vloss) restart = true;                                // ... or a virtual loss changed it
-        set81(h.cmask, action);  // the kept copy of the leaf's header follows the one in memory
+        // ---- :127-135 lane k: the stone of expansion k on a clone of the leaf's environment ----
+        NodeHdr c = h;
+        bool five = false;
+        if (lane < K) {
+            uint32_t *mine = h.turn == 0 ? c.black : c.white;
+            set81(mine, my_action);
+            five = makes_five_scalar(mine, my_action);
+            c.legal = h.legal - 1;
+            c.turn = h.turn ^ 1u;
+            c.status = five ? (h.turn == 0 ? kBlackWin : kWhiteWin) : (c.legal == 0 ? kDraw : kInProgress);
+            c.cmask[0] = c.cmask[1] = c.cmask[2] = 0;
+            c.parent = x;
+            c.action = (uint32_t)my_action;
+            c.has_policy = 0;
+        }
+        const uint32_t term_mask = __ballot_sync(kFull, lane < K && c.status != kInProgress);
+        const int t_first = term_mask ? __ffs(term_mask) - 1 : K;  // expansions before the first terminal child
+        int accepted = t_first < K ? t_first + 1 : K;
+        // ---- :158-175 expand: the child's prior is the leaf's policy entry (implicit) ----
+        if (n_nodes + (uint32_t)accepted > (uint32_t)a.cap_nodes) {  // the tree is full: keep what fits, then fail loudly
+            accepted = (int)((uint32_t)a.cap_nodes - n_nodes);
+            err = 1;
+        }
+        const bool term_accepted = t_first < accepted;
+        const uint32_t id = n_nodes + (uint32_t)lane;
+        uint8_t *xn = node_ptr(tn, x);
+        uint32_t add[3] = {0u, 0u, 0u};
+        if (lane < accepted) {
+            store_hdr(node_ptr(tn, id), c);
+            node_edge_n(xn)[my_action] = 0u;
+            node_edge_w(xn)[my_action] = 0.0f;
+            node_child(xn)[my_action] = (uint16_t)id;
+            add[my_action >> 5] = 1u << (my_action & 31);
+            if (lane < t_first) req[nreq + lane] = (uint16_t)id;  // :182-187 queue for the evaluator
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            add[k] = __reduce_or_sync(kFull, add[k]);
+            h.cmask[k] |= add[k];  // the kept copy of the leaf's header follows the one in memory
+        }
+        if (lane < 3 && sel3(add[0], add[1], add[2], lane)) reinterpret_cast<uint32_t *>(xn)[6 + lane] = sel3(h.cmask[0], h.cmask[1], h.cmask[2], lane);
+        if (accepted > 0) rng_counter = __shfl_sync(kFull, my_ctr, accepted - 1);
+        n_nodes += (uint32_t)accepted;
+        nreq += min(t_first, accepted);
+        it += accepted;
+        sims += (uint32_t)accepted;
+        __syncwarp();  // the lanes' stores above are ordered before lane 0's read-modify-writes below (and the next PUCT scan)
+        if (term_accepted) {  // :177-181 terminal child: backup the reward now
+            const int t_action = __shfl_sync(kFull, my_action, t_first);
+            const bool t_five = __shfl_sync(kFull, (int)five, t_first) != 0;
+            if (lane == 0) {
+                path[depth] = (x << 8) | (uint32_t)t_action;
+                backup_path(tn, path, depth + 1, t_five ? 1.0f : 0.0f, root_n, root_w);
+            }
+            restart = true;  // a terminal child was backed up along the path
+        } else if (a.vloss && accepted == 1) {
+            // VIRTUAL LOSS (opt-in; the reference has none, :80-90 reads the statistics as they are): the pending
+            // evaluation counts as one visit with value -1 on every edge of its path, so the round's next
+            // simulations spread over other lines.  k_apply replaces it with the real value (n + 0, w + v + 1).
+            const int v_action = __shfl_sync(kFull, my_action, 0);
+            if (lane == 0) {
+                path[depth] = (x << 8) | (uint32_t)v_action;
+                for (int d = depth; d >= 0; --d) {
+                    uint8_t *pn = node_ptr(tn, path[d] >> 8);
+                    const int pa = path[d] & 0xFF;
+                    node_edge_n(pn)[pa] += 1u;
+                    node_edge_w(pn)[pa] = __fsub_rn(node_edge_w(pn)[pa], 1.0f);
+                }
+                root_n += 1u;
+            }
+            restart = true;  // the virtual loss changed the path's statistics
+        }
 #ifdef OMK_NO_DESCENT_REUSE
-        restart = true;  // A/B build: the first version's behaviour, a full descent per simulation
+        restart = true;  // A/B build: a full descent per run
 #endif
         root_n = __shfl_sync(kFull, root_n, 0);
         root_w = __shfl_sync(kFull, root_w, 0);
