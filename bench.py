@@ -390,7 +390,7 @@ def main():
                      "achieved": tree_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tree_gbs / peaks["hbm_gbs"],
                      "note": "algorithmic 1672 B/simulation; at this pool size the kernels are bound by the latency of one serial "
                              "chain per tree (ncu: 42 % fixed-latency waits), at 65 536 trees by issue slots (78 %) with 5 % DRAM "
-                             "traffic because a round's re-reads of the root rows are L1 hits (DESIGN.md 3, profiles/r02_tree_pool_sweep.json); the PUCT descent is reused inside a round; "
+                             "traffic because a round's re-reads of the root rows are L1 hits (DESIGN.md 3, profiles/r02_tree_pool_sweep.json); the PUCT descent is reused inside a round and the expansions at a leaf run lane-parallel; "
                              "hidden behind the other search lane's fc0 in the timed region",
                      # one k_select_expand + one k_apply launch at 1024 searching trees (ncu capture with the hash evaluator)
                      "traffic": (traffic.get("k_select_expand", 0.0) + traffic.get("k_apply", 0.0)) or None}
