@@ -495,39 +495,50 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_apply(TreeArgs a, int m
     for (int c0 = 0; c0 < cnt; c0 += kChunk) {
         const int m = min(kChunk, cnt - c0);
         const uint32_t row0 = base + (uint32_t)c0;
-        // ---- (A) lane i fetches request i's node id and value ----
-        uint32_t my_id = 0;
+        // ---- (A) lane i fetches request i's node id, value and node header: one round of loads for the chunk's headers
+        //      (the first version broadcast-loaded one header per request inside the gather loop, whose four unrolled
+        //      batches each waited for a header and then for its network row: 61 % of the kernel's stall samples) ----
+        uint32_t my_id = 0, my_action = 0;
         float my_v = 0.0f;
+        uint32_t my_occ[3] = {0u, 0u, 0u};
         if (lane < m) {
             my_id = a.req_node[row0 + lane];
             if (mode == kApplySearch) my_v = -a.V[row0 + lane];  // :229 value from the opponent's perspective
+            const NodeHdr h = load_hdr(node_ptr(tn, my_id));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) my_occ[k] = h.black[k] | h.white[k];
+            my_action = h.action;
+            meta[lane][0] = my_id;
+            meta[lane][1] = h.parent | (h.action << 16);
+            meta[lane][2] = h.legal | (h.turn << 8) | (1u << 16);  // header word 10 with has_policy set
+            meta[lane][3] = __float_as_uint(my_v);
         }
-        // ---- (B) gather + mask (:232-239) ----
-#pragma unroll 4
+        // ---- (B) gather + mask (:232-239): the rows' loads do not depend on the headers ----
+#pragma unroll 8
         for (int i = 0; i < m; ++i) {
-            const uint32_t id = __shfl_sync(kFull, my_id, i);
-            const NodeHdr h = load_hdr(node_ptr(tn, id));
             const float *Prow = a.P + (size_t)(row0 + i) * kRow;
+            float pv[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int c = lane + 32 * j;
+                pv[j] = c < kCells ? Prow[c] : 0.0f;
+            }
+            const uint32_t o0 = __shfl_sync(kFull, my_occ[0], i), o1 = __shfl_sync(kFull, my_occ[1], i), o2 = __shfl_sync(kFull, my_occ[2], i);
+            const int act_i = (int)__shfl_sync(kFull, my_action, i);
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int c = lane + 32 * j;
                 if (c < kCells) {
-                    float v = Prow[c];
+                    float v = pv[j];
                     if (mode == kApplySearch) {  // mask by the node's own board
-                        const uint32_t occ = sel3(h.black[0] | h.white[0], h.black[1] | h.white[1], h.black[2] | h.white[2], c >> 5);
+                        const uint32_t occ = sel3(o0, o1, o2, j);
                         if ((occ >> (c & 31)) & 1u) v = 0.0f;
                     } else if (mode == kApplyEnsure) {  // agent.rs:165-171: the action, then the ROOT's occupancy
-                        const uint32_t occ = sel3(root_occ[0], root_occ[1], root_occ[2], c >> 5);
-                        if (c == (int)h.action || ((occ >> (c & 31)) & 1u)) v = 0.0f;
+                        const uint32_t occ = sel3(root_occ[0], root_occ[1], root_occ[2], j);
+                        if (c == act_i || ((occ >> (c & 31)) & 1u)) v = 0.0f;
                     }
                     sp[i][c] = v;
                 }
-            }
-            if (lane == i) {
-                meta[i][0] = id;
-                meta[i][1] = h.parent | (h.action << 16);
-                meta[i][2] = h.legal | (h.turn << 8) | (1u << 16);  // header word 10 with has_policy set
-                meta[i][3] = __float_as_uint(my_v);
             }
         }
         __syncwarp();

@@ -16,7 +16,14 @@ txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 rows = list(csv.reader(io.StringIO(txt)))
 hdr_i = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)
 print(rows[0][1][:120] if rows and len(rows[0]) > 1 else "")
-h, data = rows[hdr_i], [r for r in rows[hdr_i + 1:] if len(r) > 5]
+h = rows[hdr_i]
+data = []
+for r in rows[hdr_i + 1:]:  # the first matching launch only (a report with several launches repeats the header block)
+    if len(r) <= 5:
+        continue
+    if not r[0].startswith("0x"):
+        break
+    data.append(r)
 iS, iE, iN = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
 warps = int(data[0][iE])  # the first instruction is executed once by every warp
 tot = sum(int(r[iE]) for r in data)
