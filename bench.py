@@ -389,8 +389,9 @@ def main():
         roof_tree = {"bound": "hbm", "kernel": "k_select_expand + k_apply (warp per tree; 1024 searching trees per launch)",
                      "achieved": tree_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tree_gbs / peaks["hbm_gbs"],
                      "note": "algorithmic 1672 B/simulation; at this pool size the kernels are bound by the latency of one serial "
-                             "chain per tree (ncu: 42 % fixed-latency waits), at 65 536 trees by issue slots (78 %) with 5 % DRAM "
-                             "traffic because a round's re-reads of the root rows are L1 hits (DESIGN.md 3, profiles/r02_tree_pool_sweep.json); the PUCT descent is reused inside a round and the expansions at a leaf run lane-parallel; "
+                             "chain per tree, at 65 536 trees k_select_expand by issue slots (66 %) and k_apply by memory (36 % of DRAM "
+                             "throughput by ncu, 43 % of HBM by this byte model: DESIGN.md 3, profiles/r02_tree_pool_sweep.json); the PUCT "
+                             "descent is reused inside a round and the expansions at a leaf run lane-parallel; "
                              "hidden behind the other search lane's fc0 in the timed region",
                      # one k_select_expand + one k_apply launch at 1024 searching trees (ncu capture with the hash evaluator)
                      "traffic": (traffic.get("k_select_expand", 0.0) + traffic.get("k_apply", 0.0)) or None}
