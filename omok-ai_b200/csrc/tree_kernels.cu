@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_expand(TreeArgs 
         // store).  The run is cut behind the first terminal child: its reward is backed up at once (:177-181) and changes
         // the statistics, so the draws made for the simulations behind it are handed back (the stream position recorded
         // with expansion k is restored) and the walk restarts at the root -- the same children, ids, stream position and
-        // statistics as one simulation at a time (every oracle test).  Virtual loss changes the path after each expansion:
+        // statistics as one simulation at a time (every parity test).  Virtual loss changes the path after each expansion:
         // runs of one.
         const int K = a.vloss ? 1 : min(min(batch - it, ncand), 32);
         int my_action = 0;
