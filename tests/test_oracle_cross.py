@@ -104,6 +104,51 @@ def test_edge_semantics_agree(orc):
     assert_same_tree(p, c, "search from a root with an illegal child")
 
 
+def _scripted(moves, orc, seed):
+    """Both restatements' agent pairs after a scripted opening (ensure_action_exists + play_action, as the trainer feeds the
+    opponent's moves in: src/trainer.rs:147-167)."""
+    ev = orc.NativeHashEvaluator()
+    c_pair = [orc.Agent(ev, seed, 0), orc.Agent(ev, seed, 1)]
+    py_pair = [pyref.Agent(pyref.hash_evaluate_p, seed, 0), pyref.Agent(pyref.hash_evaluate_p, seed, 1)]
+    for mv in moves:
+        for c, p in zip(c_pair, py_pair):
+            c.ensure_action_exists(mv, ev)
+            p.ensure_action_exists(mv, pyref.hash_evaluate_p)
+            assert p.play_action(mv) == c.play_action(mv) == 0
+    return ev, c_pair, py_pair
+
+
+@pytest.mark.parametrize("which,keep", [("draw", 66), ("draw", 75), ("win81", 70), ("win81", 77)])
+def test_late_game_search_agrees_with_the_c_oracle(orc, which, keep):
+    """Late positions, where terminal children (backed up at once, parallel_mcts_executor.rs:177-181), terminal leaves
+    (:92-97), nodes that fill up after a handful of expansions and roots with fewer empty cells than a round has
+    simulations are the rule: the boards of the reference-derived draw / win-on-move-81 constructions (test_oracle_env.py)
+    up to `keep` stones, then searched and played to the end by both restatements, compared after every step."""
+    from test_oracle_env import draw_moves, win81_moves
+
+    moves = (draw_moves() if which == "draw" else win81_moves())[:keep]
+    ev, c_pair, py_pair = _scripted(moves, orc, 11)
+    count, batch, eps, alpha = 48, 16, 0.25, 0.3
+    ply, status = keep, 0
+    while status == 0 and ply < 81:
+        m, o = ply % 2, 1 - ply % 2
+        orc.execute([c_pair[m]], count, batch, eps, alpha, ev)
+        pyref.execute([py_pair[m]], count, batch, eps, alpha, pyref.hash_evaluate_pv)
+        assert_same_tree(py_pair[m], c_pair[m], f"{which}/{keep} ply {ply} searched")
+        ca, cpol = c_pair[m].sample_action(0)
+        pa, ppol = py_pair[m].sample_action(None)
+        assert pa == ca and bits(ppol) == cpol.tobytes(), f"ply {ply}: action / visit policy"
+        status = c_pair[m].play_action(ca)
+        assert py_pair[m].play_action(pa) == status
+        c_pair[o].ensure_action_exists(ca, ev)
+        py_pair[o].ensure_action_exists(pa, pyref.hash_evaluate_p)
+        assert py_pair[o].play_action(pa) == c_pair[o].play_action(ca)
+        assert_same_tree(py_pair[m], c_pair[m], f"ply {ply} mover re-rooted")
+        assert_same_tree(py_pair[o], c_pair[o], f"ply {ply} other re-rooted")
+        ply += 1
+    assert status != 0, "the game must end on a board with at most fifteen empty cells"
+
+
 def test_environment_agrees_on_random_playouts(orc):
     rng = np.random.default_rng(0)
     for game in range(30):

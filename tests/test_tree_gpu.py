@@ -89,6 +89,73 @@ def test_full_self_play_games_match_oracle(ctx, omk, orc):
     assert not live or ply == 81
 
 
+@pytest.mark.parametrize("batch", [16, 32])
+def test_late_game_positions_match_oracle(ctx, omk, orc, batch):
+    """Late positions -- the reference-derived draw / win-on-move-81 boards (tests/test_oracle_env.py) up to 66..77 stones --
+    where terminal children (backed up at once, parallel_mcts_executor.rs:177-181), terminal leaves (:92-97), nodes that fill
+    after a handful of expansions and roots with fewer empty cells than a round has simulations are the rule (the regime in
+    which a run of lane-parallel expansions is cut behind a terminal child and its draws are handed back): fed in move by
+    move through ensure_action_exists + play_action, then searched and played to the end, compared after every step."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_oracle_env import draw_moves, win81_moves
+
+    openings = [draw_moves()[:66], draw_moves()[:75], win81_moves()[:70], win81_moves()[:77]]
+    G = len(openings)
+    ev = orc.NativeHashEvaluator()
+    black = [orc.Agent(ev, ctx.seed, 2 * g) for g in range(G)]
+    white = [orc.Agent(ev, ctx.seed, 2 * g + 1) for g in range(G)]
+    ctx.pool_new_games(n=2 * G, evaluator=omk.EVAL_HASH)  # stream == tree id
+    for k in range(max(len(o) for o in openings)):
+        games = [g for g in range(G) if k < len(openings[g])]
+        ids = [2 * g for g in games] + [2 * g + 1 for g in games]
+        acts = [openings[g][k] for g in games] * 2
+        ctx.pool_ensure_action(acts, ids=ids, evaluator=omk.EVAL_HASH)
+        st = ctx.pool_play(acts, ids=ids)
+        assert not np.any(st), f"opening move {k}"
+        for g in games:
+            for agent in (black[g], white[g]):
+                agent.ensure_action_exists(openings[g][k], ev)
+                assert agent.play_action(openings[g][k]) == 0
+    for g in range(G):
+        assert_tree_equal(ctx, 2 * g, black[g], f"game {g} opening, black")
+        assert_tree_equal(ctx, 2 * g + 1, white[g], f"game {g} opening, white")
+    ply = [len(o) for o in openings]
+    live = list(range(G))
+    for _ in range(16):
+        if not live:
+            break
+        movers = [black[g] if ply[g] % 2 == 0 else white[g] for g in live]
+        others = [white[g] if ply[g] % 2 == 0 else black[g] for g in live]
+        mids = [2 * g + (ply[g] % 2) for g in live]
+        oids = [2 * g + 1 - (ply[g] % 2) for g in live]
+        orc.execute(movers, 48, batch, 0.25, 0.3, ev)
+        ctx.pool_search(ids=mids, count=48, batch_size=batch, epsilon=0.25, alpha=0.3, evaluator=omk.EVAL_HASH)
+        for g, mid, m in zip(live, mids, movers):
+            assert_tree_equal(ctx, mid, m, f"game {g} ply {ply[g]} searched")
+        acts, pol = ctx.pool_sample(ids=mids, modes=[0] * len(live), temperatures=[1.0] * len(live))
+        ref = [m.sample_action(0, 1.0) for m in movers]
+        assert [int(a) for a in acts] == [r[0] for r in ref]
+        assert np.stack([r[1] for r in ref]).tobytes() == pol.tobytes()
+        st = ctx.pool_play(acts, ids=mids)
+        assert [int(x) for x in st] == [m.play_action(int(a)) for m, a in zip(movers, acts)]
+        ctx.pool_ensure_action(acts, ids=oids, evaluator=omk.EVAL_HASH)
+        for o, a in zip(others, acts):
+            o.ensure_action_exists(int(a), ev)
+        st2 = ctx.pool_play(acts, ids=oids)
+        rst2 = [o.play_action(int(a)) for o, a in zip(others, acts)]
+        assert [int(x) for x in st2] == [(-1 if r is None else r) for r in rst2]
+        for g, mid, oid, m, o in zip(live, mids, oids, movers, others):
+            assert_tree_equal(ctx, mid, m, f"game {g} ply {ply[g]} mover re-rooted")
+            assert_tree_equal(ctx, oid, o, f"game {g} ply {ply[g]} other re-rooted")
+        for g in live:
+            ply[g] += 1
+        live = [g for g, x in zip(live, st) if x == 0]
+    assert not live, "every game must end on a board with at most fifteen empty cells"
+
+
 def test_play_edge_cases(ctx, omk):
     ctx.pool_new_games(ids=[200], evaluator=omk.EVAL_HASH)
     assert ctx.pool_play([5], ids=[200])[0] == -1  # action not in the tree
