@@ -264,8 +264,9 @@ static int32_t weights_changed(omk_ctx *c);
 // before any search lane forks, by every entry point that is about to evaluate the network.
 static int32_t ensure_packed(omk_ctx *c) {
     if (!c->net_pack_dirty) return OMK_OK;
-    c->net_pack_dirty = false;
-    return weights_changed(c);
+    const int32_t rc = weights_changed(c);
+    if (rc == OMK_OK) c->net_pack_dirty = false;  // a failed rebuild is retried (and reported again) by the next evaluation
+    return rc;
 }
 
 static int32_t check_evaluator(omk_ctx *c, int evaluator) {
