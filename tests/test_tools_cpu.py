@@ -1,0 +1,50 @@
+"""The profile-reading tools keep working on the committed evidence (no GPU, no ncu binary needed for the launch list)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_ncu_launch_shares_on_the_committed_launch_list():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_launch_shares.py"),
+                          os.path.join(ROOT, "profiles", "r02_ncu_launches.csv")], capture_output=True, text=True, check=True).stdout
+    head = out.splitlines()[0]
+    assert re.match(r"\d+ launches, [\d.]+ ms of serialised kernel time", head), head
+    shares = {}
+    for line in out.splitlines()[1:]:
+        m = re.search(r"([\d.]+) %", line)
+        if m:
+            shares[line[:48].strip()] = float(m.group(1))
+    assert abs(sum(shares.values()) - 100.0) < 1.0
+    # the two network kernels are the step (tower ~47 %, fc0 ~35 %)
+    tower = next(v for k, v in shares.items() if k.startswith("k_tower16"))
+    fc0 = next(v for k, v in shares.items() if k.startswith("k_fc16<10368, 9, 1"))
+    assert 40.0 < tower < 55.0 and 28.0 < fc0 < 42.0, (tower, fc0)
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    for name in ("r02_bench_final_1gpu.json", "r02_bench_final_2gpu.json", "r02_bench_final_4gpu.json", "r02_bench_final_8gpu.json"):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+                    "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert key in d, (name, key)
+        assert d["metric"] == "mcts_simulations_per_sec" and d["scaling"] == "weak" and d["gpu_launches"] > 0
+        r = d["roofline"]
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["bound"] in ("tensor", "hbm")
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    one = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_final_1gpu.json")))
+    assert one["cpu_baseline"]["kind"] == "port" and one["cpu_baseline"]["cores"] >= 1
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_final_reference_arm.json")))
+    assert ref["impl"] == "reference" and ref["steps"] == 5 and ref["warmup"] == 3
+    assert one["value"] / ref["value"] > 100  # the GPU path against the CPU port on the same box
+
+
+def test_tree_sweep_reaches_the_documented_fraction():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_tree_pool_sweep.json")))
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6451.8}
+    last = d["tree_sweep"][-1]
+    assert last["trees"] == 65536 and last["bytes_per_sim"] == 1672
+    assert last["algorithmic_GBs"] / peaks["hbm_gbs"] > 0.40  # 43 % of the measured HBM bandwidth
