@@ -44,7 +44,7 @@ def test_committed_bench_lines_carry_the_contract_keys():
 
 def test_tree_sweep_reaches_the_documented_fraction():
     d = json.load(open(os.path.join(ROOT, "profiles", "r02_tree_pool_sweep.json")))
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6451.8}
+    peaks = {"hbm_gbs": 6451.8}  # the measured copy bandwidth the documents quote (MEASURED_PEAKS.json of this round's pod)
     last = d["tree_sweep"][-1]
     assert last["trees"] == 65536 and last["bytes_per_sim"] == 1672
     assert last["algorithmic_GBs"] / peaks["hbm_gbs"] > 0.40  # 43 % of the measured HBM bandwidth
